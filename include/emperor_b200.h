@@ -1,0 +1,228 @@
+/*
+ * emperor_b200.h — C-ABI of the B200-native EMPEROR hot path.
+ *
+ * The reference (ReddTea/astroemperor 0.9.10) is pure Python: its hot path is
+ * the *generated* functions my_model / my_likelihood / my_prior that
+ * reddemcee.PTSampler calls once per walker per step.  There is
+ * no FFI in the reference; the entry points below are what a ctypes binding for
+ * that path binds (INTEGRATION.md shows the stub).  Each entry cites the
+ * reference interface it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - every function returns 0 on success or a negative EMP_E* code; the text of
+ *     the last error of the calling thread is available from emp_last_error().
+ *   - "dev" pointers are CUDA device pointers on the handle's device, "host"
+ *     pointers are ordinary host memory.  All arrays are C-contiguous FP64 unless
+ *     stated.
+ *   - a handle owns one CUDA stream; calls on one handle are not re-entrant,
+ *     different handles may be used from different threads.
+ *   - there is NO CPU fallback: if no CUDA device is usable emp_create fails.
+ */
+#ifndef EMPEROR_B200_H
+#define EMPEROR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMP_ABI_VERSION 3
+
+#define EMP_MAX_KEP 10   /* Keplerian blocks                                  */
+#define EMP_MAX_INS 16   /* instruments (offset / jitter entries)             */
+#define EMP_MAX_DIM 128  /* length of the full parameter vector (free+fixed)  */
+#define EMP_MAX_ACC 4    /* polynomial acceleration order                     */
+#define EMP_MAX_MA 4     /* moving-average order                              */
+#define EMP_MAX_PRIOR_OPS (2 * EMP_MAX_DIM + 2 * EMP_MAX_KEP + 8)
+
+/* error codes */
+#define EMP_OK 0
+#define EMP_EINVAL (-1)   /* bad argument / unsupported descriptor            */
+#define EMP_ECUDA (-2)    /* CUDA runtime error (see emp_last_error)          */
+#define EMP_ENODEV (-3)   /* no usable sm_100 device                          */
+#define EMP_ENOMEM (-4)
+#define EMP_EUNSUPPORTED (-5) /* feature exists in the reference but not here */
+
+/* Keplerian templates: support/models/kep0{0,1,2,3,4,6,7}.model, akep00.model */
+enum EmpKepModel {
+  EMP_KEP00 = 0, /* per, A, phase, ecc, w        ; ((1+e)/(1-e))**0.5          */
+  EMP_KEP01 = 1, /* per, A, phase, S, C          ; ecc<1e-6 -> w=0             */
+  EMP_KEP02 = 2, /* lnP, As, Ac, S, C            ; ecc<1e-5 -> w=0             */
+  EMP_KEP03 = 3, /* per, A, tp, ecc, w           ; M = freq*(t-tp)             */
+  EMP_KEP04 = 4, /* per, A, tp, S, C             ; ecc<1e-5                    */
+  EMP_AKEP00 = 5,/* per, A, pha, ecc, w, I, Om   ; RV part ignores I, Om       */
+  EMP_KEP06 = 6, /* lnP, A, phase, ecc, w                                      */
+  EMP_KEP07 = 7  /* lnP, A, phase, S, C          ; ecc<1e-6                    */
+};
+
+/* support/priors/{Uniform,Normal,Jeffreys,Isotropic,Fixed}.prior */
+enum EmpPriorKind {
+  EMP_PRIOR_UNIFORM = 0,   /* a0 = logZ                                        */
+  EMP_PRIOR_NORMAL = 1,    /* a0 = mu, a1 = s, a2 = logZ, a3 = log(s*sqrt(2pi))*/
+  EMP_PRIOR_JEFFREYS = 2,  /* implemented as uniform in the reference; a0=logZ */
+  EMP_PRIOR_ISOTROPIC = 3, /* log(0.5 sin x) - a0                              */
+  EMP_PRIOR_FIXED = 4      /* contributes 0                                    */
+};
+
+/* my_prior is a straight-line program (emp.py:182-254); one op per line. */
+enum EmpPriorOpKind {
+  EMP_POP_PARAM = 0,  /* lp += Prior(theta_full[i0])                           */
+  EMP_POP_CHECK = 1,  /* if lp == -inf: return lp   (end of each block)        */
+  EMP_POP_SUMSQ = 2   /* x = theta_full[i0]**2 + theta_full[i1]**2; lp += Prior(x) */
+};
+
+typedef struct EmpPriorOp {
+  int32_t op;    /* EmpPriorOpKind */
+  int32_t prior; /* EmpPriorKind   */
+  int32_t i0, i1;
+  double lo, hi;
+  double a0, a1, a2, a3;
+} EmpPriorOp;
+
+/* moving-average handling */
+enum EmpMaMode {
+  EMP_MA_NONE = 0,
+  EMP_MA_REFERENCE_NOOP = 1, /* support/models/moav00.model: parameters only enter the prior */
+  EMP_MA_GLOBAL = 2          /* support/models/moav01.model: recurrence over all points      */
+};
+
+/*
+ * Model descriptor: what emp_model.py:706-781 (_write_model_RV) and
+ * emp.py:182-254 (_write_prior_reddemcee) bake into the generated script.
+ * All *_off fields index the FULL theta (after the fixed parameters were
+ * re-inserted, emp_model.py:709-711).
+ */
+typedef struct EmpModelDesc {
+  int32_t abi_version; /* = EMP_ABI_VERSION */
+  int32_t ndim_free;   /* sampler dimension (model.ndim__)                     */
+  int32_t ndim_full;   /* len(theta) after np.insert of the fixed values       */
+  int32_t n_kep;
+  int32_t kep_model[EMP_MAX_KEP]; /* EmpKepModel */
+  int32_t kep_off[EMP_MAX_KEP];
+  int32_t acc_order;   /* 0 = no AccelerationBlock (support/models/acc.model)  */
+  int32_t acc_off;
+  int32_t n_ins;       /* instruments; Flag values are 1..n_ins                */
+  int32_t offset_off;  /* support/models/offset00.model                        */
+  int32_t has_jitter;  /* support/models/jitter00.model                        */
+  int32_t jitter_off;
+  int32_t ma_mode;     /* EmpMaMode */
+  int32_t ma_order;
+  int32_t ma_off;
+  int32_t am_enabled;  /* Hipparcos-Gaia block (emp_model.py:1232-1672)        */
+  int32_t am_offset_off; /* AstrometryOffsetBlock: 5 params                    */
+  int32_t am_jitter_off; /* AstrometryJitterBlock: J_H, J_G                    */
+  int32_t n_prior_ops;
+  int32_t _pad0;
+  int32_t free_to_full[EMP_MAX_DIM]; /* full index of free parameter j         */
+  double full_init[EMP_MAX_DIM];     /* fixed values at their full index, 0 elsewhere */
+  EmpPriorOp prior_ops[EMP_MAX_PRIOR_OPS];
+} EmpModelDesc;
+
+/*
+ * Hipparcos-Gaia constants: the arrays emp_model.py:610-702 (_write_data_AM)
+ * loads into the generated script (qol_utils.py:305-446 computes them once on
+ * the host).  All pointers are HOST pointers; emp_create copies them.
+ */
+typedef struct EmpAmData {
+  int32_t n_hipp;      /* len(data_iad_hipp)                                   */
+  int32_t n_gost;      /* len(data_iad_gost) after filtering                   */
+  int32_t n_mask2;     /* sum(mask_GDR2)                                       */
+  int32_t n_mask3;     /* sum(mask_GDR3)                                       */
+  double common_t;     /* RV time origin                                       */
+  const double *time_hipp;   /* [n_hipp] BJD                                   */
+  const double *cpsi_hipp, *spsi_hipp, *epoch_hipp, *parf_hipp, *res_hipp, *sres_hipp; /* [n_hipp] */
+  const double *time_gost;   /* [n_gost] BJD                                   */
+  const double *cpsi_gost, *spsi_gost, *parf_gost; /* [n_gost]                 */
+  const int32_t *idx_mask2;  /* [n_mask2] indices into the gost arrays         */
+  const int32_t *idx_mask3;  /* [n_mask3]                                      */
+  const double *gsv2;        /* [5, n_mask2] AM_GSV['GDR2']                    */
+  const double *gsv3;        /* [5, n_mask3] AM_GSV['GDR3']                    */
+  const double *inv_cov;     /* [3,5,5] AM_inv_COV                             */
+  const double *log_det_cov; /* [3]                                            */
+  const double *astro_gost;  /* [2,5] AM_astro_gost.values (dra,ddec,plx,pmra,pmdec) */
+  const double *catalogs;    /* [3,7] ref_epoch, ra, dec, parallax, pmra, pmdec, rv */
+} EmpAmData;
+
+typedef struct EmpHandle EmpHandle;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+
+/* Replaces the data/constant section of the generated script
+ * (emp_model.py:406-433 _write_data_RV: X_, Y_, YERR_, mask{i}).
+ * t, y, yerr, flag: HOST arrays of n points in time order; flag in 1..n_ins.
+ * am: NULL unless desc->am_enabled. */
+int emp_create(const EmpModelDesc *desc, const double *t, const double *y, const double *yerr,
+               const int32_t *flag, int64_t n, const EmpAmData *am, int device, EmpHandle **out);
+int emp_destroy(EmpHandle *h);
+const char *emp_last_error(void);
+int emp_abi_version(void);
+/* The CUDA stream (cudaStream_t as void*) all work of this handle is queued on. */
+int emp_stream(EmpHandle *h, void **stream);
+int emp_synchronize(EmpHandle *h);
+
+/* ---- likelihood / prior -------------------------------------------------- */
+
+/* Batched my_likelihood + my_prior (support/likelihoods/00.like:3-5, a00.like:3-8,
+ * emp.py:190-254): for each of n_eval rows of theta_dev[n_eval, ndim_free] writes
+ * logl_dev[i] and logp_dev[i].  Rows whose prior is -inf get logl = -inf without
+ * evaluating the model (emcee semantics).  Asynchronous on the handle's stream. */
+int emp_logl_batch(EmpHandle *h, const double *theta_dev, int64_t n_eval, double *logl_dev,
+                   double *logp_dev);
+/* Same with host buffers: H2D copy, kernel, D2H copy, synchronises. */
+int emp_logl_batch_host(EmpHandle *h, const double *theta_host, int64_t n_eval, double *logl_host,
+                        double *logp_host);
+/* my_model(theta) for ONE theta (emp_model.py:706-781): model0[n], err20[n] to host.
+ * Used by the reference's post-processing (emp.py:1546-1558). */
+int emp_model_host(EmpHandle *h, const double *theta_host, double *model_host, double *err2_host);
+
+/* ---- parallel-tempering step -------------------------------------------- */
+
+/* One emcee RedBlue stretch-move step of every temperature held by this handle
+ * (reddemcee.PTSampler / emcee 3.1.6 StretchMove(a=2), SURVEY.md §3.3 and §8a
+ * row A15), from host-supplied draws that were already copied to the device:
+ *   p      [T, W, ndim]  walker positions (updated in place)
+ *   logl   [T, W], logp [T, W]  (updated in place)
+ *   betas  [T]
+ *   split  [T, W] int32   0/1: which half a walker is in (shuffled arange(W) % 2)
+ *   zz     [T, W]         stretch factor of the walker, ((a-1)u+1)^2/a
+ *   rint   [T, W] int32   index of the partner inside the complementary half
+ *   lnu    [T, W]         log of the accept uniform
+ *   accepted [T, W] uint8 (output; 1 where the proposal was accepted)
+ * Both halves are processed (half 0 then half 1, emcee order). */
+int emp_pt_stretch_step(EmpHandle *h, int32_t T, int32_t W, double *p, double *logl, double *logp,
+                        const double *betas, const int32_t *split, const double *zz,
+                        const int32_t *rint, const double *lnu, uint8_t *accepted);
+
+/* Adjacent-temperature swap sweep, hot -> cold (ptemcee lineage).
+ *   logl_all [T, W]   log-likelihood of every temperature (read only)
+ *   betas    [T]
+ *   perm     [T-1, 2, W] int32  pair j couples temperature i=j+1 with i-1=j:
+ *                               perm[j,0,:] indexes walkers of i, perm[j,1,:] of i-1
+ *   lnu      [T-1, W]
+ * Outputs:
+ *   src      [T, W] int32  flat index (t*W + w) of the walker that ends up in slot (t, w)
+ *   n_acc    [T-1] int32   accepted swaps per pair
+ * Every rank of a sharded ladder replays this identically from the all-gathered logl. */
+int emp_pt_swap_plan(EmpHandle *h, int32_t T, int32_t W, const double *logl_all,
+                     const double *betas, const int32_t *perm, const double *lnu, int32_t *src,
+                     int32_t *n_acc);
+/* Apply a swap plan to local state: rows t0..t0+T_loc-1 of the ladder.
+ * dst[t,w,:] = src_rows[src[t0+t, w]] for p, logl, logp (out-of-place). */
+int emp_pt_apply_plan(EmpHandle *h, int32_t T_loc, int32_t W, int32_t t0, const int32_t *src,
+                      const double *p_in, const double *logl_in, const double *logp_in,
+                      double *p_out, double *logl_out, double *logp_out);
+
+/* ---- introspection -------------------------------------------------------- */
+/* Number of kernels this handle has launched since creation (bench.py gpu_launches). */
+int emp_launch_count(EmpHandle *h, int64_t *count);
+/* Time in ms of the last emp_logl_batch kernel (CUDA events on the handle's stream);
+ * only valid after emp_synchronize.  Enabled by emp_set_timing(h, 1). */
+int emp_set_timing(EmpHandle *h, int enable);
+int emp_last_logl_ms(EmpHandle *h, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMPEROR_B200_H */
