@@ -1,0 +1,433 @@
+// emp_abi.cu — C-ABI of the B200-native EMPEROR hot path (include/emperor_b200.h).
+// Host side: handle lifetime, data packing/upload, kernel launches.  No CPU fallback.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/emperor_b200.h"
+#include "emp_device.cuh"
+#include "emp_logl.cuh"
+#include "emp_pt.cuh"
+#include "emp_am.cuh"
+
+using namespace emp;
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return fail(EMP_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));           \
+  } while (0)
+
+struct EmpHandle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool owns_stream = false;
+  EmpModelDesc desc;
+  EmpModelDesc* d_desc = nullptr;
+  int64_t n = 0;
+  int32_t n_tiles = 0;
+  char* d_tiles = nullptr;
+  double *d_t = nullptr, *d_y = nullptr, *d_e2 = nullptr;
+  int32_t* d_ins = nullptr;
+  double t0 = 0.0;
+  double ll_const = 0.0;
+  // scratch for the host-buffer entry points and the PT step
+  double *d_theta = nullptr, *d_ll = nullptr, *d_lp = nullptr;
+  int64_t cap_eval = 0;
+  double *d_q = nullptr, *d_llq = nullptr, *d_lpq = nullptr;
+  int64_t cap_q = 0;
+  double* d_llwork = nullptr;
+  int64_t cap_llwork = 0;
+  uint32_t* d_nan = nullptr;
+  AmDevice am;
+  int num_sms = 148;
+  int64_t launches = 0;
+  bool timing = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+extern "C" const char* emp_last_error(void) { return g_last_error.c_str(); }
+extern "C" int emp_abi_version(void) { return EMP_ABI_VERSION; }
+
+static int validate_desc(const EmpModelDesc* d) {
+  if (!d) return fail(EMP_EINVAL, "desc is NULL");
+  if (d->abi_version != EMP_ABI_VERSION)
+    return fail(EMP_EINVAL, "descriptor abi_version " + std::to_string(d->abi_version) + " != library " +
+                                std::to_string(EMP_ABI_VERSION));
+  if (d->ndim_full < 1 || d->ndim_full > EMP_MAX_DIM || d->ndim_free < 1 || d->ndim_free > d->ndim_full)
+    return fail(EMP_EINVAL, "bad ndim");
+  if (d->n_kep < 0 || d->n_kep > EMP_MAX_KEP) return fail(EMP_EINVAL, "bad n_kep");
+  if (d->n_ins < 1 || d->n_ins > EMP_MAX_INS) return fail(EMP_EINVAL, "bad n_ins");
+  if (d->acc_order < 0 || d->acc_order > EMP_MAX_ACC) return fail(EMP_EINVAL, "bad acc_order");
+  if (d->ma_order < 0 || d->ma_order > EMP_MAX_MA) return fail(EMP_EINVAL, "bad ma_order");
+  if (d->ma_mode < EMP_MA_NONE || d->ma_mode > EMP_MA_GLOBAL) return fail(EMP_EINVAL, "bad ma_mode");
+  if (d->n_prior_ops < 0 || d->n_prior_ops > EMP_MAX_PRIOR_OPS) return fail(EMP_EINVAL, "bad n_prior_ops");
+  for (int k = 0; k < d->n_kep; ++k) {
+    int m = d->kep_model[k];
+    if (m < 0 || m > 7) return fail(EMP_EINVAL, "bad kep_model");
+    int np = (m == EMP_AKEP00) ? 7 : 5;
+    if (d->kep_off[k] < 0 || d->kep_off[k] + np > d->ndim_full) return fail(EMP_EINVAL, "bad kep_off");
+  }
+  if (d->offset_off < 0 || d->offset_off + d->n_ins > d->ndim_full) return fail(EMP_EINVAL, "bad offset_off");
+  if (d->has_jitter && (d->jitter_off < 0 || d->jitter_off + d->n_ins > d->ndim_full))
+    return fail(EMP_EINVAL, "bad jitter_off");
+  for (int j = 0; j < d->ndim_free; ++j)
+    if (d->free_to_full[j] < 0 || d->free_to_full[j] >= d->ndim_full) return fail(EMP_EINVAL, "bad free_to_full");
+  for (int i = 0; i < d->n_prior_ops; ++i) {
+    const EmpPriorOp& o = d->prior_ops[i];
+    if (o.op < EMP_POP_PARAM || o.op > EMP_POP_SUMSQ) return fail(EMP_EINVAL, "bad prior op");
+    if (o.op != EMP_POP_CHECK) {
+      if (o.prior < EMP_PRIOR_UNIFORM || o.prior > EMP_PRIOR_FIXED)
+        return fail(EMP_EUNSUPPORTED, "prior kind not implemented on the device path");
+      if (o.i0 < 0 || o.i0 >= d->ndim_full || o.i1 < 0 || o.i1 >= d->ndim_full)
+        return fail(EMP_EINVAL, "bad prior index");
+    }
+  }
+  return EMP_OK;
+}
+
+extern "C" int emp_create(const EmpModelDesc* desc, const double* t, const double* y, const double* yerr,
+                          const int32_t* flag, int64_t n, const EmpAmData* am, int device, EmpHandle** out) {
+  if (!out) return fail(EMP_EINVAL, "out is NULL");
+  *out = nullptr;
+  int rc = validate_desc(desc);
+  if (rc) return rc;
+  if (!t || !y || !yerr || !flag || n < 1) return fail(EMP_EINVAL, "bad data arrays");
+  if (desc->am_enabled && !am) return fail(EMP_EINVAL, "am_enabled but am data is NULL");
+  for (int64_t i = 0; i < n; ++i)
+    if (flag[i] < 1 || flag[i] > desc->n_ins) return fail(EMP_EINVAL, "flag out of 1..n_ins");
+
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(EMP_ENODEV, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                " (there is no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(EMP_EINVAL, "device index out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(EMP_ENODEV, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                                std::to_string(prop.minor) + "; this library is built for sm_100a only");
+
+  EmpHandle* h = new (std::nothrow) EmpHandle();
+  if (!h) return fail(EMP_ENOMEM, "host allocation failed");
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  h->desc = *desc;
+  h->n = n;
+  h->n_tiles = int32_t((n + kTilePoints - 1) / kTilePoints);
+  h->t0 = t[0];
+  h->ll_const = -0.5 * log(2.0 * M_PI) * double(n);  // 00.like:1
+
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->owns_stream = true;
+  CUDA_TRY(cudaEventCreate(&h->ev0));
+  CUDA_TRY(cudaEventCreate(&h->ev1));
+
+  // pack tiles: [t | y | yerr^2 | ins] per tile; padding replicates the last timestamp
+  std::vector<char> packed(size_t(h->n_tiles) * kTileBytes);
+  std::vector<double> e2(n);
+  std::vector<int32_t> ins(n);
+  for (int64_t i = 0; i < n; ++i) {
+    e2[i] = yerr[i] * yerr[i];  // err20 = YERR_ ** 2 (emp_model.py:714)
+    ins[i] = flag[i] - 1;
+  }
+  for (int32_t tix = 0; tix < h->n_tiles; ++tix) {
+    char* base = packed.data() + size_t(tix) * kTileBytes;
+    double* pt = reinterpret_cast<double*>(base);
+    double* py = pt + kTilePoints;
+    double* pe = py + kTilePoints;
+    int32_t* pi = reinterpret_cast<int32_t*>(pe + kTilePoints);
+    for (int j = 0; j < kTilePoints; ++j) {
+      int64_t i = int64_t(tix) * kTilePoints + j;
+      bool ok = i < n;
+      pt[j] = ok ? t[i] : t[n - 1];
+      py[j] = ok ? y[i] : 0.0;
+      pe[j] = ok ? e2[i] : 1.0;
+      pi[j] = ok ? ins[i] : 0;
+    }
+  }
+  CUDA_TRY(cudaMalloc(&h->d_tiles, packed.size()));
+  CUDA_TRY(cudaMemcpy(h->d_tiles, packed.data(), packed.size(), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&h->d_t, n * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->d_y, n * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->d_e2, n * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->d_ins, n * sizeof(int32_t)));
+  CUDA_TRY(cudaMemcpy(h->d_t, t, n * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(h->d_y, y, n * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(h->d_e2, e2.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(h->d_ins, ins.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&h->d_desc, sizeof(EmpModelDesc)));
+  CUDA_TRY(cudaMemcpy(h->d_desc, desc, sizeof(EmpModelDesc), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&h->d_nan, sizeof(uint32_t)));
+  CUDA_TRY(cudaMemset(h->d_nan, 0, sizeof(uint32_t)));
+
+  CUDA_TRY(cudaFuncSetAttribute(logl_rv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                int(kLoglSmemBytes)));
+  if (desc->am_enabled) {
+    rc = am_upload(am, &h->am);
+    if (rc) {
+      std::string msg = g_last_error;
+      emp_destroy(h);
+      return fail(rc, msg);
+    }
+  }
+  *out = h;
+  return EMP_OK;
+}
+
+extern "C" int emp_destroy(EmpHandle* h) {
+  if (!h) return EMP_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->d_tiles); cudaFree(h->d_t); cudaFree(h->d_y); cudaFree(h->d_e2); cudaFree(h->d_ins);
+  cudaFree(h->d_desc); cudaFree(h->d_theta); cudaFree(h->d_ll); cudaFree(h->d_lp);
+  cudaFree(h->d_q); cudaFree(h->d_llq); cudaFree(h->d_lpq); cudaFree(h->d_llwork); cudaFree(h->d_nan);
+  am_free(&h->am);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->owns_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return EMP_OK;
+}
+
+extern "C" int emp_stream(EmpHandle* h, void** stream) {
+  if (!h || !stream) return fail(EMP_EINVAL, "NULL argument");
+  *stream = (void*)h->stream;
+  return EMP_OK;
+}
+
+extern "C" int emp_set_stream(EmpHandle* h, void* stream) {
+  if (!h) return fail(EMP_EINVAL, "NULL handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (h->stream) CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (h->owns_stream && h->stream) CUDA_TRY(cudaStreamDestroy(h->stream));
+  h->stream = (cudaStream_t)stream;
+  h->owns_stream = false;
+  return EMP_OK;
+}
+
+extern "C" int emp_synchronize(EmpHandle* h) {
+  if (!h) return fail(EMP_EINVAL, "NULL handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return EMP_OK;
+}
+
+static int launch_logl(EmpHandle* h, const double* theta_dev, int64_t n_eval, double* logl_dev,
+                       double* logp_dev) {
+  if (n_eval == 0) return EMP_OK;
+  LoglParams P;
+  P.desc = h->d_desc;
+  P.tiles = h->d_tiles;
+  P.n_points = h->n;
+  P.n_tiles = h->n_tiles;
+  P.theta = theta_dev;
+  P.eval_index = nullptr;
+  P.n_eval = n_eval;
+  P.logl = logl_dev;
+  P.logp = logp_dev;
+  P.logp_in = nullptr;
+  P.t0 = h->t0;
+  P.ll_const = h->ll_const;
+  const int64_t grid = (n_eval + kWalkerWarps - 1) / kWalkerWarps;
+  if (grid > 2147483647LL) return fail(EMP_EINVAL, "n_eval too large for one launch");
+  if (h->timing) CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  logl_rv_kernel<<<dim3((unsigned)grid), dim3(kLoglThreads), kLoglSmemBytes, h->stream>>>(P);
+  if (h->timing) CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  h->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  if (h->desc.am_enabled) {
+    int rc = am_launch(&h->am, h->d_desc, theta_dev, n_eval, logl_dev, h->stream, &h->launches);
+    if (rc) return rc;
+  }
+  return EMP_OK;
+}
+
+extern "C" int emp_logl_batch(EmpHandle* h, const double* theta_dev, int64_t n_eval, double* logl_dev,
+                              double* logp_dev) {
+  if (!h || !theta_dev || !logl_dev || !logp_dev || n_eval < 0) return fail(EMP_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  return launch_logl(h, theta_dev, n_eval, logl_dev, logp_dev);
+}
+
+static int ensure_eval_scratch(EmpHandle* h, int64_t n_eval) {
+  if (n_eval <= h->cap_eval) return EMP_OK;
+  cudaFree(h->d_theta); cudaFree(h->d_ll); cudaFree(h->d_lp);
+  h->d_theta = h->d_ll = h->d_lp = nullptr;
+  h->cap_eval = 0;
+  CUDA_TRY(cudaMalloc(&h->d_theta, size_t(n_eval) * h->desc.ndim_free * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->d_ll, size_t(n_eval) * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->d_lp, size_t(n_eval) * sizeof(double)));
+  h->cap_eval = n_eval;
+  return EMP_OK;
+}
+
+extern "C" int emp_logl_batch_host(EmpHandle* h, const double* theta_host, int64_t n_eval, double* logl_host,
+                                   double* logp_host) {
+  if (!h || !theta_host || !logl_host || !logp_host || n_eval < 0) return fail(EMP_EINVAL, "bad argument");
+  if (n_eval == 0) return EMP_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  int rc = ensure_eval_scratch(h, n_eval);
+  if (rc) return rc;
+  const size_t nb = size_t(n_eval) * h->desc.ndim_free * sizeof(double);
+  CUDA_TRY(cudaMemcpyAsync(h->d_theta, theta_host, nb, cudaMemcpyHostToDevice, h->stream));
+  rc = launch_logl(h, h->d_theta, n_eval, h->d_ll, h->d_lp);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(logl_host, h->d_ll, n_eval * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(logp_host, h->d_lp, n_eval * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return EMP_OK;
+}
+
+extern "C" int emp_model_host(EmpHandle* h, const double* theta_host, double* model_host, double* err2_host) {
+  if (!h || !theta_host || !model_host || !err2_host) return fail(EMP_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  int rc = ensure_eval_scratch(h, 1);
+  if (rc) return rc;
+  double *d_model = nullptr, *d_err2 = nullptr;
+  CUDA_TRY(cudaMalloc(&d_model, h->n * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&d_err2, h->n * sizeof(double)));
+  CUDA_TRY(cudaMemcpyAsync(h->d_theta, theta_host, h->desc.ndim_free * sizeof(double), cudaMemcpyHostToDevice,
+                           h->stream));
+  int blocks = int((h->n + 255) / 256);
+  if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms;
+  model_rv_kernel<<<blocks, 256, 0, h->stream>>>(h->d_desc, h->d_theta, h->d_t, h->d_y, h->d_e2, h->d_ins, h->n,
+                                                 h->t0, d_model, d_err2);
+  h->launches += 1;
+  if (h->desc.ma_mode == EMP_MA_GLOBAL && h->desc.ma_order > 0) {
+    model_ma_kernel<<<1, 32, 0, h->stream>>>(h->d_desc, h->d_theta, h->d_t, h->d_y, h->n, d_model);
+    h->launches += 1;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(model_host, d_model, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(err2_host, d_err2, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_model);
+  cudaFree(d_err2);
+  if (e != cudaSuccess) return fail(EMP_ECUDA, cudaGetErrorString(e));
+  return EMP_OK;
+}
+
+// ---- parallel tempering ------------------------------------------------------------------
+
+static int ensure_q_scratch(EmpHandle* h, int64_t n_prop) {
+  if (n_prop <= h->cap_q) return EMP_OK;
+  cudaFree(h->d_q); cudaFree(h->d_llq); cudaFree(h->d_lpq);
+  h->d_q = h->d_llq = h->d_lpq = nullptr;
+  h->cap_q = 0;
+  CUDA_TRY(cudaMalloc(&h->d_q, size_t(n_prop) * h->desc.ndim_free * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->d_llq, size_t(n_prop) * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->d_lpq, size_t(n_prop) * sizeof(double)));
+  h->cap_q = n_prop;
+  return EMP_OK;
+}
+
+extern "C" int emp_pt_stretch_step(EmpHandle* h, int32_t T, int32_t W, double* p, double* logl, double* logp,
+                                   const double* betas, const int32_t* half_idx, const double* zz,
+                                   const int32_t* rint, const double* factors, const double* lnu,
+                                   uint8_t* accepted) {
+  if (!h || !p || !logl || !logp || !betas || !half_idx || !zz || !rint || !factors || !lnu || !accepted)
+    return fail(EMP_EINVAL, "NULL argument");
+  if (T < 1 || W < 2 || (W & 1)) return fail(EMP_EINVAL, "need T >= 1 and an even number of walkers");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int32_t ndim = h->desc.ndim_free;
+  const int32_t H = W / 2;
+  const int64_t n_prop = int64_t(T) * H;
+  int rc = ensure_q_scratch(h, n_prop);
+  if (rc) return rc;
+  const int threads = 256;
+  const int64_t max_blocks = int64_t(h->num_sms) * 8;
+  for (int split = 0; split < 2; ++split) {
+    int64_t total = n_prop * ndim;
+    int blocks = int(std::min<int64_t>((total + threads - 1) / threads, max_blocks));
+    pt_propose_kernel<<<blocks, threads, 0, h->stream>>>(p, T, W, ndim, split, half_idx, zz, rint, h->d_q);
+    h->launches += 1;
+    rc = launch_logl(h, h->d_q, n_prop, h->d_llq, h->d_lpq);
+    if (rc) return rc;
+    blocks = int(std::min<int64_t>((n_prop * 32 + threads - 1) / threads, max_blocks));
+    pt_accept_kernel<<<blocks, threads, 0, h->stream>>>(p, logl, logp, T, W, ndim, split, half_idx, betas, factors,
+                                                        lnu, h->d_q, h->d_llq, h->d_lpq, accepted, h->d_nan);
+    h->launches += 1;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return EMP_OK;
+}
+
+extern "C" int emp_pt_swap_plan(EmpHandle* h, int32_t T, int32_t W, const double* logl_all, const double* betas,
+                                const int32_t* perm, const double* lnu, int32_t* src, int32_t* n_acc) {
+  if (!h || !logl_all || !betas || !src || !n_acc) return fail(EMP_EINVAL, "NULL argument");
+  if (T < 1 || W < 1) return fail(EMP_EINVAL, "bad T/W");
+  if (T > 1 && (!perm || !lnu)) return fail(EMP_EINVAL, "NULL draws");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (2 * int64_t(W) > h->cap_llwork) {
+    cudaFree(h->d_llwork);
+    h->d_llwork = nullptr;
+    h->cap_llwork = 0;
+    CUDA_TRY(cudaMalloc(&h->d_llwork, 2 * size_t(W) * sizeof(double)));
+    h->cap_llwork = 2 * int64_t(W);
+  }
+  pt_swap_plan_kernel<<<1, 1024, 0, h->stream>>>(T, W, logl_all, betas, perm, lnu, src, n_acc, h->d_llwork);
+  h->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return EMP_OK;
+}
+
+extern "C" int emp_pt_gather_rows(EmpHandle* h, int64_t n_rows, int32_t ndim, const int32_t* src,
+                                  const double* p_in, const double* logl_in, const double* logp_in, double* p_out,
+                                  double* logl_out, double* logp_out) {
+  if (!h || !src || !p_in || !logl_in || !logp_in || !p_out || !logl_out || !logp_out)
+    return fail(EMP_EINVAL, "NULL argument");
+  if (n_rows == 0) return EMP_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int threads = 256;
+  int blocks = int(std::min<int64_t>((n_rows * 32 + threads - 1) / threads, int64_t(h->num_sms) * 8));
+  pt_gather_rows_kernel<<<blocks, threads, 0, h->stream>>>(n_rows, ndim, src, p_in, logl_in, logp_in, p_out,
+                                                           logl_out, logp_out);
+  h->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return EMP_OK;
+}
+
+extern "C" int emp_nan_count(EmpHandle* h, uint32_t* count) {
+  if (!h || !count) return fail(EMP_EINVAL, "NULL argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpyAsync(count, h->d_nan, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return EMP_OK;
+}
+
+// ---- introspection ---------------------------------------------------------------------------
+extern "C" int emp_launch_count(EmpHandle* h, int64_t* count) {
+  if (!h || !count) return fail(EMP_EINVAL, "NULL argument");
+  *count = h->launches;
+  return EMP_OK;
+}
+
+extern "C" int emp_set_timing(EmpHandle* h, int enable) {
+  if (!h) return fail(EMP_EINVAL, "NULL handle");
+  h->timing = enable != 0;
+  return EMP_OK;
+}
+
+extern "C" int emp_last_logl_ms(EmpHandle* h, float* ms) {
+  if (!h || !ms) return fail(EMP_EINVAL, "NULL argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaEventSynchronize(h->ev1));
+  CUDA_TRY(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return EMP_OK;
+}

@@ -1,0 +1,313 @@
+// emp_device.cuh — device-side building blocks of the EMPEROR hot path (sm_100a).
+//
+// What the reference computes per (walker, datapoint) — SURVEY.md §8a rows A3-A9:
+//   M = freq*t + phase ; E = kepler.solve(M, e) ; f = 2 atan(sqrt((1+e)/(1-e)) tan(E/2)) ;
+//   model += A (cos(f+w) + e cos w)                     support/models/kep00.model:4-8
+// Here (B200-first, FP64 CUDA cores, no tensor cores — this is not a contraction):
+//   * M is formed with the reference's two roundings and reduced mod 2pi EXACTLY
+//     (rint + one FMA), so the solver sees bit-identical input to NumPy's fmod path;
+//   * same Markley starter and same single high-order refinement as kepler.py
+//     (oracle/kepler_oracle.c), evaluated with FMAs;
+//   * sin E / (1 - cos E) of the refined E are obtained from the refinement's own
+//     series by a 4th-order rotation (|dE| <= 5e-4), and the RV term is evaluated as
+//       A (cos(f+w) + e cos w) = [a1 (1-e - (1-cos E)) + a2 sin E] / (1 - e cos E) + a3
+//     with a1 = A cos w, a2 = -A sin w sqrt(1-e^2), a3 = A e cos w per walker —
+//     algebraically identical to the tan/atan/cos chain, ~3x fewer FP64 instructions.
+#pragma once
+#include <stdint.h>
+#include "../../include/emperor_b200.h"
+
+namespace emp {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kTwoPi = 2.0 * 3.14159265358979323846;  // == np.float64(2*np.pi)
+constexpr double kPi2 = 1.57079632679489661923;
+constexpr double kPi4 = 0.78539816339744830962;
+constexpr double kInvTwoPi = 0.15915494309189533577;
+constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52: (x + kMagic) - kMagic == rint(x)
+// Markley (1995) constants, as in kepler.py
+constexpr double kF1 = 3.0 * kPi / (kPi - 6.0 / kPi);
+constexpr double kF2 = 1.6 / (kPi - 6.0 / kPi);
+
+// Per (walker, Keplerian) constants, computed once in the kernel prologue.
+struct KepConst {
+  double freq;    // 2 pi / per
+  double ph;      // phase, or t_p for kep03/kep04
+  double e;       // eccentricity
+  double ome;     // 1 - e
+  double c2;      // kF2 / (1 + e)
+  double ome3;    // 3 (1 - e)
+  double a1;      // A cos w
+  double a2;      // -A sin w sqrt(1 - e^2)
+  double a3;      // A e cos w
+  double use_tp;  // != 0: M = freq * (t - ph)
+};
+constexpr int kKepConstDoubles = sizeof(KepConst) / sizeof(double);
+
+// ---- parameter transforms: support/models/kep0{0,1,2,3,4,6,7}.model, akep00.model ----
+__device__ inline void kep_elements(int model, const double* th, double& per, double& A, double& ph,
+                                    double& e, double& w, bool& use_tp) {
+  use_tp = false;
+  double S = 0.0, C = 0.0, thr = 0.0;
+  bool sc = false;
+  switch (model) {
+    case EMP_KEP00:
+    case EMP_AKEP00:
+      per = th[0]; A = th[1]; ph = th[2]; e = th[3]; w = th[4];
+      break;
+    case EMP_KEP01:
+      per = th[0]; A = th[1]; ph = th[2]; S = th[3]; C = th[4]; sc = true; thr = 1e-6;
+      break;
+    case EMP_KEP02: {
+      per = exp(th[0]);
+      double As = th[1], Ac = th[2];
+      A = __dadd_rn(__dmul_rn(As, As), __dmul_rn(Ac, Ac));
+      S = th[3]; C = th[4]; sc = true; thr = 1e-5;
+      ph = acos(Ac / sqrt(A));
+      if (As < 0.0) ph = kTwoPi - ph;
+      break;
+    }
+    case EMP_KEP03:
+      per = th[0]; A = th[1]; ph = th[2]; e = th[3]; w = th[4]; use_tp = true;
+      break;
+    case EMP_KEP04:
+      per = th[0]; A = th[1]; ph = th[2]; S = th[3]; C = th[4]; sc = true; thr = 1e-5; use_tp = true;
+      break;
+    case EMP_KEP06:
+      per = exp(th[0]); A = th[1]; ph = th[2]; e = th[3]; w = th[4];
+      break;
+    case EMP_KEP07:
+    default:
+      per = exp(th[0]); A = th[1]; ph = th[2]; S = th[3]; C = th[4]; sc = true; thr = 1e-6;
+      break;
+  }
+  if (sc) {
+    e = __dadd_rn(__dmul_rn(S, S), __dmul_rn(C, C));
+    if (e < thr) {
+      w = 0.0;
+    } else {
+      w = acos(C / sqrt(e));
+      if (S < 0.0) w = kTwoPi - w;
+    }
+  }
+}
+
+__device__ inline void kep_constants(int model, const double* th, KepConst& k) {
+  double per, A, ph, e, w;
+  bool use_tp;
+  kep_elements(model, th, per, A, ph, e, w, use_tp);
+  double sw, cw;
+  sincos(w, &sw, &cw);
+  double ome = 1.0 - e;
+  k.freq = kTwoPi / per;
+  k.ph = ph;
+  k.e = e;
+  k.ome = ome;
+  k.c2 = kF2 / (1.0 + e);
+  k.ome3 = 3.0 * ome;
+  k.a1 = A * cw;
+  k.a2 = -A * sw * sqrt(ome * (1.0 + e));
+  k.a3 = A * e * cw;
+  k.use_tp = use_tp ? 1.0 : 0.0;
+}
+
+// ---- mean anomaly, reduced to [0, pi] exactly like NumPy's remainder ------------------
+__device__ __forceinline__ double mean_anomaly(const KepConst& k, double t) {
+  // two roundings, as `freq * X_ + phase` (kep00.model:5) / `freq * (X_ - tp)` (kep03.model:4)
+  return (k.use_tp != 0.0) ? __dmul_rn(k.freq, __dsub_rn(t, k.ph))
+                           : __dadd_rn(__dmul_rn(k.freq, t), k.ph);
+}
+
+__device__ __noinline__ double mod_two_pi_slow(double M) {
+  double m = fmod(M, kTwoPi);
+  if (m != 0.0) {
+    if (m < 0.0) m += kTwoPi;
+  } else {
+    m = 0.0;
+  }
+  return m;
+}
+
+// r = M mod 2pi in [0, 2pi] with Python semantics. Every step is exact: k = rint(M/2pi),
+// M - k*c has at most 53 significant bits (multiple of ulp(c), |.| < 8), so the FMA and
+// the conditional +c reproduce fmod()+fix-up bit for bit.
+__device__ __forceinline__ double mod_two_pi(double M) {
+  double kd = __dadd_rn(__dadd_rn(__dmul_rn(M, kInvTwoPi), kMagic), -kMagic);
+  double r = __fma_rn(-kd, kTwoPi, M);
+  if (r < 0.0) r = __dadd_rn(r, kTwoPi);
+  if (!(fabs(M) < 1.0e12)) r = mod_two_pi_slow(M);
+  return r;
+}
+
+// ---- x - sin x and 1 - cos x on [0, pi] (Nijenhuis-style folding, Taylor core) ----------
+__device__ __forceinline__ void sin_cos_reduc(double x, double& sn, double& cs) {
+  bool bigg = x > kPi2;
+  double u = bigg ? kPi - x : x;
+  bool big = u > kPi4;
+  double v = big ? kPi2 - u : u;
+  double w = v * v;
+  // (v - sin v)/v^3 = 1/3! - w/5! + w^2/7! - ...   (8 terms: next term < 1e-18 relative)
+  double ps = -1.0 / 355687428096000.0;            // -1/17!
+  ps = fma(ps, w, 1.0 / 1307674368000.0);          // 1/15!
+  ps = fma(ps, w, -1.0 / 6227020800.0);            // -1/13!
+  ps = fma(ps, w, 1.0 / 39916800.0);               // 1/11!
+  ps = fma(ps, w, -1.0 / 362880.0);                // -1/9!
+  ps = fma(ps, w, 1.0 / 5040.0);                   // 1/7!
+  ps = fma(ps, w, -1.0 / 120.0);                   // -1/5!
+  ps = fma(ps, w, 1.0 / 6.0);                      // 1/3!
+  // (1 - cos v)/v^2 = 1/2! - w/4! + w^2/6! - ...   (9 terms)
+  double pc = 1.0 / 6402373705728000.0;            // 1/18!
+  pc = fma(pc, w, -1.0 / 20922789888000.0);        // -1/16!
+  pc = fma(pc, w, 1.0 / 87178291200.0);            // 1/14!
+  pc = fma(pc, w, -1.0 / 479001600.0);             // -1/12!
+  pc = fma(pc, w, 1.0 / 3628800.0);                // 1/10!
+  pc = fma(pc, w, -1.0 / 40320.0);                 // -1/8!
+  pc = fma(pc, w, 1.0 / 720.0);                    // 1/6!
+  pc = fma(pc, w, -1.0 / 24.0);                    // -1/4!
+  pc = fma(pc, w, 0.5);                            // 1/2!
+  double ss = ps * (v * w);
+  double cc = pc * w;
+  double s1 = big ? (u - 1.0) + cc : ss;
+  double c1 = big ? ((1.0 - kPi2) + u) + ss : cc;
+  sn = bigg ? fma(2.0, x, -kPi) + s1 : s1;
+  cs = bigg ? 2.0 - c1 : c1;
+}
+
+// One Keplerian's RV at time t (everything of kep00.model:4-8 for one point).
+__device__ __forceinline__ double kep_rv(const KepConst& k, double t) {
+  const double M = mean_anomaly(k, t);
+  const double r0 = mod_two_pi(M);
+  const bool high = r0 > kPi;
+  const double Mr = high ? __dsub_rn(kTwoPi, r0) : r0;
+
+  // Markley starter (kepler.py get_markley_starter), one division
+  const double M2 = Mr * Mr;
+  const double alpha = fma(k.c2, kPi - Mr, kF1);
+  const double d = fma(alpha, k.e, k.ome3);
+  const double ad = alpha * d;
+  const double r = fma(3.0 * ad, d - k.ome, M2) * Mr;
+  const double q = fma(2.0 * ad, k.ome, -M2);
+  const double q2 = q * q;
+  const double x = fabs(r) + sqrt(fma(q2, q, r * r));
+  const double cb = cbrt(x);
+  const double w = cb * cb;
+  const double den0 = fma(w, w + q, q2);
+  const double E0 = fma(2.0 * r, w, Mr * den0) / (den0 * d);
+
+  // single high-order refinement (kepler.py refine_estimate)
+  double sE, cE;
+  sin_cos_reduc(E0, sE, cE);
+  const double s0 = E0 - sE;  // sin E0
+  const double f0 = fma(k.e, sE, fma(E0, k.ome, -Mr));
+  const double f1 = fma(k.e, cE, k.ome);
+  const double f2 = k.e * s0;
+  const double f3 = 1.0 - f1;
+  const double d3 = -f0 * f1 / fma(f1, f1, -0.5 * f0 * f2);
+  const double d4 = -f0 / fma(d3 * d3, f3 * (1.0 / 6.0), fma(0.5 * d3, f2, f1));
+  const double d42 = d4 * d4;
+  const double dE = -f0 / fma(-d42 * d4, f2 * (1.0 / 24.0), fma(d42, f3 * (1.0 / 6.0), fma(0.5 * d4, f2, f1)));
+
+  // rotate (sin E0, 1 - cos E0) by dE: |dE| <= 5e-4, 4th order is exact to < 1e-20
+  const double dE2 = dE * dE;
+  const double sd = fma(-dE * dE2, 1.0 / 6.0, dE);             // sin dE
+  const double cdm = dE2 * fma(dE2, -1.0 / 24.0, 0.5);         // 1 - cos dE
+  const double c0 = 1.0 - cE;                                  // cos E0
+  const double s1 = s0 + fma(c0, sd, -s0 * cdm);               // sin E1
+  const double cE1 = cE + fma(s0, sd, c0 * cdm);               // 1 - cos E1
+
+  const double den = fma(k.e, cE1, k.ome);                     // 1 - e cos E1
+  const double a2s = high ? -k.a2 : k.a2;                      // sin(2pi - E) = -sin E
+  const double num = fma(k.a1, k.ome - cE1, a2s * s1);
+  return num / den + k.a3;
+}
+
+// ---- priors: support/priors/{Uniform,Normal,Jeffreys,Isotropic,Fixed}.prior ------------
+__device__ inline double prior_value(const EmpPriorOp& o, double x) {
+  if (o.prior == EMP_PRIOR_FIXED) return 0.0;
+  if (!(o.lo <= x && x <= o.hi)) return -INFINITY;
+  switch (o.prior) {
+    case EMP_PRIOR_UNIFORM:
+    case EMP_PRIOR_JEFFREYS:
+      return o.a0;
+    case EMP_PRIOR_NORMAL: {
+      // -0.5*((x - mu)/s)**2 - np.log(s*np.sqrt(2*np.pi)) - logZ   (Normal.prior:8), same roundings
+      double z = __ddiv_rn(__dsub_rn(x, o.a0), o.a1);
+      double v = __dmul_rn(-0.5, __dmul_rn(z, z));
+      return __dsub_rn(__dsub_rn(v, o.a3), o.a2);
+    }
+    case EMP_PRIOR_ISOTROPIC:
+      return __dsub_rn(log(__dmul_rn(0.5, sin(x))), o.a0);  // Isotropic.prior:4
+    default:
+      return NAN;
+  }
+}
+
+// my_prior (emp.py:190-254) as the straight-line program in the descriptor.
+__device__ inline double prior_program(const EmpPriorOp* ops, int n_ops, const double* th) {
+  double lp = 0.0;
+  for (int i = 0; i < n_ops; ++i) {
+    const EmpPriorOp& o = ops[i];
+    if (o.op == EMP_POP_PARAM) {
+      lp = __dadd_rn(lp, prior_value(o, th[o.i0]));
+    } else if (o.op == EMP_POP_CHECK) {
+      if (lp == -INFINITY) return lp;
+    } else {
+      double a = th[o.i0], b = th[o.i1];
+      double x = __dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b));
+      lp = __dadd_rn(lp, prior_value(o, x));
+    }
+  }
+  return lp;
+}
+
+// ---- small helpers -----------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// mbarrier + 1-D bulk TMA (cp.async.bulk; SASS: UBLKCP) -----------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+}  // namespace emp

@@ -1,0 +1,319 @@
+// emp_logl.cuh — batched my_likelihood + my_prior kernel.
+//
+// Work decomposition:
+//   * one WARP per walker (theta row); lanes own consecutive pairs of datapoints, so the
+//     Keplerian constants are warp-uniform and every shared-memory read is a conflict-free
+//     128-bit access;
+//   * one CTA = NW walker warps + 1 producer warp.  The producer streams the packed data set
+//     (t | y | yerr^2 | instrument id per tile) from L2 into a STAGES-deep shared-memory ring
+//     with 1-D bulk TMA (cp.async.bulk + mbarrier complete_tx); all NW walkers of the CTA
+//     consume the same tile, so each tile is fetched once per NW evaluations;
+//   * chi^2 and sum(log err2) are accumulated per lane, reduced with warp shuffles in a fixed
+//     order (bit-reproducible run to run), one store per walker.
+#pragma once
+#include "emp_device.cuh"
+
+namespace emp {
+
+constexpr int kTilePoints = 512;                       // datapoints per TMA tile
+constexpr int kTileBytes = kTilePoints * (3 * 8 + 4);  // t, y, e2 (FP64) + ins (int32)
+constexpr int kStages = 3;
+constexpr int kWalkerWarps = 8;                        // walker warps per CTA
+constexpr int kLoglThreads = (kWalkerWarps + 1) * 32;  // + 1 producer warp
+
+// per-walker constants in shared memory (one slot per walker warp)
+struct WalkerConst {
+  double th[EMP_MAX_DIM];
+  KepConst kep[EMP_MAX_KEP];
+  double gamma[EMP_MAX_INS];
+  double jit2[EMP_MAX_INS];
+  double acc[EMP_MAX_ACC];
+  double ma[2 * EMP_MAX_MA];
+};
+
+struct LoglParams {
+  const EmpModelDesc* desc;  // device copy
+  const char* tiles;         // packed tiles, kTileBytes each, 128B aligned
+  int64_t n_points;
+  int32_t n_tiles;
+  const double* theta;       // [n_eval, ndim_free]
+  const int32_t* eval_index; // optional compaction map (NULL: identity)
+  int64_t n_eval;
+  double* logl;
+  double* logp;              // may be NULL when the prior was evaluated elsewhere
+  const double* logp_in;     // if non-NULL: take the prior from here instead of computing it
+  double t0;                 // X_[0] (acc.model uses X_ - X_[0])
+  double ll_const;           // -0.5*log(2*pi)*ndat  (00.like:1)
+};
+
+constexpr size_t kLoglSmemBytes =
+    size_t(kStages) * kTileBytes + 2 * kStages * sizeof(uint64_t) + kWalkerWarps * sizeof(WalkerConst);
+
+// Fill the walker's constants; returns log-prior (evaluated redundantly by all lanes: uniform).
+__device__ inline double walker_prologue(const EmpModelDesc* __restrict__ d, const double* __restrict__ theta_row,
+                                         WalkerConst& wc, int lane, bool eval_prior) {
+  const int nfull = d->ndim_full, nfree = d->ndim_free;
+  for (int i = lane; i < nfull; i += 32) wc.th[i] = d->full_init[i];
+  __syncwarp();
+  for (int j = lane; j < nfree; j += 32) wc.th[d->free_to_full[j]] = theta_row[j];
+  __syncwarp();
+  double lp = 0.0;
+  if (eval_prior) lp = prior_program(d->prior_ops, d->n_prior_ops, wc.th);
+  if (lp == -INFINITY) return lp;
+  if (lane < d->n_kep) {
+    KepConst kc;
+    kep_constants(d->kep_model[lane], wc.th + d->kep_off[lane], kc);
+    wc.kep[lane] = kc;
+  }
+  if (lane < d->n_ins) {
+    wc.gamma[lane] = wc.th[d->offset_off + lane];
+    double s = d->has_jitter ? wc.th[d->jitter_off + lane] : 0.0;
+    wc.jit2[lane] = __dmul_rn(s, s);  // theta ** 2 (jitter00.model:3)
+  }
+  if (lane < d->acc_order) wc.acc[lane] = wc.th[d->acc_off + lane];
+  if (lane < 2 * d->ma_order) wc.ma[lane] = wc.th[d->ma_off + lane];
+  __syncwarp();
+  return lp;
+}
+
+// np.polyval([a_n .. a_1, 0], x) with NumPy's Horner roundings (acc.model:2)
+__device__ __forceinline__ double accel_term(const double* acc, int order, double x) {
+  double y = acc[0];
+  for (int j = 1; j < order; ++j) y = __dadd_rn(__dmul_rn(y, x), acc[j]);
+  return __dadd_rn(__dmul_rn(y, x), 0.0);
+}
+
+__global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglParams P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* tiles_s = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + size_t(kStages) * kTileBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  WalkerConst* wcs = reinterpret_cast<WalkerConst*>(empty_bar + kStages);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const EmpModelDesc* __restrict__ d = P.desc;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kWalkerWarps);
+    }
+    fence_barrier_init();
+  }
+
+  // ---- prologue: priors + per-walker constants ------------------------------------------
+  bool active = false;
+  int64_t slot = -1;
+  double lp = 0.0;
+  if (warp < kWalkerWarps) {
+    int64_t e = int64_t(blockIdx.x) * kWalkerWarps + warp;
+    if (e < P.n_eval) {
+      slot = P.eval_index ? int64_t(P.eval_index[e]) : e;
+      const bool eval_prior = (P.logp_in == nullptr);
+      lp = walker_prologue(d, P.theta + slot * d->ndim_free, wcs[warp], lane, eval_prior);
+      if (!eval_prior) lp = P.logp_in[slot];
+      active = (lp != -INFINITY);  // emcee: the likelihood is not evaluated at -inf prior
+      if (lane == 0) {
+        if (P.logp) P.logp[slot] = lp;
+        if (!active) P.logl[slot] = -INFINITY;
+      }
+    }
+  }
+  const int any_active = __syncthreads_or(active ? 1 : 0);  // also publishes the barrier inits
+  if (!any_active) return;
+
+  const int n_tiles = P.n_tiles;
+
+  if (warp == kWalkerWarps) {
+    // ===== producer warp: bulk-TMA the tiles through the ring ==============================
+    if (lane == 0) {
+      for (int i = 0; i < n_tiles; ++i) {
+        const int s = i % kStages;
+        if (i >= kStages) mbar_wait(&empty_bar[s], ((i / kStages) - 1) & 1);
+        mbar_arrive_expect_tx(&full_bar[s], kTileBytes);
+        tma_bulk_g2s(tiles_s + size_t(s) * kTileBytes, P.tiles + size_t(i) * kTileBytes, kTileBytes,
+                     &full_bar[s]);
+      }
+    }
+    return;
+  }
+
+  // ===== walker warps =========================================================================
+  const WalkerConst& wc = wcs[warp];
+  const int K = d->n_kep;
+  const int acc_order = d->acc_order;
+  const int ma_order = (d->ma_mode == EMP_MA_GLOBAL) ? d->ma_order : 0;
+  double* ma_scratch = nullptr;  // order >= 2 path reuses wc.th as scratch (th is dead after the prologue)
+
+  double chi = 0.0, lsum = 0.0, prod = 1.0;
+  int nprod = 0;
+  // MA(1) carry (warp-uniform): previous residual and previous timestamp
+  double r_carry = 0.0, t_prev = 0.0;
+  // MA(order>=2) history, newest first (warp-uniform)
+  double rh[EMP_MAX_MA], thist[EMP_MAX_MA];
+#pragma unroll
+  for (int c = 0; c < EMP_MAX_MA; ++c) { rh[c] = 0.0; thist[c] = 0.0; }
+  (void)ma_scratch;
+
+  for (int i = 0; i < n_tiles; ++i) {
+    const int s = i % kStages;
+    mbar_wait(&full_bar[s], (i / kStages) & 1);
+    if (active) {
+      const unsigned char* tb = tiles_s + size_t(s) * kTileBytes;
+      const double2* ts = reinterpret_cast<const double2*>(tb);
+      const double2* ys = reinterpret_cast<const double2*>(tb + kTilePoints * 8);
+      const double2* es = reinterpret_cast<const double2*>(tb + kTilePoints * 16);
+      const int2* is = reinterpret_cast<const int2*>(tb + kTilePoints * 24);
+      const int64_t base = int64_t(i) * kTilePoints;
+      const int64_t rem = P.n_points - base;
+      const int cnt = rem < kTilePoints ? int(rem) : kTilePoints;
+      const int iters = (cnt + 63) >> 6;
+      for (int it = 0; it < iters; ++it) {
+        const int li = it * 32 + lane;
+        const double2 t2 = ts[li];
+        const int p0 = it * 64 + 2 * lane;
+        const bool v0 = p0 < cnt, v1 = (p0 + 1) < cnt;
+        double m0 = 0.0, m1 = 0.0;
+        for (int k = 0; k < K; ++k) {
+          const KepConst kc = wc.kep[k];
+          m0 += kep_rv(kc, t2.x);
+          m1 += kep_rv(kc, t2.y);
+        }
+        if (acc_order > 0) {
+          m0 += accel_term(wc.acc, acc_order, __dsub_rn(t2.x, P.t0));
+          m1 += accel_term(wc.acc, acc_order, __dsub_rn(t2.y, P.t0));
+        }
+        const int2 in2 = is[li];
+        const double2 y2 = ys[li];
+        const double2 e2 = es[li];
+        m0 += wc.gamma[in2.x];
+        m1 += wc.gamma[in2.y];
+        double d0 = v0 ? y2.x - m0 : 0.0;
+        double d1 = v1 ? y2.y - m1 : 0.0;
+        const double w0 = v0 ? e2.x + wc.jit2[in2.x] : 1.0;
+        const double w1 = v1 ? e2.y + wc.jit2[in2.y] : 1.0;
+
+        if (ma_order == 1) {
+          // moav01.model: r_i = d_i - phi*exp(-|t_i - t_{i-1}|/tau) * r_{i-1}, sequential in i.
+          // Evaluated as a warp scan over the affine maps r -> a*r + b (exact algebra).
+          const double phi = wc.ma[0], tau = wc.ma[1];
+          const double tl = __shfl_up_sync(0xffffffffu, t2.y, 1);
+          const double tp0 = (lane == 0) ? t_prev : tl;
+          const bool first = (base + p0) == 0;  // i == 0: no MA term (`if i > c`)
+          double a0 = (v0 && !first) ? -phi * exp(-fabs(t2.x - tp0) / tau) : 0.0;
+          double a1 = v1 ? -phi * exp(-fabs(t2.y - t2.x) / tau) : 0.0;
+          // compose the lane's two maps, then inclusive scan across lanes
+          double A = a1 * a0, B = fma(a1, d0, d1);
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            const double Ap = __shfl_up_sync(0xffffffffu, A, off);
+            const double Bp = __shfl_up_sync(0xffffffffu, B, off);
+            if (lane >= off) { B = fma(A, Bp, B); A = A * Ap; }
+          }
+          const double r_last = fma(A, r_carry, B);        // residual at this lane's 2nd point
+          double r_prev = __shfl_up_sync(0xffffffffu, r_last, 1);
+          if (lane == 0) r_prev = r_carry;
+          d0 = fma(a0, r_prev, d0);
+          d1 = fma(a1, d0, d1);
+          // carry to the next 64 points: last VALID point of this iteration
+          const int last_lane = min(31, (cnt - it * 64 - 1) >> 1);
+          const bool last_is_second = ((cnt - it * 64) >= 2 * (last_lane + 1));
+          const double rc = __shfl_sync(0xffffffffu, last_is_second ? d1 : d0, last_lane);
+          const double tc = __shfl_sync(0xffffffffu, last_is_second ? t2.y : t2.x, last_lane);
+          r_carry = rc;
+          t_prev = tc;
+        } else if (ma_order >= 2) {
+          // general order: serial recurrence over the 64 points (rare configuration), every lane
+          // runs the same uniform loop on shuffled values so no shared scratch is needed.
+          for (int j = 0; j < 64; ++j) {
+            const int src = j >> 1;
+            const double dj = __shfl_sync(0xffffffffu, (j & 1) ? d1 : d0, src);
+            const double tj = __shfl_sync(0xffffffffu, (j & 1) ? t2.y : t2.x, src);
+            const bool vj = (it * 64 + j) < cnt;
+            const int64_t gi = base + it * 64 + j;
+            double r = dj;
+            if (vj) {
+#pragma unroll
+              for (int c = 0; c < EMP_MAX_MA; ++c) {
+                if (c < ma_order && gi > c) {
+                  const double ma = wc.ma[2 * c] * exp(-fabs(tj - thist[c]) / wc.ma[2 * c + 1]) * rh[c];
+                  r -= ma;
+                }
+              }
+#pragma unroll
+              for (int c = EMP_MAX_MA - 1; c > 0; --c) { rh[c] = rh[c - 1]; thist[c] = thist[c - 1]; }
+              rh[0] = r;
+              thist[0] = tj;
+              if (src == lane) { if (j & 1) d1 = r; else d0 = r; }
+            }
+          }
+        }
+
+        // chi^2 and log-det: sum(r^2/err2 + log err2)  (00.like:5); logs taken on 4-point products
+        chi += d0 * d0 / w0;
+        chi += d1 * d1 / w1;
+        prod *= w0 * w1;
+        if (++nprod == 2) { lsum += log(prod); prod = 1.0; nprod = 0; }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+  }
+
+  if (active) {
+    lsum += log(prod);
+    const double tot = warp_sum(chi + lsum);
+    if (lane == 0) P.logl[slot] = fma(-0.5, tot, P.ll_const);
+  }
+}
+
+// my_model(theta) for one theta: model0[n], err20[n]  (emp_model.py:706-781); thread per point
+// for the first pass, MA recurrence (if any) applied serially by one thread afterwards.
+__global__ void model_rv_kernel(const EmpModelDesc* __restrict__ d, const double* __restrict__ theta,
+                                const double* __restrict__ t, const double* __restrict__ y,
+                                const double* __restrict__ e2, const int32_t* __restrict__ ins, int64_t n,
+                                double t0, double* __restrict__ model, double* __restrict__ err2) {
+  __shared__ WalkerConst wc;
+  if (threadIdx.x < 32) walker_prologue(d, theta, wc, threadIdx.x, false);
+  __syncthreads();
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    double m = 0.0;
+    for (int k = 0; k < d->n_kep; ++k) m += kep_rv(wc.kep[k], t[i]);
+    if (d->acc_order > 0) m += accel_term(wc.acc, d->acc_order, __dsub_rn(t[i], t0));
+    m += wc.gamma[ins[i]];
+    model[i] = m;
+    err2[i] = e2[i] + wc.jit2[ins[i]];
+  }
+}
+
+__global__ void model_ma_kernel(const EmpModelDesc* __restrict__ d, const double* __restrict__ theta,
+                                const double* __restrict__ t, const double* __restrict__ y, int64_t n,
+                                double* __restrict__ model) {
+  // moav01.model:3-15, serial (post-processing helper, one theta)
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const int order = d->ma_order;
+  double th_ma[2 * EMP_MAX_MA];
+  double full[EMP_MAX_DIM];
+  for (int i = 0; i < d->ndim_full; ++i) full[i] = d->full_init[i];
+  for (int j = 0; j < d->ndim_free; ++j) full[d->free_to_full[j]] = theta[j];
+  for (int c = 0; c < 2 * order; ++c) th_ma[c] = full[d->ma_off + c];
+  double rh[EMP_MAX_MA], thist[EMP_MAX_MA];
+  for (int c = 0; c < EMP_MAX_MA; ++c) { rh[c] = 0.0; thist[c] = 0.0; }
+  for (int64_t i = 0; i < n; ++i) {
+    double r = y[i] - model[i];
+    double m = model[i];
+    for (int c = 0; c < order; ++c) {
+      if (i > c) {
+        const double ma = th_ma[2 * c] * exp(-fabs(t[i] - thist[c]) / th_ma[2 * c + 1]) * rh[c];
+        m += ma;
+        r -= ma;
+      }
+    }
+    for (int c = EMP_MAX_MA - 1; c > 0; --c) { rh[c] = rh[c - 1]; thist[c] = thist[c - 1]; }
+    rh[0] = r;
+    thist[0] = t[i];
+    model[i] = m;
+  }
+}
+
+}  // namespace emp

@@ -1,0 +1,105 @@
+"""Host-side random draws for the parallel-tempering step.
+
+BASELINE.json north_star: "the affine-invariant stretch-move proposal, the
+Metropolis accept and the adjacent-temperature swap are done on device from
+host-supplied random draws".  This module is that host supply.  The draw ORDER
+restates what the reference stack consumes from its `numpy.random.RandomState`
+(emcee 3.1.6 `RedBlueMove.propose` + `StretchMove.get_proposal`, then the
+ptemcee-lineage swap sweep of reddemcee; SURVEY.md §3.3, §8c row C2 — recalled,
+the packages are not vendored):
+
+  for t in range(ntemps):                 # reddemcee iterates temperatures serially
+    for step in range(nsteps):
+      inds = arange(W) % 2 ; shuffle(inds)
+      for split in (0, 1):
+        zz   = ((a-1)*rand(Ns) + 1)**2 / a
+        rint = randint(Nc, size=Ns)
+        u    = rand() for each walker of the split, in index order
+  for i in range(ntemps-1, 0, -1):        # hot -> cold
+    iperm = permutation(W) ; i1perm = permutation(W) ; raccept = log(uniform(size=W))
+
+Logs (`(ndim-1)*log(zz)`, `log(u)`) are taken here with NumPy so the device and
+the oracle compare against bit-identical thresholds.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass
+class SweepDraws:
+    half_idx: np.ndarray  # [nsteps, T, 2, H] int32: walkers of split 0 / 1 (ascending)
+    zz: np.ndarray        # [nsteps, T, 2, H]
+    rint: np.ndarray      # [nsteps, T, 2, H] int32
+    factors: np.ndarray   # [nsteps, T, 2, H]  (ndim-1)*log(zz)
+    lnu: np.ndarray       # [nsteps, T, 2, H]  log(u)
+    perm: np.ndarray      # [T-1, 2, W] int32: perm[j] couples temperature j+1 (row 0) with j (row 1)
+    lnu_swap: np.ndarray  # [T-1, W]
+
+    def nbytes(self) -> int:
+        return sum(getattr(self, f).nbytes for f in
+                   ("half_idx", "zz", "rint", "factors", "lnu", "perm", "lnu_swap"))
+
+
+def draw_sweep(rng: np.random.RandomState, T: int, W: int, ndim: int, nsteps: int, a: float = 2.0,
+               swap: bool = True) -> SweepDraws:
+    if W % 2:
+        raise ValueError("nwalkers must be even (two equal halves, emcee RedBlueMove nsplits=2)")
+    H = W // 2
+    half_idx = np.empty((nsteps, T, 2, H), dtype=np.int32)
+    zz = np.empty((nsteps, T, 2, H))
+    rint = np.empty((nsteps, T, 2, H), dtype=np.int32)
+    u = np.empty((nsteps, T, 2, H))
+    base = np.arange(W) % 2
+    for t in range(T):
+        for s in range(nsteps):
+            inds = base.copy()
+            rng.shuffle(inds)
+            half_idx[s, t, 0] = np.flatnonzero(inds == 0)
+            half_idx[s, t, 1] = np.flatnonzero(inds == 1)
+            for split in (0, 1):
+                zz[s, t, split] = ((a - 1.0) * rng.rand(H) + 1) ** 2.0 / a
+                rint[s, t, split] = rng.randint(H, size=(H,))
+                u[s, t, split] = rng.rand(H)
+    factors = (ndim - 1.0) * np.log(zz)
+    with np.errstate(divide="ignore"):
+        lnu = np.log(u)
+    perm = np.empty((max(T - 1, 0), 2, W), dtype=np.int32)
+    lnu_swap = np.empty((max(T - 1, 0), W))
+    if swap:
+        for i in range(T - 1, 0, -1):
+            perm[i - 1, 0] = rng.permutation(W)
+            perm[i - 1, 1] = rng.permutation(W)
+            with np.errstate(divide="ignore"):
+                lnu_swap[i - 1] = np.log(rng.uniform(size=W))
+    return SweepDraws(half_idx, zz, rint, factors, lnu, perm, lnu_swap)
+
+
+def initial_positions(rng: np.random.RandomState, spec, ntemps: int, nwalkers: int) -> np.ndarray:
+    """set_init() of the generated script (emp.py:617-654): per temperature and free parameter
+    `pos = r*(2*sort(U(0,1,W)) - 1) + m`, shuffled; m, r from init_pos or the limits, r*0.707
+    for `is_hou` parameters."""
+    fp = spec.free_params()
+    pos = np.zeros((ntemps, nwalkers, len(fp)))
+    for t in range(ntemps):
+        for j, p in enumerate(fp):
+            r_f = 0.707 if p.is_hou else 1
+            b = p.limits[0] if p.init_pos[0] is None else np.round(p.init_pos[0], 8)
+            a = p.limits[1] if p.init_pos[1] is None else np.round(p.init_pos[1], 8)
+            m = (a + b) / 2
+            r = (a - b) / 2 * r_f
+            dist = np.sort(rng.uniform(0, 1, nwalkers))
+            pos[t][:, j] = r * (2 * dist - 1) + m
+            rng.shuffle(pos[t, :, j])
+    return pos
+
+
+def default_betas(ndim: int, ntemps: int) -> np.ndarray:
+    """Geometric ladder with the emcee-v2 / ptemcee `default_beta_ladder` spacing (the table for
+    ndim <= 100 is fitted by the large-ndim law below to < 3 % for ndim >= 3; Tmax = inf is not
+    used: the hottest chain keeps a finite temperature).  reddemcee's own default is not
+    recoverable offline; pass `betas=` for an exact ladder."""
+    tstep = 1.0 + 2.0 * np.sqrt(np.log(4.0)) / np.sqrt(ndim)
+    return tstep ** (-np.arange(ntemps, dtype=np.float64))

@@ -1,0 +1,166 @@
+"""Device likelihood engine: the drop-in for the generated `my_likelihood` /
+`my_prior` / `my_model` callables (support/likelihoods/00.like:3-5,
+emp.py:190-254, emp_model.py:706-781) and the object the PT sampler drives.
+
+`LikelihoodEngine` owns one `EmpHandle` (include/emperor_b200.h).  torch is used
+for device memory and stream plumbing only: tensors are passed to the C-ABI as
+raw device pointers and all kernels run on torch's current stream.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from .modelspec import CompiledModel, ModelSpec
+
+
+def _np64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class LikelihoodEngine:
+    def __init__(self, model, t, y, yerr, flag, am=None, device: int = 0):
+        import torch  # device memory / streams only
+
+        self.cm: CompiledModel = model.compile() if isinstance(model, ModelSpec) else model
+        self.ndim = self.cm.ndim_free
+        self.t, self.y, self.yerr = _np64(t), _np64(y), _np64(yerr)
+        self.flag = np.ascontiguousarray(flag, dtype=np.int32)
+        self.ndat = len(self.t)
+        if not (len(self.y) == len(self.yerr) == len(self.flag) == self.ndat):
+            raise ValueError("t, y, yerr, flag must have the same length")
+        if not torch.cuda.is_available():
+            raise _lib.EmperorB200Error(-3, "no CUDA device visible (there is no CPU fallback)")
+        self.device = int(device)
+        self.torch_device = torch.device("cuda", self.device)
+        L = _lib.lib()
+        self._desc = self.cm.to_c()
+        self._am_keepalive = None
+        am_ptr = None
+        if self.cm.am_enabled:
+            if am is None:
+                raise ValueError("model has an astrometric block but no `am` data was given")
+            from .amdata import am_to_c
+            am_c, self._am_keepalive = am_to_c(am)
+            am_ptr = ctypes.cast(ctypes.pointer(am_c), ctypes.c_void_p)
+        h = ctypes.c_void_p()
+        _lib.check(L.emp_create(ctypes.cast(ctypes.pointer(self._desc), ctypes.c_void_p),
+                                self.t.ctypes.data, self.y.ctypes.data, self.yerr.ctypes.data,
+                                self.flag.ctypes.data, self.ndat, am_ptr, self.device, ctypes.byref(h)))
+        self._h = h
+        self._L = L
+        self.use_torch_stream()
+
+    # ---- lifetime -------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.emp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def use_torch_stream(self):
+        """Run the handle's kernels on torch's current stream of this device."""
+        import torch
+        s = torch.cuda.current_stream(self.torch_device).cuda_stream
+        _lib.check(self._L.emp_set_stream(self._h, ctypes.c_void_p(s)))
+
+    def synchronize(self):
+        _lib.check(self._L.emp_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        c = ctypes.c_int64()
+        _lib.check(self._L.emp_launch_count(self._h, ctypes.byref(c)))
+        return int(c.value)
+
+    def set_timing(self, on: bool):
+        _lib.check(self._L.emp_set_timing(self._h, 1 if on else 0))
+
+    def last_logl_ms(self) -> float:
+        ms = ctypes.c_float()
+        _lib.check(self._L.emp_last_logl_ms(self._h, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def nan_count(self) -> int:
+        c = ctypes.c_uint32()
+        _lib.check(self._L.emp_nan_count(self._h, ctypes.byref(c)))
+        return int(c.value)
+
+    # ---- batched likelihood + prior ---------------------------------------------
+    def logl_batch_device(self, theta, logl=None, logp=None):
+        """theta: CUDA float64 tensor [n, ndim] -> (logl[n], logp[n]) CUDA tensors (async)."""
+        import torch
+        if theta.dtype != torch.float64 or not theta.is_cuda or not theta.is_contiguous():
+            raise ValueError("theta must be a contiguous CUDA float64 tensor")
+        if theta.shape[-1] != self.ndim:
+            raise ValueError(f"theta has {theta.shape[-1]} columns, model has ndim={self.ndim}")
+        n = theta.numel() // self.ndim
+        if logl is None:
+            logl = torch.empty(n, dtype=torch.float64, device=theta.device)
+        if logp is None:
+            logp = torch.empty(n, dtype=torch.float64, device=theta.device)
+        _lib.check(self._L.emp_logl_batch(self._h, theta.data_ptr(), n, logl.data_ptr(), logp.data_ptr()))
+        return logl, logp
+
+    def logl_batch(self, thetas) -> Tuple[np.ndarray, np.ndarray]:
+        """Host entry (the plugin call): thetas[n, ndim] -> (logl[n], logp[n]) NumPy arrays.
+        Includes the H2D / D2H copies; synchronous."""
+        th = _np64(thetas).reshape(-1, self.ndim)
+        n = len(th)
+        ll = np.empty(n, dtype=np.float64)
+        lp = np.empty(n, dtype=np.float64)
+        _lib.check(self._L.emp_logl_batch_host(self._h, th.ctypes.data, n, ll.ctypes.data, lp.ctypes.data))
+        return ll, lp
+
+    # ---- scalar-compatible callables (B1 of SURVEY.md §8b) ---------------------------
+    def my_likelihood(self, theta) -> float:
+        """my_likelihood(theta) (00.like:3-5).  Like the reference it evaluates the
+        model regardless of the prior; use `logl_batch` for sampler semantics."""
+        th = _np64(theta).reshape(-1, self.ndim)
+        ll, lp = self.logl_batch(th)
+        if np.any(~np.isfinite(lp)):
+            raise ValueError("my_likelihood called outside the prior support; the device path "
+                             "does not evaluate the model there (emcee never does either)")
+        return float(ll[0]) if len(ll) == 1 else ll
+
+    def my_prior(self, theta) -> float:
+        th = _np64(theta).reshape(-1, self.ndim)
+        _, lp = self.logl_batch(th)
+        return float(lp[0]) if len(lp) == 1 else lp
+
+    def my_model(self, theta):
+        """my_model(theta) -> (model0[ndat], err20[ndat]) (emp_model.py:706-781)."""
+        th = _np64(theta).reshape(self.ndim)
+        model = np.empty(self.ndat)
+        err2 = np.empty(self.ndat)
+        _lib.check(self._L.emp_model_host(self._h, th.ctypes.data, model.ctypes.data, err2.ctypes.data))
+        return model, err2
+
+    # ---- PT step primitives (used by sampler.PTSampler) -------------------------------
+    def pt_stretch_step(self, p, logl, logp, betas, half_idx, zz, rint, factors, lnu, accepted):
+        T, W, nd = p.shape
+        _lib.check(self._L.emp_pt_stretch_step(
+            self._h, T, W, p.data_ptr(), logl.data_ptr(), logp.data_ptr(), betas.data_ptr(),
+            half_idx.data_ptr(), zz.data_ptr(), rint.data_ptr(), factors.data_ptr(), lnu.data_ptr(),
+            accepted.data_ptr()))
+
+    def pt_swap_plan(self, logl_all, betas, perm, lnu, src, n_acc):
+        T, W = logl_all.shape
+        _lib.check(self._L.emp_pt_swap_plan(
+            self._h, T, W, logl_all.data_ptr(), betas.data_ptr(),
+            perm.data_ptr() if perm is not None else None, lnu.data_ptr() if lnu is not None else None,
+            src.data_ptr(), n_acc.data_ptr()))
+
+    def pt_gather_rows(self, src, p_in, ll_in, lp_in, p_out, ll_out, lp_out):
+        n_rows = src.numel()
+        _lib.check(self._L.emp_pt_gather_rows(
+            self._h, n_rows, p_in.shape[-1], src.data_ptr(), p_in.data_ptr(), ll_in.data_ptr(),
+            lp_in.data_ptr(), p_out.data_ptr(), ll_out.data_ptr(), lp_out.data_ptr()))

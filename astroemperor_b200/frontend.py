@@ -1,0 +1,289 @@
+"""Host-side mirror of the reference front end, for the hot path only.
+
+`default_spec` restates what `Simulation._autorun_add_blocks` + `SmartSetter`
+(emp.py:2614-2651, block_repo.py:505-867) produce for an RV model: the block
+order (Keplerians first, emp.py:1235; then Acceleration, Offset, Jitter, MOAV),
+the parameter names and the data-derived default limits / priors.  It is checked
+against the REAL reference's output in tests/test_frontend.py via the golden
+`<case>.json` files.
+
+`Simulation` keeps the reference's user-facing names (`load_data`,
+`set_engine('reddemcee')`, `engine_config['setup']`, `add_condition`,
+`keplerian_parameterisation`, `moav`, `acceleration`, `autorun`) so the README
+mini test reads the same; underneath, instead of generating a script and
+spawning `ipython` (emp.py:2575-2582), it builds a `LikelihoodEngine` and a
+device `PTSampler` in-process.  Post-processing, plotting, tables, the
+model-comparison loop's GM/HDI machinery are out of scope (SURVEY.md §2 rows
+12-18): `autorun` records max-likelihood / BIC per model and stops on the
+reference's default criterion (BIC_old - BIC_new < 5, emp.py:1131-1133).
+"""
+from __future__ import annotations
+
+import itertools
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .data import RVData, load_rv_folder
+from .modelspec import (AdditionalPrior, BlockSpec, ModelSpec, ParamSpec, finalize_prargs,
+                        UnsupportedModelError)
+
+TWO_PI_LIMITS = [0, 2 * np.pi]
+
+# parameter names per Keplerian template (block_repo.py:22-31, param_repo.py)
+KEP_PARAM_NAMES = {
+    0: ["Period", "Amplitude", "Phase", "Eccentricity", "Longitude"],
+    1: ["Period", "Amplitude", "Phase", "Ecc_sin", "Ecc_cos"],
+    2: ["lPeriod", "Amp_sin", "Amp_cos", "Ecc_sin", "Ecc_cos"],
+    3: ["Period", "Amplitude", "T_0", "Eccentricity", "Longitude"],
+    4: ["Period", "Amplitude", "T_0", "Ecc_sin", "Ecc_cos"],
+    6: ["lPeriod", "Amplitude", "Phase", "Eccentricity", "Longitude"],
+    7: ["lPeriod", "Amplitude", "Phase", "Ecc_sin", "Ecc_cos"],
+}
+HOU_NAMES = ("Amp_sin", "Amp_cos", "Ecc_sin", "Ecc_cos")  # param_repo.py: is_hou=True
+
+
+def _param(name, prior, limits, prargs):
+    base = name.split(" ")[0]
+    return ParamSpec(name=name, prior=prior, limits=[_f(limits[0]), _f(limits[1])], prargs=prargs,
+                     is_hou=base in HOU_NAMES)
+
+
+def _f(x):
+    return x.item() if isinstance(x, (np.floating, np.integer)) else x
+
+
+def keplerian_block(data: RVData, number: int, parameterisation: int, ecc_limits, ecc_prargs,
+                    astrometry: bool = False) -> BlockSpec:
+    """KeplerianBlock + SmartSetter.set_Keplerian (block_repo.py:22-78, 517-607)."""
+    sig_limiter = np.std(data.y)  # data['RV'].std(ddof=0)
+    per_limiter = data.t.max() - data.t.min()
+    amp_limiter = sig_limiter * np.sqrt(4)
+    uni, norm = "Uniform", "Normal"
+    p = parameterisation
+    addi: List[AdditionalPrior] = []
+    if p == 0:
+        lims = [[1.5, per_limiter], [1e-6, amp_limiter], TWO_PI_LIMITS, ecc_limits, TWO_PI_LIMITS]
+        priors = [uni, uni, uni, norm, uni]
+        prargs = [None, None, None, list(ecc_prargs), None]
+    elif p == 1:
+        lims = [[1.5, per_limiter], [1e-6, amp_limiter], TWO_PI_LIMITS, [-1, 1], [-1, 1]]
+        priors, prargs = [uni] * 5, [None] * 5
+        addi.append(AdditionalPrior("Ecc", uni, [0, 1], None))
+    elif p == 2:
+        kamp = np.sqrt(amp_limiter / 2)
+        lims = [[np.log(1.5), np.log(per_limiter)], [-kamp, kamp], [-kamp, kamp], [-1, 1], [-1, 1]]
+        priors, prargs = [uni] * 5, [None] * 5
+        addi.append(AdditionalPrior("Ecc", uni, [0, 1], None))
+    elif p == 3:
+        lims = [[1.5, per_limiter], [1e-6, amp_limiter], [-1000, 1000], ecc_limits, TWO_PI_LIMITS]
+        priors = [uni, uni, uni, norm, uni]
+        prargs = [None, None, None, list(ecc_prargs), None]
+    elif p == 4:
+        lims = [[1.5, per_limiter], [1e-6, amp_limiter], [-1000, 1000], [-1, 1], [-1, 1]]
+        priors, prargs = [uni] * 5, [None] * 5
+        addi.append(AdditionalPrior("Ecc", uni, [0, 1], None))
+    elif p == 6:
+        lims = [[np.log(1.5), np.log(per_limiter)], [1e-6, amp_limiter], TWO_PI_LIMITS, ecc_limits,
+                TWO_PI_LIMITS]
+        priors = ["Jeffreys", uni, uni, norm, uni]
+        prargs = [None, None, None, list(ecc_prargs), None]
+    elif p == 7:
+        lims = [[np.log(1.5), np.log(per_limiter)], [1e-6, amp_limiter], TWO_PI_LIMITS, [-1, 1], [-1, 1]]
+        priors, prargs = ["Jeffreys", uni, uni, uni, uni], [None] * 5
+        addi.append(AdditionalPrior("Ecc", norm, [0, 1], list(ecc_prargs)))
+    else:
+        raise UnsupportedModelError(f"keplerian_parameterisation {p}")
+    names = list(KEP_PARAM_NAMES[p])
+    if astrometry:
+        if p != 0:
+            raise UnsupportedModelError("astrometric Keplerians use parameterisation 0 (block_repo.py:524-541)")
+        names += ["Inclination", "Omega"]
+        lims += [[0, np.pi], TWO_PI_LIMITS]
+        priors += ["Isotropic", uni]
+        prargs += [None, None]
+    params = [_param(f"{n} {number}", pr, lim, pa) for n, pr, lim, pa in zip(names, priors, lims, prargs)]
+    return BlockSpec(type_="Keplerian", params=params, parameterisation=p, astrometry=astrometry,
+                     number=number, additional=addi)
+
+
+def instrument_blocks(data: RVData, acceleration=0, jitter=True, moav=None,
+                      jitter_prargs=(5, 5)) -> List[BlockSpec]:
+    """_autorun_add_RV_ins (emp.py:2628-2651) + SmartSetter.set_{Acceleration,Offset,Jitter,MOAV}."""
+    nins = data.nins
+    blocks = []
+    if acceleration:
+        ps = []
+        for i in range(acceleration):
+            name = "Acceleration" if i == 0 else f"Acceleration Order {i + 1}"
+            ps.append(_param(name, "Uniform", [-1, 1], None))
+        blocks.append(BlockSpec(type_="Acceleration", params=ps, number=acceleration))
+    lims = []
+    for nin in range(nins):
+        m = data.flag == (nin + 1)
+        lims.append(np.abs(data.y[m]).max())
+    blocks.append(BlockSpec(type_="Offset", number=nins,
+                            params=[_param(f"Offset {i + 1}", "Uniform", [-lims[i], lims[i]], None)
+                                    for i in range(nins)]))
+    if jitter:
+        blocks.append(BlockSpec(type_="Jitter", number=nins,
+                                params=[_param(f"Jitter {i + 1}", "Normal", [1e-5, lims[i]], list(jitter_prargs))
+                                        for i in range(nins)]))
+    if moav and moav.get("order", 0):
+        order, is_global = int(moav["order"]), bool(moav.get("global", False))
+        ps = []
+        for i, j in itertools.product(range(1 if is_global else nins), range(order)):
+            ps.append(_param(f"MACoefficient {i + 1} Order {j + 1}", "Uniform", [0.0, 0.3], None))
+            ps.append(_param(f"MATimescale {i + 1} Order {j + 1}", "Uniform", [5, 25], None))
+        blocks.append(BlockSpec(type_="MOAV", params=ps, number=nins, moav_order=order, moav_global=is_global))
+    return blocks
+
+
+def astrometry_blocks() -> List[BlockSpec]:
+    """add_offset_am / add_jitter_am (emp.py:1300-1311) + SmartSetter.set_Astrometry* (block_repo.py:835-850)."""
+    off = [_param(n, "Uniform", [-1e1, 1e1], [])
+           for n in ("Offset RA", "Offset DE", "Offset PLX", "Offset pm RA", "Offset pm DE")]
+    jit = [_param("Jitter Hipp", "Uniform", [0, 20], []), _param("Jitter Gaia", "Uniform", [0, 10], [])]
+    return [BlockSpec(type_="AstrometryOffset", params=off, number=5),
+            BlockSpec(type_="AstrometryJitter", params=jit, number=2)]
+
+
+def apply_conditions(spec: ModelSpec, conds: Sequence[Sequence]) -> None:
+    """Simulation.apply_conditions (emp.py:2790-2806): [param_name, attribute, value]."""
+    for b in spec.blocks:
+        for p in b.params:
+            for c in conds:
+                if p.name == c[0]:
+                    if c[1] not in ("limits", "prior", "prargs", "fixed", "init_pos"):
+                        raise UnsupportedModelError(f"condition on attribute '{c[1]}'")
+                    setattr(p, c[1], c[2])
+
+
+def finalize(spec: ModelSpec) -> ModelSpec:
+    """ReddModel.refresh__ (emp_model.py:223-330): fixed handling + prior normalisers."""
+    for b in spec.blocks:
+        for p in b.params:
+            if p.fixed is not None:  # Parameter_Block._handle_fixed_params (emp_model.py:75-80)
+                p.prior, p.limits = "Fixed", [float("nan"), float("nan")]
+            else:
+                p.prargs = finalize_prargs(p.prior, p.limits, p.prargs)
+        for a in b.additional:
+            a.prargs = finalize_prargs(a.prior, a.limits, a.prargs)
+    return spec
+
+
+def default_spec(data: RVData, kplan: int, parameterisation: int = 0, acceleration: int = 0,
+                 jitter: bool = True, moav: Optional[dict] = None, conditions: Sequence = (),
+                 eccentricity_limits=(0, 1), eccentricity_prargs=(0, 0.1), jitter_prargs=(5, 5),
+                 astrometry: bool = False) -> ModelSpec:
+    blocks = [keplerian_block(data, k + 1, parameterisation, list(eccentricity_limits),
+                              list(eccentricity_prargs), astrometry=astrometry) for k in range(kplan)]
+    blocks += instrument_blocks(data, acceleration, jitter, moav, jitter_prargs)
+    if astrometry:
+        blocks += astrometry_blocks()
+    spec = ModelSpec(blocks=blocks, nins=data.nins)
+    apply_conditions(spec, conditions)
+    return finalize(spec)
+
+
+class Simulation:
+    """The slice of `astroemperor.Simulation` (emp.py:2240-2917) that leads to the hot path."""
+
+    def __init__(self):
+        self.starname = None
+        self.read_loc = ""
+        self.instrument_names_RV = None
+        self.starmass = 1.0
+        self.keplerian_parameterisation = 0
+        self.acceleration = 0
+        self.switch_jitter = True
+        self.moav = {"order": 0, "global": False}
+        self.eccentricity_limits = [0, 1]
+        self.eccentricity_prargs = [0, 0.1]
+        self.jitter_prargs = [5, 5]
+        self.conds = []
+        self.cores__ = None  # accepted and ignored: walkers are evaluated on the GPU
+        self.engine__ = None
+        self.engine_config = {}
+        self.run_config = {}
+        self.device = 0
+        self.seed = None
+        self.data: Optional[RVData] = None
+        self.am_data = None
+        self.sampler = None
+        self.model: Optional[ModelSpec] = None
+        self.history = []  # one dict per model run by autorun
+        self.BIC = np.inf
+
+    # -- reference API --------------------------------------------------------------
+    def load_data(self, folder_name: str):
+        """`datafiles/<star>/RV/*.vels` under read_loc (qol_utils.py:16-100)."""
+        self.starname = folder_name
+        base = os.path.join(f"{self.read_loc}datafiles", folder_name)
+        self.data = load_rv_folder(os.path.join(base, "RV") + os.sep)
+        am_dir = os.path.join(base, "AM")
+        if os.path.isdir(am_dir) and os.listdir(am_dir):
+            from .amdata import load_am_folder
+            self.am_data = load_am_folder(am_dir + os.sep, common_t=self.data.common_t)
+
+    def set_engine(self, eng: str):
+        if eng != "reddemcee":
+            raise UnsupportedModelError(f"engine '{eng}': only the reddemcee PT path is on the device")
+        self.engine__ = "reddemcee"
+        # defaults of Simulation._set_engine_reddemcee (emp.py:2370-2388)
+        self.engine_config = {"setup": np.array([5, 100, 500, 2]), "ntemps": 5, "betas": None, "moves": None,
+                              "tsw_history": True, "smd_history": True, "adapt_tau": 1000, "adapt_nu": 1,
+                              "adapt_mode": 0, "progress": True}
+        self.run_config = {"burnin": None, "adaptation_batches": None, "adaptation_nsweeps": None,
+                           "thin": 1, "discard": 0.5, "logger_level": "CRITICAL"}
+
+    def add_condition(self, cond):
+        self.conds.append(list(cond))
+
+    def build_model(self, kplan: int) -> ModelSpec:
+        if self.data is None:
+            raise RuntimeError("load_data() first")
+        return default_spec(self.data, kplan, self.keplerian_parameterisation, self.acceleration,
+                            self.switch_jitter, self.moav if self.moav.get("order") else None, self.conds,
+                            self.eccentricity_limits, self.eccentricity_prargs, self.jitter_prargs,
+                            astrometry=self.am_data is not None)
+
+    def run(self, kplan: int):
+        """_run_engine_reddemcee (emp.py:2559-2582) without the script / child process."""
+        from .engine import LikelihoodEngine
+        from .sampler import PTSampler
+        if self.engine__ != "reddemcee":
+            raise RuntimeError("set_engine('reddemcee') first")
+        ntemps, nwalkers, nsweeps, nsteps = [int(v) for v in self.engine_config["setup"]]
+        if self.engine_config["betas"] is not None:
+            assert len(self.engine_config["betas"]) == ntemps, f"betas should have {ntemps} items"
+        self.model = self.build_model(kplan)
+        d = self.data
+        eng = LikelihoodEngine(self.model, d.t, d.y, d.yerr, d.flag, am=self.am_data, device=self.device)
+        cfg = self.engine_config
+        self.sampler = PTSampler(nwalkers, self.model.ndim, eng, ntemps=ntemps, betas=cfg["betas"],
+                                 tsw_history=cfg["tsw_history"], smd_history=cfg["smd_history"],
+                                 adapt_tau=cfg["adapt_tau"], adapt_nu=cfg["adapt_nu"],
+                                 adapt_mode=cfg["adapt_mode"], seed=self.seed)
+        self.sampler.D_ = self.model.prior_widths()  # emp.py:595-602
+        p1 = self.sampler.initial_positions(self.model)
+        self.sampler.run_mcmc(p1, nsweeps=nsweeps, nsteps=nsteps, progress=bool(cfg.get("progress")))
+        return self.sampler
+
+    def autorun(self, k_start=0, k_end=10):
+        """autorun loop (emp.py:2414-2460) reduced to: run k Keplerians, record max logL and
+        BIC = ndim ln n - 2 lnL_max (emp.py:1195), stop when BIC stops improving by > 5."""
+        assert k_start <= k_end, f"Invalid keplerian starting point: ({k_start}, {k_end})"
+        bic_old = np.inf
+        for k in range(k_start, k_end + 1):
+            s = self.run(k)
+            ll = s.get_log_like(flat=True)[0]
+            like_max = float(np.max(ll))
+            bic = self.model.ndim * np.log(len(self.data)) - 2 * like_max
+            self.history.append(dict(k=k, ndim=self.model.ndim, like_max=like_max, BIC=bic))
+            self.BIC = bic
+            if not (bic_old - bic > 5):
+                break
+            bic_old = bic
+        return self.history

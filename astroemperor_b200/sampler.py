@@ -1,0 +1,302 @@
+"""Device parallel-tempering sampler: the drop-in for `reddemcee.PTSampler` as EMPEROR
+constructs and drives it (emp.py:576-603 `_set_sampler_reddemcee`,
+support/endit_reddemcee.scr:3 `sampler.run_mcmc(p1, nsweeps=, nsteps=, progress=)`) and
+as the parent later reads it back (get_chain / get_log_like /
+get_log_prob / betas / get_betas / get_tsw / acceptance_fraction ...).
+
+State lives on the GPU for the whole run: `p[T,W,ndim]`, `logl[T,W]`, `logp[T,W]`.
+Per sweep the host supplies the random draws (draws.py), the device does
+nsteps x (propose, likelihood, accept) per half-ensemble and one swap sweep; the
+ladder adaptation needs only the T-1 swap counts and runs on the host exactly like
+the oracle (bit-identical beta history).
+
+With `torch.distributed` initialised (one process per GPU) the temperature ladder
+is sharded in contiguous blocks of T/G temperatures (dist.py): the stretch steps
+need no communication, the swap sweep all-gathers logL over NCCL and every rank
+replays the same plan.
+"""
+from __future__ import annotations
+
+import time as _time
+from typing import Optional
+
+import numpy as np
+
+from . import dist as _dist
+from .draws import SweepDraws, default_betas, draw_sweep, initial_positions
+
+
+class PTSampler:
+    def __init__(self, nwalkers: int, ndim: int, log_like, log_prior=None, ntemps: int = 1, pool=None,
+                 backend=None, betas=None, tsw_history: bool = True, smd_history: bool = True,
+                 adapt_tau: float = 1000, adapt_nu: float = 1, adapt_mode: int = 0, a: float = 2.0,
+                 seed: Optional[int] = None, random_state: Optional[np.random.RandomState] = None,
+                 store: str = "device", thin_by: int = 1, adapt: bool = True, group=None):
+        """`log_like` is the LikelihoodEngine (it carries the prior as well; `log_prior`,
+        `pool` and `backend` are accepted for signature compatibility and ignored — the
+        walkers are evaluated on the GPU, not through a multiprocessing pool)."""
+        import torch
+        from .engine import LikelihoodEngine
+        if not isinstance(log_like, LikelihoodEngine):
+            raise TypeError("log_like must be an astroemperor_b200.engine.LikelihoodEngine; the device "
+                            "sampler cannot call Python likelihoods (no CPU fallback)")
+        self.engine = log_like
+        if ndim != self.engine.ndim:
+            raise ValueError(f"ndim={ndim} but the engine's model has {self.engine.ndim} free parameters")
+        if nwalkers % 2 or nwalkers < 2:
+            raise ValueError("nwalkers must be even")
+        if adapt_mode != 0:
+            raise NotImplementedError("only adapt_mode=0 (equalise swap rates) is implemented")
+        self.nwalkers, self.ndim, self.ntemps = int(nwalkers), int(ndim), int(ntemps)
+        self.a = float(a)
+        self.adapt_tau, self.adapt_nu, self.adapt_mode, self.adapt = adapt_tau, adapt_nu, adapt_mode, adapt
+        self.tsw_history_bool, self.smd_history_bool = bool(tsw_history), bool(smd_history)
+        self.betas = (np.array(betas, dtype=np.float64) if betas is not None
+                      else default_betas(ndim, ntemps))
+        if len(self.betas) != self.ntemps:
+            raise ValueError(f"betas should have {ntemps} items")
+        self.random = random_state if random_state is not None else np.random.RandomState(seed)
+        self.D_ = None
+        self.store, self.thin_by = store, int(thin_by)
+        self.torch = torch
+        self.dev = self.engine.torch_device
+        self.shard = _dist.LadderShard(self.ntemps, group=group)
+        self.iteration = 0  # sweeps done
+        self.time = 0
+        self._chain = self._ll = self._lp = None
+        self._beta_hist, self._tsw_hist, self._smd_hist = [], [], []
+        self._n_accepted = None
+        self._n_steps = 0
+        self.timings = {"draws": 0.0, "h2d": 0.0}
+
+    # ------------------------------------------------------------------------------
+    def initial_positions(self, spec, max_repeats: int = 100) -> np.ndarray:
+        """set_init() + test_init() of the generated script (emp.py:617-684): redraw walkers whose
+        prior is -inf, at most `max_repeats` rounds."""
+        p0 = initial_positions(self.random, spec, self.ntemps, self.nwalkers)
+        for _ in range(max_repeats):
+            lp = self.engine.my_prior(p0.reshape(-1, self.ndim)).reshape(self.ntemps, self.nwalkers)
+            bad = ~np.isfinite(np.atleast_2d(lp))
+            if not bad.any():
+                break
+            fresh = initial_positions(self.random, spec, self.ntemps, self.nwalkers)
+            p0[bad] = fresh[bad]
+        else:
+            print("COULDNT FIND VALID INITIAL POSITION")
+        return p0
+
+    def _upload(self, arr, dtype=None):
+        t = self.torch.from_numpy(np.ascontiguousarray(arr))
+        return t.to(self.dev, non_blocking=True)
+
+    def _init_state(self, p0):
+        torch = self.torch
+        p0 = np.asarray(p0, dtype=np.float64)
+        if p0.shape != (self.ntemps, self.nwalkers, self.ndim):
+            raise ValueError(f"p0 must have shape {(self.ntemps, self.nwalkers, self.ndim)}")
+        sl = self.shard.local_slice
+        self.p = self._upload(p0[sl]).contiguous()
+        Tl = self.shard.n_local
+        self.logl = torch.empty((Tl, self.nwalkers), dtype=torch.float64, device=self.dev)
+        self.logp = torch.empty_like(self.logl)
+        self.engine.logl_batch_device(self.p.view(-1, self.ndim), self.logl.view(-1), self.logp.view(-1))
+        self.accepted = torch.zeros((Tl, self.nwalkers), dtype=torch.uint8, device=self.dev)
+        self._n_accepted = torch.zeros((Tl, self.nwalkers), dtype=torch.int64, device=self.dev)
+        self._p_alt = torch.empty_like(self.p)
+        self._ll_alt = torch.empty_like(self.logl)
+        self._lp_alt = torch.empty_like(self.logp)
+        self._src = torch.empty((self.ntemps, self.nwalkers), dtype=torch.int32, device=self.dev)
+        self._n_acc = torch.zeros((max(self.ntemps - 1, 1),), dtype=torch.int32, device=self.dev)
+        self._betas_dev = self._upload(self.betas)
+
+    def _alloc_store(self, nsweeps):
+        torch = self.torch
+        n = (nsweeps + self.thin_by - 1) // self.thin_by
+        Tl, W, nd = self.shard.n_local, self.nwalkers, self.ndim
+        if self.store == "device":
+            dev, pin = self.dev, False
+        elif self.store == "host":
+            dev, pin = "cpu", True
+        else:
+            self._chain = None
+            return
+        kw = dict(dtype=torch.float64, device=dev)
+        if pin:
+            kw["pin_memory"] = True
+        new_chain = torch.empty((n, Tl, W, nd), **kw)
+        new_ll = torch.empty((n, Tl, W), **kw)
+        new_lp = torch.empty((n, Tl, W), **kw)
+        if self._chain is not None:
+            self._chain = torch.cat([self._chain[:self._stored], new_chain])
+            self._ll = torch.cat([self._ll[:self._stored], new_ll])
+            self._lp = torch.cat([self._lp[:self._stored], new_lp])
+        else:
+            self._chain, self._ll, self._lp = new_chain, new_ll, new_lp
+            self._stored = 0
+
+    # ------------------------------------------------------------------------------
+    def sweep(self, draws: SweepDraws):
+        """nsteps stretch steps of every local temperature + one swap sweep + adaptation."""
+        torch = self.torch
+        eng = self.engine
+        sl = self.shard.local_slice
+        t0 = _time.perf_counter()
+        d_half = self._upload(draws.half_idx[:, sl])
+        d_zz = self._upload(draws.zz[:, sl])
+        d_rint = self._upload(draws.rint[:, sl])
+        d_fac = self._upload(draws.factors[:, sl])
+        d_lnu = self._upload(draws.lnu[:, sl])
+        self.timings["h2d"] += _time.perf_counter() - t0
+        nsteps = draws.zz.shape[0]
+        for s in range(nsteps):
+            eng.pt_stretch_step(self.p, self.logl, self.logp, self._betas_dev[sl], d_half[s], d_zz[s], d_rint[s],
+                                d_fac[s], d_lnu[s], self.accepted)
+            self._n_accepted += self.accepted
+            self._n_steps += 1
+        n_acc = None
+        if self.ntemps > 1:
+            d_perm = self._upload(draws.perm)
+            d_lnus = self._upload(draws.lnu_swap)
+            logl_all = self.shard.all_gather_rows(self.logl)  # [T, W]; NCCL all-gather when sharded
+            eng.pt_swap_plan(logl_all, self._betas_dev, d_perm, d_lnus, self._src, self._n_acc)
+            self._apply_plan()
+            n_acc = self._n_acc.cpu().numpy()[: self.ntemps - 1]  # syncs: 4*(T-1) bytes
+        self.time += 1
+        self.iteration += 1
+        if n_acc is not None:
+            ratios = n_acc / self.nwalkers
+            if self.tsw_history_bool:
+                self._tsw_hist.append(ratios)
+            if self.adapt and self.ntemps > 2:
+                self.betas = _adapt_ladder(self.betas, ratios, self.time, self.adapt_tau, self.adapt_nu)
+                self._betas_dev = self._upload(self.betas)
+        self._beta_hist.append(self.betas.copy())
+        return n_acc
+
+    def _apply_plan(self):
+        eng, sh = self.engine, self.shard
+        if sh.world == 1:
+            eng.pt_gather_rows(self._src.view(-1), self.p.view(-1, self.ndim), self.logl.view(-1),
+                               self.logp.view(-1), self._p_alt.view(-1, self.ndim), self._ll_alt.view(-1),
+                               self._lp_alt.view(-1))
+        else:
+            rows = self.torch.cat([self.p.view(-1, self.ndim), self.logl.view(-1, 1), self.logp.view(-1, 1)], 1)
+            staged, src_local = sh.exchange_rows(self._src, rows, self.nwalkers)
+            pin = staged[:, : self.ndim].contiguous()
+            llin = staged[:, self.ndim].contiguous()
+            lpin = staged[:, self.ndim + 1].contiguous()
+            eng.pt_gather_rows(src_local, pin, llin, lpin, self._p_alt.view(-1, self.ndim),
+                               self._ll_alt.view(-1), self._lp_alt.view(-1))
+        self.p, self._p_alt = self._p_alt, self.p
+        self.logl, self._ll_alt = self._ll_alt, self.logl
+        self.logp, self._lp_alt = self._lp_alt, self.logp
+
+    def run_mcmc(self, p0, nsweeps: int, nsteps: int = 1, progress: bool = False):
+        if p0 is not None:
+            self._init_state(p0)
+        elif not hasattr(self, "p"):
+            raise ValueError("first call needs initial positions")
+        self._alloc_store(nsweeps)
+        it = range(nsweeps)
+        if progress:
+            try:
+                from tqdm import tqdm
+                it = tqdm(it, total=nsweeps)
+            except Exception:
+                pass
+        for k in it:
+            t0 = _time.perf_counter()
+            draws = draw_sweep(self.random, self.ntemps, self.nwalkers, self.ndim, nsteps, self.a,
+                               swap=self.ntemps > 1)
+            self.timings["draws"] += _time.perf_counter() - t0
+            self.sweep(draws)
+            if self._chain is not None and (k % self.thin_by == 0):
+                j = self._stored
+                self._chain[j].copy_(self.p, non_blocking=True)
+                self._ll[j].copy_(self.logl, non_blocking=True)
+                self._lp[j].copy_(self.logp, non_blocking=True)
+                self._stored += 1
+        self.torch.cuda.synchronize(self.dev)
+        return self.p
+
+    # ---- read-back API the reference's parent process uses --------
+    def _get(self, buf, discard, thin, flat):
+        if buf is None:
+            raise RuntimeError("chain storage is disabled (store=None)")
+        x = buf[: self._stored][discard::thin]
+        x = self.shard.gather_to_all(x, dim=1) if self.shard.world > 1 else x
+        x = x.cpu().numpy()
+        x = np.swapaxes(x, 0, 1)  # [T, n, W, ...]
+        if flat:
+            x = x.reshape((x.shape[0], x.shape[1] * x.shape[2]) + x.shape[3:])
+        return x
+
+    def get_chain(self, discard=0, thin=1, flat=False):
+        return self._get(self._chain, discard, thin, flat)
+
+    def get_log_like(self, discard=0, thin=1, flat=False):
+        return self._get(self._ll, discard, thin, flat)
+
+    def get_log_prob(self, discard=0, thin=1, flat=False):
+        """Tempered posterior beta*logL + logP per stored sample."""
+        ll = self._get(self._ll, discard, thin, False)
+        lp = self._get(self._lp, discard, thin, False)
+        bh = np.array(self._beta_hist)[:: self.thin_by][discard::thin]  # [n, T]
+        out = bh.T[:, :, None] * ll + lp
+        return out.reshape(out.shape[0], -1) if flat else out
+
+    def get_log_prior(self, discard=0, thin=1, flat=False):
+        return self._get(self._lp, discard, thin, flat)
+
+    def get_betas(self, discard=0):
+        return np.array(self._beta_hist)[discard:]
+
+    def get_tsw(self, discard=0):
+        return np.array(self._tsw_hist)[discard:]
+
+    def get_smd(self, discard=0):
+        return np.array(self._smd_hist)[discard:]
+
+    @property
+    def acceptance_fraction(self):
+        a = self._n_accepted.double() / max(self._n_steps, 1)
+        if self.shard.world > 1:
+            a = self.shard.gather_to_all(a, dim=0)
+        return a.cpu().numpy()
+
+    def state_numpy(self):
+        """(p, logl, logp) of the whole ladder as NumPy arrays."""
+        p, ll, lp = self.p, self.logl, self.logp
+        if self.shard.world > 1:
+            p, ll, lp = (self.shard.gather_to_all(x, dim=0) for x in (p, ll, lp))
+        return p.cpu().numpy(), ll.cpu().numpy(), lp.cpu().numpy()
+
+    def get_evidence_ti(self, discard=0):
+        """Thermodynamic-integration log-evidence: trapezoid of <logL>_beta over beta
+        (the simplest of the estimators emp.py:1432-1447 falls back through)."""
+        ll = self.get_log_like(discard=discard)  # [T, n, W]
+        mean_ll = ll.reshape(ll.shape[0], -1).mean(axis=1)
+        b = self.betas
+        order = np.argsort(b)
+        b, m = b[order], mean_ll[order]
+        if b[0] > 0:
+            b, m = np.concatenate([[0.0], b]), np.concatenate([[m[0]], m])
+        logz = float(np.trapezoid(m, b)) if hasattr(np, "trapezoid") else float(np.trapz(m, b))
+        b2, m2 = b[::2], m[::2]
+        if b2[-1] != b[-1]:
+            b2, m2 = np.append(b2, b[-1]), np.append(m2, m[-1])
+        logz2 = float(np.trapezoid(m2, b2)) if hasattr(np, "trapezoid") else float(np.trapz(m2, b2))
+        return logz, abs(logz - logz2)
+
+
+def _adapt_ladder(betas, ratios, time, adapt_tau, adapt_nu):
+    """Vousden, Farr & Mandel (2016) ladder dynamics in reddemcee's (adapt_tau, adapt_nu)
+    parameterisation; same arithmetic as oracle/pt_oracle.py::adapt_ladder."""
+    betas = betas.copy()
+    decay = adapt_tau / (time + adapt_tau)
+    kappa = decay / adapt_nu
+    dSs = kappa * (ratios[:-1] - ratios[1:])
+    deltaTs = np.diff(1 / betas[:-1])
+    deltaTs = deltaTs * np.exp(dSs)
+    betas[1:-1] = 1 / (np.cumsum(deltaTs) + 1 / betas[0])
+    return betas

@@ -160,6 +160,9 @@ const char *emp_last_error(void);
 int emp_abi_version(void);
 /* The CUDA stream (cudaStream_t as void*) all work of this handle is queued on. */
 int emp_stream(EmpHandle *h, void **stream);
+/* Queue all further work of this handle on a caller-owned stream (e.g. torch's current
+ * stream, so that torch copies and these kernels are ordered without extra syncs). */
+int emp_set_stream(EmpHandle *h, void *stream);
 int emp_synchronize(EmpHandle *h);
 
 /* ---- likelihood / prior -------------------------------------------------- */
@@ -180,39 +183,47 @@ int emp_model_host(EmpHandle *h, const double *theta_host, double *model_host, d
 /* ---- parallel-tempering step -------------------------------------------- */
 
 /* One emcee RedBlue stretch-move step of every temperature held by this handle
- * (reddemcee.PTSampler / emcee 3.1.6 StretchMove(a=2), SURVEY.md §3.3 and §8a
- * row A15), from host-supplied draws that were already copied to the device:
- *   p      [T, W, ndim]  walker positions (updated in place)
- *   logl   [T, W], logp [T, W]  (updated in place)
- *   betas  [T]
- *   split  [T, W] int32   0/1: which half a walker is in (shuffled arange(W) % 2)
- *   zz     [T, W]         stretch factor of the walker, ((a-1)u+1)^2/a
- *   rint   [T, W] int32   index of the partner inside the complementary half
- *   lnu    [T, W]         log of the accept uniform
- *   accepted [T, W] uint8 (output; 1 where the proposal was accepted)
- * Both halves are processed (half 0 then half 1, emcee order). */
+ * (reddemcee.PTSampler / emcee 3.1.6 RedBlueMove + StretchMove(a=2), SURVEY.md §3.3 and §8a
+ * row A15), from host-supplied draws that were already copied to the device.  H = W/2.
+ *   p        [T, W, ndim]  walker positions (updated in place)
+ *   logl     [T, W], logp [T, W]  (updated in place)
+ *   betas    [T]
+ *   half_idx [T, 2, H] int32  walkers of split 0 / split 1, ascending (the shuffled
+ *                             `arange(W) % 2` of RedBlueMove.propose, as index lists)
+ *   zz       [T, 2, H]     stretch factor ((a-1)u+1)^2/a of the j-th walker of split s
+ *   rint     [T, 2, H] int32  partner index inside the complementary half
+ *   factors  [T, 2, H]     (ndim-1)*ln zz   (host computes the log so the decision is bit-exact)
+ *   lnu      [T, 2, H]     log of the accept uniform
+ *   accepted [T, W] uint8  (output; 1 where the proposal was accepted)
+ * Split 0 is proposed/evaluated/accepted first, then split 1 (emcee order):
+ * 2 x (propose kernel, likelihood kernel, accept kernel) on the handle's stream. */
 int emp_pt_stretch_step(EmpHandle *h, int32_t T, int32_t W, double *p, double *logl, double *logp,
-                        const double *betas, const int32_t *split, const double *zz,
-                        const int32_t *rint, const double *lnu, uint8_t *accepted);
+                        const double *betas, const int32_t *half_idx, const double *zz,
+                        const int32_t *rint, const double *factors, const double *lnu,
+                        uint8_t *accepted);
 
 /* Adjacent-temperature swap sweep, hot -> cold (ptemcee lineage).
- *   logl_all [T, W]   log-likelihood of every temperature (read only)
+ *   logl_all [T, W]   log-likelihood of every temperature of the ladder (read only)
  *   betas    [T]
  *   perm     [T-1, 2, W] int32  pair j couples temperature i=j+1 with i-1=j:
  *                               perm[j,0,:] indexes walkers of i, perm[j,1,:] of i-1
  *   lnu      [T-1, W]
  * Outputs:
- *   src      [T, W] int32  flat index (t*W + w) of the walker that ends up in slot (t, w)
+ *   src      [T, W] int32  flat index (t*W + w) of the slot whose walker ends up in (t, w)
  *   n_acc    [T-1] int32   accepted swaps per pair
  * Every rank of a sharded ladder replays this identically from the all-gathered logl. */
 int emp_pt_swap_plan(EmpHandle *h, int32_t T, int32_t W, const double *logl_all,
                      const double *betas, const int32_t *perm, const double *lnu, int32_t *src,
                      int32_t *n_acc);
-/* Apply a swap plan to local state: rows t0..t0+T_loc-1 of the ladder.
- * dst[t,w,:] = src_rows[src[t0+t, w]] for p, logl, logp (out-of-place). */
-int emp_pt_apply_plan(EmpHandle *h, int32_t T_loc, int32_t W, int32_t t0, const int32_t *src,
-                      const double *p_in, const double *logl_in, const double *logp_in,
-                      double *p_out, double *logl_out, double *logp_out);
+/* Row gather that applies a swap plan: for r in [0, n_rows):
+ *   p_out[r,:] = p_in[src[r],:], logl_out[r] = logl_in[src[r]], logp_out[r] = logp_in[src[r]].
+ * `src` indexes rows of the *_in arrays (the caller translates global plan indices when the
+ * ladder is sharded and remote rows were staged behind the local ones). */
+int emp_pt_gather_rows(EmpHandle *h, int64_t n_rows, int32_t ndim, const int32_t *src,
+                       const double *p_in, const double *logl_in, const double *logp_in,
+                       double *p_out, double *logl_out, double *logp_out);
+/* Proposals whose log-likelihood came out NaN (rejected; emcee would raise). */
+int emp_nan_count(EmpHandle *h, uint32_t *count);
 
 /* ---- introspection -------------------------------------------------------- */
 /* Number of kernels this handle has launched since creation (bench.py gpu_launches). */
