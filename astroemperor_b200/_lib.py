@@ -56,7 +56,9 @@ SYMBOLS = [
     ("emp_nan_count", ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint32)]),
     ("emp_launch_count", ctypes.c_int, [_P, ctypes.POINTER(_I64)]),
     ("emp_set_timing", ctypes.c_int, [_P, ctypes.c_int]),
-    ("emp_last_logl_ms", ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_float)]),
+    ("emp_timing_collect", ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_I64)]),
+    ("emp_counters", ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint64)]),
+    ("emp_fp64_peak", ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
 ]
 
 

@@ -51,12 +51,19 @@ struct EmpHandle {
   int64_t cap_q = 0;
   double* d_llwork = nullptr;
   int64_t cap_llwork = 0;
-  uint32_t* d_nan = nullptr;
+  int32_t* d_index = nullptr;  // compact list of evaluations inside the prior support
+  int32_t* d_nact = nullptr;   // its length
+  int64_t cap_index = 0;
+  uint32_t* d_nan = nullptr;          // [0] NaN proposals
+  unsigned long long* d_cnt = nullptr; // [0] proposals, [1] proposals inside the prior support, [2] accepted
   AmDevice am;
   int num_sms = 148;
   int64_t launches = 0;
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // per-launch timing of the likelihood kernel (bench.py roofline): ring of event pairs
+  std::vector<cudaEvent_t> tev;
+  size_t tev_used = 0;
 };
 
 extern "C" const char* emp_last_error(void) { return g_last_error.c_str(); }
@@ -175,6 +182,8 @@ extern "C" int emp_create(const EmpModelDesc* desc, const double* t, const doubl
   CUDA_TRY(cudaMemcpy(h->d_desc, desc, sizeof(EmpModelDesc), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(&h->d_nan, sizeof(uint32_t)));
   CUDA_TRY(cudaMemset(h->d_nan, 0, sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&h->d_cnt, 4 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(h->d_cnt, 0, 4 * sizeof(unsigned long long)));
 
   CUDA_TRY(cudaFuncSetAttribute(logl_rv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 int(kLoglSmemBytes)));
@@ -231,24 +240,48 @@ extern "C" int emp_synchronize(EmpHandle* h) {
 static int launch_logl(EmpHandle* h, const double* theta_dev, int64_t n_eval, double* logl_dev,
                        double* logp_dev) {
   if (n_eval == 0) return EMP_OK;
+  if (n_eval > 2147483647LL - kWalkerWarps) return fail(EMP_EINVAL, "n_eval too large for one launch");
+  if (n_eval > h->cap_index) {
+    cudaFree(h->d_index);
+    h->d_index = nullptr;
+    h->cap_index = 0;
+    CUDA_TRY(cudaMalloc(&h->d_index, size_t(n_eval) * sizeof(int32_t)));
+    h->cap_index = n_eval;
+  }
+  if (!h->d_nact) CUDA_TRY(cudaMalloc(&h->d_nact, sizeof(int32_t)));
+  CUDA_TRY(cudaMemsetAsync(h->d_nact, 0, sizeof(int32_t), h->stream));
+  const unsigned grid_p = unsigned((n_eval + kPriorWarps - 1) / kPriorWarps);
+  prior_compact_kernel<<<grid_p, kPriorWarps * 32, 0, h->stream>>>(h->d_desc, theta_dev, n_eval, logl_dev, logp_dev,
+                                                                 h->d_index, h->d_nact);
+  h->launches += 1;
   LoglParams P;
   P.desc = h->d_desc;
   P.tiles = h->d_tiles;
   P.n_points = h->n;
   P.n_tiles = h->n_tiles;
   P.theta = theta_dev;
-  P.eval_index = nullptr;
-  P.n_eval = n_eval;
+  P.eval_index = h->d_index;
+  P.n_active = h->d_nact;
   P.logl = logl_dev;
-  P.logp = logp_dev;
-  P.logp_in = nullptr;
   P.t0 = h->t0;
   P.ll_const = h->ll_const;
-  const int64_t grid = (n_eval + kWalkerWarps - 1) / kWalkerWarps;
-  if (grid > 2147483647LL) return fail(EMP_EINVAL, "n_eval too large for one launch");
-  if (h->timing) CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-  logl_rv_kernel<<<dim3((unsigned)grid), dim3(kLoglThreads), kLoglSmemBytes, h->stream>>>(P);
-  if (h->timing) CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  const unsigned grid = unsigned((n_eval + kWalkerWarps - 1) / kWalkerWarps);
+  cudaEvent_t e0 = h->ev0, e1 = h->ev1;
+  if (h->timing) {
+    if (h->tev_used + 2 > h->tev.size()) {
+      for (int k = 0; k < 2; ++k) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        h->tev.push_back(e);
+      }
+    }
+    e0 = h->tev[h->tev_used];
+    e1 = h->tev[h->tev_used + 1];
+    h->tev_used += 2;
+    CUDA_TRY(cudaEventRecord(e0, h->stream));
+  }
+  logl_rv_kernel<<<grid, kLoglThreads, kLoglSmemBytes, h->stream>>>(P);
+  if (h->timing) CUDA_TRY(cudaEventRecord(e1, h->stream));
   h->launches += 1;
   CUDA_TRY(cudaGetLastError());
   if (h->desc.am_enabled) {
@@ -361,7 +394,7 @@ extern "C" int emp_pt_stretch_step(EmpHandle* h, int32_t T, int32_t W, double* p
     if (rc) return rc;
     blocks = int(std::min<int64_t>((n_prop * 32 + threads - 1) / threads, max_blocks));
     pt_accept_kernel<<<blocks, threads, 0, h->stream>>>(p, logl, logp, T, W, ndim, split, half_idx, betas, factors,
-                                                        lnu, h->d_q, h->d_llq, h->d_lpq, accepted, h->d_nan);
+                                                        lnu, h->d_q, h->d_llq, h->d_lpq, accepted, h->d_nan, h->d_cnt);
     h->launches += 1;
   }
   CUDA_TRY(cudaGetLastError());
@@ -421,13 +454,76 @@ extern "C" int emp_launch_count(EmpHandle* h, int64_t* count) {
 extern "C" int emp_set_timing(EmpHandle* h, int enable) {
   if (!h) return fail(EMP_EINVAL, "NULL handle");
   h->timing = enable != 0;
+  h->tev_used = 0;
   return EMP_OK;
 }
 
-extern "C" int emp_last_logl_ms(EmpHandle* h, float* ms) {
-  if (!h || !ms) return fail(EMP_EINVAL, "NULL argument");
+extern "C" int emp_timing_collect(EmpHandle* h, double* total_ms, int64_t* n_launches) {
+  if (!h || !total_ms || !n_launches) return fail(EMP_EINVAL, "NULL argument");
   CUDA_TRY(cudaSetDevice(h->device));
-  CUDA_TRY(cudaEventSynchronize(h->ev1));
-  CUDA_TRY(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  double tot = 0.0;
+  for (size_t i = 0; i + 1 < h->tev_used; i += 2) {
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->tev[i], h->tev[i + 1]));
+    tot += ms;
+  }
+  *total_ms = tot;
+  *n_launches = int64_t(h->tev_used / 2);
+  h->tev_used = 0;
+  return EMP_OK;
+}
+
+extern "C" int emp_counters(EmpHandle* h, uint64_t* out4) {
+  if (!h || !out4) return fail(EMP_EINVAL, "NULL argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  unsigned long long c[4];
+  uint32_t nn = 0;
+  CUDA_TRY(cudaMemcpyAsync(c, h->d_cnt, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(&nn, h->d_nan, sizeof(nn), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  out4[0] = c[0]; out4[1] = c[1]; out4[2] = c[2]; out4[3] = nn;
+  return EMP_OK;
+}
+
+// FP64 FMA peak of the device: the roofline denominator of this path (SURVEY.md §8d row D3;
+// MEASURED_PEAKS.json carries no FP64 entry).  8 independent DFMA chains per thread.
+__global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+         x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+extern "C" int emp_fp64_peak(int device, double* tflops) {
+  if (!tflops) return fail(EMP_EINVAL, "NULL argument");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  const int threads = 512, blocks = prop.multiProcessorCount * 4, iters = 1 << 16;
+  double* d_out = nullptr;
+  CUDA_TRY(cudaMalloc(&d_out, size_t(blocks) * threads * sizeof(double)));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0));
+    fp64_peak_kernel<<<blocks, threads>>>(d_out, iters, 0.999999, 1e-7);
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 8.0 * double(iters) * double(blocks) * threads;
+    const double tf = fl / (ms * 1e-3) * 1e-12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  *tflops = best;
   return EMP_OK;
 }

@@ -29,6 +29,19 @@ constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52: (x + kMagic) - kMa
 constexpr double kF1 = 3.0 * kPi / (kPi - 6.0 / kPi);
 constexpr double kF2 = 1.6 / (kPi - 6.0 / kPi);
 
+// Hot-loop FP64 literals live in constant memory so that DFMA/DADD take them as a
+// constant-bank operand (a 64-bit immediate would cost two UMOVs per use).
+//   (v - sin v)/v^3 = 1/3! - w/5! + w^2/7! - ...   (8 terms: next term < 1e-18 relative on [0, pi/4])
+//   (1 - cos v)/v^2 = 1/2! - w/4! + w^2/6! - ...   (9 terms)
+__constant__ double kSinC[8] = {-1.0 / 355687428096000.0, 1.0 / 1307674368000.0, -1.0 / 6227020800.0,
+                                1.0 / 39916800.0,         -1.0 / 362880.0,       1.0 / 5040.0,
+                                -1.0 / 120.0,             1.0 / 6.0};
+__constant__ double kCosC[9] = {1.0 / 6402373705728000.0, -1.0 / 20922789888000.0, 1.0 / 87178291200.0,
+                                -1.0 / 479001600.0,       1.0 / 3628800.0,         -1.0 / 40320.0,
+                                1.0 / 720.0,              -1.0 / 24.0,             0.5};
+// [0] pi [1] 2pi [2] pi/2 [3] pi/4 [4] 1/(2pi) [5] rint magic [6] F1 [7] 1/6 [8] 1/24 [9] 1 - pi/2
+__constant__ double kC[10] = {kPi, kTwoPi, kPi2, kPi4, kInvTwoPi, kMagic, kF1, 1.0 / 6.0, 1.0 / 24.0, 1.0 - kPi2};
+
 // Per (walker, Keplerian) constants, computed once in the kernel prologue.
 struct KepConst {
   double freq;    // 2 pi / per
@@ -132,44 +145,31 @@ __device__ __noinline__ double mod_two_pi_slow(double M) {
 // M - k*c has at most 53 significant bits (multiple of ulp(c), |.| < 8), so the FMA and
 // the conditional +c reproduce fmod()+fix-up bit for bit.
 __device__ __forceinline__ double mod_two_pi(double M) {
-  double kd = __dadd_rn(__dadd_rn(__dmul_rn(M, kInvTwoPi), kMagic), -kMagic);
-  double r = __fma_rn(-kd, kTwoPi, M);
-  if (r < 0.0) r = __dadd_rn(r, kTwoPi);
+  double kd = __dsub_rn(__dadd_rn(__dmul_rn(M, kC[4]), kC[5]), kC[5]);
+  double r = __fma_rn(-kd, kC[1], M);
+  if (r < 0.0) r = __dadd_rn(r, kC[1]);
   if (!(fabs(M) < 1.0e12)) r = mod_two_pi_slow(M);
   return r;
 }
 
 // ---- x - sin x and 1 - cos x on [0, pi] (Nijenhuis-style folding, Taylor core) ----------
 __device__ __forceinline__ void sin_cos_reduc(double x, double& sn, double& cs) {
-  bool bigg = x > kPi2;
-  double u = bigg ? kPi - x : x;
-  bool big = u > kPi4;
-  double v = big ? kPi2 - u : u;
+  bool bigg = x > kC[2];
+  double u = bigg ? kC[0] - x : x;
+  bool big = u > kC[3];
+  double v = big ? kC[2] - u : u;
   double w = v * v;
-  // (v - sin v)/v^3 = 1/3! - w/5! + w^2/7! - ...   (8 terms: next term < 1e-18 relative)
-  double ps = -1.0 / 355687428096000.0;            // -1/17!
-  ps = fma(ps, w, 1.0 / 1307674368000.0);          // 1/15!
-  ps = fma(ps, w, -1.0 / 6227020800.0);            // -1/13!
-  ps = fma(ps, w, 1.0 / 39916800.0);               // 1/11!
-  ps = fma(ps, w, -1.0 / 362880.0);                // -1/9!
-  ps = fma(ps, w, 1.0 / 5040.0);                   // 1/7!
-  ps = fma(ps, w, -1.0 / 120.0);                   // -1/5!
-  ps = fma(ps, w, 1.0 / 6.0);                      // 1/3!
-  // (1 - cos v)/v^2 = 1/2! - w/4! + w^2/6! - ...   (9 terms)
-  double pc = 1.0 / 6402373705728000.0;            // 1/18!
-  pc = fma(pc, w, -1.0 / 20922789888000.0);        // -1/16!
-  pc = fma(pc, w, 1.0 / 87178291200.0);            // 1/14!
-  pc = fma(pc, w, -1.0 / 479001600.0);             // -1/12!
-  pc = fma(pc, w, 1.0 / 3628800.0);                // 1/10!
-  pc = fma(pc, w, -1.0 / 40320.0);                 // -1/8!
-  pc = fma(pc, w, 1.0 / 720.0);                    // 1/6!
-  pc = fma(pc, w, -1.0 / 24.0);                    // -1/4!
-  pc = fma(pc, w, 0.5);                            // 1/2!
+  double ps = kSinC[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) ps = fma(ps, w, kSinC[i]);
+  double pc = kCosC[0];
+#pragma unroll
+  for (int i = 1; i < 9; ++i) pc = fma(pc, w, kCosC[i]);
   double ss = ps * (v * w);
   double cc = pc * w;
   double s1 = big ? (u - 1.0) + cc : ss;
-  double c1 = big ? ((1.0 - kPi2) + u) + ss : cc;
-  sn = bigg ? fma(2.0, x, -kPi) + s1 : s1;
+  double c1 = big ? (kC[9] + u) + ss : cc;
+  sn = bigg ? fma(2.0, x, -kC[0]) + s1 : s1;
   cs = bigg ? 2.0 - c1 : c1;
 }
 
@@ -177,12 +177,12 @@ __device__ __forceinline__ void sin_cos_reduc(double x, double& sn, double& cs) 
 __device__ __forceinline__ double kep_rv(const KepConst& k, double t) {
   const double M = mean_anomaly(k, t);
   const double r0 = mod_two_pi(M);
-  const bool high = r0 > kPi;
-  const double Mr = high ? __dsub_rn(kTwoPi, r0) : r0;
+  const bool high = r0 > kC[0];
+  const double Mr = high ? __dsub_rn(kC[1], r0) : r0;
 
   // Markley starter (kepler.py get_markley_starter), one division
   const double M2 = Mr * Mr;
-  const double alpha = fma(k.c2, kPi - Mr, kF1);
+  const double alpha = fma(k.c2, kC[0] - Mr, kC[6]);
   const double d = fma(alpha, k.e, k.ome3);
   const double ad = alpha * d;
   const double r = fma(3.0 * ad, d - k.ome, M2) * Mr;
@@ -203,14 +203,15 @@ __device__ __forceinline__ double kep_rv(const KepConst& k, double t) {
   const double f2 = k.e * s0;
   const double f3 = 1.0 - f1;
   const double d3 = -f0 * f1 / fma(f1, f1, -0.5 * f0 * f2);
-  const double d4 = -f0 / fma(d3 * d3, f3 * (1.0 / 6.0), fma(0.5 * d3, f2, f1));
+  const double f36 = f3 * kC[7], f22 = 0.5 * f2;
+  const double d4 = -f0 / fma(d3 * d3, f36, fma(d3, f22, f1));
   const double d42 = d4 * d4;
-  const double dE = -f0 / fma(-d42 * d4, f2 * (1.0 / 24.0), fma(d42, f3 * (1.0 / 6.0), fma(0.5 * d4, f2, f1)));
+  const double dE = -f0 / fma(-d42 * d4, f2 * kC[8], fma(d42, f36, fma(d4, f22, f1)));
 
   // rotate (sin E0, 1 - cos E0) by dE: |dE| <= 5e-4, 4th order is exact to < 1e-20
   const double dE2 = dE * dE;
-  const double sd = fma(-dE * dE2, 1.0 / 6.0, dE);             // sin dE
-  const double cdm = dE2 * fma(dE2, -1.0 / 24.0, 0.5);         // 1 - cos dE
+  const double sd = fma(-dE * dE2, kC[7], dE);                 // sin dE
+  const double cdm = dE2 * fma(dE2, -kC[8], 0.5);              // 1 - cos dE
   const double c0 = 1.0 - cE;                                  // cos E0
   const double s1 = s0 + fma(c0, sd, -s0 * cdm);               // sin E1
   const double cE1 = cE + fma(s0, sd, c0 * cdm);               // 1 - cos E1
@@ -293,12 +294,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra WAIT_DONE;\n"
       "bra WAIT_LOOP;\n"
       "WAIT_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)  // suspend-time hint: the waiting thread sleeps in hardware
       : "memory");
 }
 __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,

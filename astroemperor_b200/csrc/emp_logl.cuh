@@ -1,15 +1,21 @@
-// emp_logl.cuh — batched my_likelihood + my_prior kernel.
+// emp_logl.cuh — batched my_likelihood + my_prior kernels.
 //
-// Work decomposition:
-//   * one WARP per walker (theta row); lanes own consecutive pairs of datapoints, so the
-//     Keplerian constants are warp-uniform and every shared-memory read is a conflict-free
-//     128-bit access;
-//   * one CTA = NW walker warps + 1 producer warp.  The producer streams the packed data set
-//     (t | y | yerr^2 | instrument id per tile) from L2 into a STAGES-deep shared-memory ring
-//     with 1-D bulk TMA (cp.async.bulk + mbarrier complete_tx); all NW walkers of the CTA
-//     consume the same tile, so each tile is fetched once per NW evaluations;
-//   * chi^2 and sum(log err2) are accumulated per lane, reduced with warp shuffles in a fixed
-//     order (bit-reproducible run to run), one store per walker.
+// Two launches per batch:
+//   1. prior_compact_kernel — one warp per evaluation: re-insert the fixed parameters, run the
+//      prior program, write logp; rows with prior == -inf get logl = -inf and are dropped
+//      (emcee never evaluates the likelihood there), the others are appended to a compact
+//      index list.  Without this pass ~40 % of the proposals of a young chain sit outside the
+//      prior box and their warps would idle next to working ones.
+//   2. logl_rv_kernel — one WARP per surviving evaluation; lanes own consecutive pairs of
+//      datapoints, so the Keplerian constants are warp-uniform and every shared-memory read is
+//      a conflict-free 128-bit access.  A CTA is kWalkerWarps walkers that consume the same
+//      stream of data tiles (t | y | yerr^2 | instrument id), staged from L2 into a
+//      kStages-deep shared-memory ring by 1-D bulk TMA (cp.async.bulk + mbarrier complete_tx):
+//      each tile is fetched once per kWalkerWarps evaluations.  There is no producer warp:
+//      lane 0 of warp 0 refills the stage that every warp released one tile ago, so it only
+//      ever blocks on a warp that is two tiles behind.
+//      chi^2 and sum(log err2) are accumulated per lane and reduced with warp shuffles in a
+//      fixed order: results are bit-reproducible run to run and independent of the slot.
 #pragma once
 #include "emp_device.cuh"
 
@@ -18,8 +24,8 @@ namespace emp {
 constexpr int kTilePoints = 512;                       // datapoints per TMA tile
 constexpr int kTileBytes = kTilePoints * (3 * 8 + 4);  // t, y, e2 (FP64) + ins (int32)
 constexpr int kStages = 3;
-constexpr int kWalkerWarps = 8;                        // walker warps per CTA
-constexpr int kLoglThreads = (kWalkerWarps + 1) * 32;  // + 1 producer warp
+constexpr int kWalkerWarps = 8;                        // walkers per CTA
+constexpr int kLoglThreads = kWalkerWarps * 32;
 
 // per-walker constants in shared memory (one slot per walker warp)
 struct WalkerConst {
@@ -32,34 +38,33 @@ struct WalkerConst {
 };
 
 struct LoglParams {
-  const EmpModelDesc* desc;  // device copy
-  const char* tiles;         // packed tiles, kTileBytes each, 128B aligned
+  const EmpModelDesc* desc;   // device copy
+  const char* tiles;          // packed tiles, kTileBytes each
   int64_t n_points;
   int32_t n_tiles;
-  const double* theta;       // [n_eval, ndim_free]
-  const int32_t* eval_index; // optional compaction map (NULL: identity)
-  int64_t n_eval;
+  const double* theta;        // [n_eval, ndim_free]
+  const int32_t* eval_index;  // compact list of rows to evaluate
+  const int32_t* n_active;    // number of entries in eval_index (device)
   double* logl;
-  double* logp;              // may be NULL when the prior was evaluated elsewhere
-  const double* logp_in;     // if non-NULL: take the prior from here instead of computing it
-  double t0;                 // X_[0] (acc.model uses X_ - X_[0])
-  double ll_const;           // -0.5*log(2*pi)*ndat  (00.like:1)
+  double t0;                  // X_[0] (acc.model uses X_ - X_[0])
+  double ll_const;            // -0.5*log(2*pi)*ndat  (00.like:1)
 };
 
 constexpr size_t kLoglSmemBytes =
     size_t(kStages) * kTileBytes + 2 * kStages * sizeof(uint64_t) + kWalkerWarps * sizeof(WalkerConst);
 
-// Fill the walker's constants; returns log-prior (evaluated redundantly by all lanes: uniform).
-__device__ inline double walker_prologue(const EmpModelDesc* __restrict__ d, const double* __restrict__ theta_row,
-                                         WalkerConst& wc, int lane, bool eval_prior) {
+// theta[ndim_free] -> full theta in shared memory (emp_model.py:709-711)
+__device__ __forceinline__ void load_full_theta(const EmpModelDesc* __restrict__ d,
+                                                const double* __restrict__ theta_row, double* th, int lane) {
   const int nfull = d->ndim_full, nfree = d->ndim_free;
-  for (int i = lane; i < nfull; i += 32) wc.th[i] = d->full_init[i];
+  for (int i = lane; i < nfull; i += 32) th[i] = d->full_init[i];
   __syncwarp();
-  for (int j = lane; j < nfree; j += 32) wc.th[d->free_to_full[j]] = theta_row[j];
+  for (int j = lane; j < nfree; j += 32) th[d->free_to_full[j]] = theta_row[j];
   __syncwarp();
-  double lp = 0.0;
-  if (eval_prior) lp = prior_program(d->prior_ops, d->n_prior_ops, wc.th);
-  if (lp == -INFINITY) return lp;
+}
+
+// Keplerian / instrument constants of one walker from its full theta
+__device__ __forceinline__ void walker_constants(const EmpModelDesc* __restrict__ d, WalkerConst& wc, int lane) {
   if (lane < d->n_kep) {
     KepConst kc;
     kep_constants(d->kep_model[lane], wc.th + d->kep_off[lane], kc);
@@ -73,7 +78,28 @@ __device__ inline double walker_prologue(const EmpModelDesc* __restrict__ d, con
   if (lane < d->acc_order) wc.acc[lane] = wc.th[d->acc_off + lane];
   if (lane < 2 * d->ma_order) wc.ma[lane] = wc.th[d->ma_off + lane];
   __syncwarp();
-  return lp;
+}
+
+// ---- launch 1: prior + compaction ---------------------------------------------------------
+constexpr int kPriorWarps = 8;
+__global__ void __launch_bounds__(kPriorWarps * 32)
+prior_compact_kernel(const EmpModelDesc* __restrict__ d, const double* __restrict__ theta, int64_t n_eval,
+                     double* __restrict__ logl, double* __restrict__ logp, int32_t* __restrict__ eval_index,
+                     int32_t* __restrict__ n_active) {
+  __shared__ double th_s[kPriorWarps][EMP_MAX_DIM];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t e = int64_t(blockIdx.x) * kPriorWarps + warp;
+  if (e >= n_eval) return;
+  load_full_theta(d, theta + e * d->ndim_free, th_s[warp], lane);
+  if (lane == 0) {
+    const double lp = prior_program(d->prior_ops, d->n_prior_ops, th_s[warp]);
+    logp[e] = lp;
+    if (lp == -INFINITY) {
+      logl[e] = -INFINITY;
+    } else {
+      eval_index[atomicAdd(n_active, 1)] = int32_t(e);
+    }
+  }
 }
 
 // np.polyval([a_n .. a_1, 0], x) with NumPy's Horner roundings (acc.model:2)
@@ -83,6 +109,7 @@ __device__ __forceinline__ double accel_term(const double* acc, int order, doubl
   return __dadd_rn(__dmul_rn(y, x), 0.0);
 }
 
+// ---- launch 2: likelihood -------------------------------------------------------------------
 __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* tiles_s = smem;
@@ -90,8 +117,13 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
   uint64_t* empty_bar = full_bar + kStages;
   WalkerConst* wcs = reinterpret_cast<WalkerConst*>(empty_bar + kStages);
 
+  const int n_active = *P.n_active;
+  const int first = blockIdx.x * kWalkerWarps;
+  if (first >= n_active) return;  // whole CTA beyond the compact list
+
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const EmpModelDesc* __restrict__ d = P.desc;
+  const int n_tiles = P.n_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -99,51 +131,28 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
       mbar_init(&empty_bar[s], kWalkerWarps);
     }
     fence_barrier_init();
+    // prime the ring
+    const int pre = n_tiles < kStages ? n_tiles : kStages;
+    for (int i = 0; i < pre; ++i) {
+      mbar_arrive_expect_tx(&full_bar[i], kTileBytes);
+      tma_bulk_g2s(tiles_s + size_t(i) * kTileBytes, P.tiles + size_t(i) * kTileBytes, kTileBytes, &full_bar[i]);
+    }
   }
 
-  // ---- prologue: priors + per-walker constants ------------------------------------------
-  bool active = false;
+  // ---- prologue: per-walker constants -------------------------------------------------------
+  const bool active = (first + warp) < n_active;
   int64_t slot = -1;
-  double lp = 0.0;
-  if (warp < kWalkerWarps) {
-    int64_t e = int64_t(blockIdx.x) * kWalkerWarps + warp;
-    if (e < P.n_eval) {
-      slot = P.eval_index ? int64_t(P.eval_index[e]) : e;
-      const bool eval_prior = (P.logp_in == nullptr);
-      lp = walker_prologue(d, P.theta + slot * d->ndim_free, wcs[warp], lane, eval_prior);
-      if (!eval_prior) lp = P.logp_in[slot];
-      active = (lp != -INFINITY);  // emcee: the likelihood is not evaluated at -inf prior
-      if (lane == 0) {
-        if (P.logp) P.logp[slot] = lp;
-        if (!active) P.logl[slot] = -INFINITY;
-      }
-    }
+  WalkerConst& wc = wcs[warp];
+  if (active) {
+    slot = P.eval_index[first + warp];
+    load_full_theta(d, P.theta + slot * d->ndim_free, wc.th, lane);
+    walker_constants(d, wc, lane);
   }
-  const int any_active = __syncthreads_or(active ? 1 : 0);  // also publishes the barrier inits
-  if (!any_active) return;
+  __syncthreads();  // publishes the barrier inits to all warps
 
-  const int n_tiles = P.n_tiles;
-
-  if (warp == kWalkerWarps) {
-    // ===== producer warp: bulk-TMA the tiles through the ring ==============================
-    if (lane == 0) {
-      for (int i = 0; i < n_tiles; ++i) {
-        const int s = i % kStages;
-        if (i >= kStages) mbar_wait(&empty_bar[s], ((i / kStages) - 1) & 1);
-        mbar_arrive_expect_tx(&full_bar[s], kTileBytes);
-        tma_bulk_g2s(tiles_s + size_t(s) * kTileBytes, P.tiles + size_t(i) * kTileBytes, kTileBytes,
-                     &full_bar[s]);
-      }
-    }
-    return;
-  }
-
-  // ===== walker warps =========================================================================
-  const WalkerConst& wc = wcs[warp];
   const int K = d->n_kep;
   const int acc_order = d->acc_order;
   const int ma_order = (d->ma_mode == EMP_MA_GLOBAL) ? d->ma_order : 0;
-  double* ma_scratch = nullptr;  // order >= 2 path reuses wc.th as scratch (th is dead after the prologue)
 
   double chi = 0.0, lsum = 0.0, prod = 1.0;
   int nprod = 0;
@@ -153,10 +162,19 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
   double rh[EMP_MAX_MA], thist[EMP_MAX_MA];
 #pragma unroll
   for (int c = 0; c < EMP_MAX_MA; ++c) { rh[c] = 0.0; thist[c] = 0.0; }
-  (void)ma_scratch;
 
   for (int i = 0; i < n_tiles; ++i) {
     const int s = i % kStages;
+    // refill: the stage of tile i-2 was released by every warp unless one lags two tiles behind
+    // -> load tile i+1 into it (one tile of prefetch distance; a tile is >100 us of math)
+    if (threadIdx.x == 0 && i >= 2 && (i - 2 + kStages) < n_tiles) {
+      const int sp = (i - 2) % kStages;
+      mbar_wait(&empty_bar[sp], ((i - 2) / kStages) & 1);
+      mbar_arrive_expect_tx(&full_bar[sp], kTileBytes);
+      tma_bulk_g2s(tiles_s + size_t(sp) * kTileBytes, P.tiles + size_t(i - 2 + kStages) * kTileBytes, kTileBytes,
+                   &full_bar[sp]);
+    }
+    __syncwarp();
     mbar_wait(&full_bar[s], (i / kStages) & 1);
     if (active) {
       const unsigned char* tb = tiles_s + size_t(s) * kTileBytes;
@@ -175,7 +193,7 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
         const bool v0 = p0 < cnt, v1 = (p0 + 1) < cnt;
         double m0 = 0.0, m1 = 0.0;
         for (int k = 0; k < K; ++k) {
-          const KepConst kc = wc.kep[k];
+          const KepConst& kc = wc.kep[k];
           m0 += kep_rv(kc, t2.x);
           m1 += kep_rv(kc, t2.y);
         }
@@ -199,8 +217,8 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
           const double phi = wc.ma[0], tau = wc.ma[1];
           const double tl = __shfl_up_sync(0xffffffffu, t2.y, 1);
           const double tp0 = (lane == 0) ? t_prev : tl;
-          const bool first = (base + p0) == 0;  // i == 0: no MA term (`if i > c`)
-          double a0 = (v0 && !first) ? -phi * exp(-fabs(t2.x - tp0) / tau) : 0.0;
+          const bool first_pt = (base + p0) == 0;  // i == 0: no MA term (`if i > c`)
+          double a0 = (v0 && !first_pt) ? -phi * exp(-fabs(t2.x - tp0) / tau) : 0.0;
           double a1 = v1 ? -phi * exp(-fabs(t2.y - t2.x) / tau) : 0.0;
           // compose the lane's two maps, then inclusive scan across lanes
           double A = a1 * a0, B = fma(a1, d0, d1);
@@ -218,10 +236,8 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
           // carry to the next 64 points: last VALID point of this iteration
           const int last_lane = min(31, (cnt - it * 64 - 1) >> 1);
           const bool last_is_second = ((cnt - it * 64) >= 2 * (last_lane + 1));
-          const double rc = __shfl_sync(0xffffffffu, last_is_second ? d1 : d0, last_lane);
-          const double tc = __shfl_sync(0xffffffffu, last_is_second ? t2.y : t2.x, last_lane);
-          r_carry = rc;
-          t_prev = tc;
+          r_carry = __shfl_sync(0xffffffffu, last_is_second ? d1 : d0, last_lane);
+          t_prev = __shfl_sync(0xffffffffu, last_is_second ? t2.y : t2.x, last_lane);
         } else if (ma_order >= 2) {
           // general order: serial recurrence over the 64 points (rare configuration), every lane
           // runs the same uniform loop on shuffled values so no shared scratch is needed.
@@ -274,7 +290,10 @@ __global__ void model_rv_kernel(const EmpModelDesc* __restrict__ d, const double
                                 const double* __restrict__ e2, const int32_t* __restrict__ ins, int64_t n,
                                 double t0, double* __restrict__ model, double* __restrict__ err2) {
   __shared__ WalkerConst wc;
-  if (threadIdx.x < 32) walker_prologue(d, theta, wc, threadIdx.x, false);
+  if (threadIdx.x < 32) {
+    load_full_theta(d, theta, wc.th, threadIdx.x);
+    walker_constants(d, wc, threadIdx.x);
+  }
   __syncthreads();
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
     double m = 0.0;

@@ -46,7 +46,7 @@ __global__ void pt_accept_kernel(double* __restrict__ p, double* __restrict__ lo
                                  const double* __restrict__ factors, const double* __restrict__ lnu,
                                  const double* __restrict__ q, const double* __restrict__ llq,
                                  const double* __restrict__ lpq, uint8_t* __restrict__ accepted,
-                                 uint32_t* __restrict__ n_nan) {
+                                 uint32_t* __restrict__ n_nan, unsigned long long* __restrict__ cnt) {
   const int32_t H = W / 2;
   const int64_t total = int64_t(T) * H;
   // one warp per proposal so the coordinate copy is coalesced
@@ -69,6 +69,9 @@ __global__ void pt_accept_kernel(double* __restrict__ p, double* __restrict__ lo
     if (lane == 0) {
       accepted[w] = acc ? 1 : 0;
       if (ll_new != ll_new && lp_new != -INFINITY) atomicAdd(n_nan, 1u);
+      atomicAdd(&cnt[0], 1ull);
+      if (lp_new != -INFINITY) atomicAdd(&cnt[1], 1ull);
+      if (acc) atomicAdd(&cnt[2], 1ull);
     }
     if (acc) {
       for (int dd = lane; dd < ndim; dd += 32) p[w * ndim + dd] = q[tj * ndim + dd];

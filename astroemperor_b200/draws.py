@@ -8,14 +8,14 @@ restates what the reference stack consumes from its `numpy.random.RandomState`
 ptemcee-lineage swap sweep of reddemcee; SURVEY.md §3.3, §8c row C2 — recalled,
 the packages are not vendored):
 
-  for t in range(ntemps):                 # reddemcee iterates temperatures serially
+  per temperature (its own RandomState, like reddemcee's one emcee sampler per temperature):
     for step in range(nsteps):
       inds = arange(W) % 2 ; shuffle(inds)
       for split in (0, 1):
         zz   = ((a-1)*rand(Ns) + 1)**2 / a
         rint = randint(Nc, size=Ns)
         u    = rand() for each walker of the split, in index order
-  for i in range(ntemps-1, 0, -1):        # hot -> cold
+  swap stream, for i in range(ntemps-1, 0, -1):        # hot -> cold
     iperm = permutation(W) ; i1perm = permutation(W) ; raccept = log(uniform(size=W))
 
 Logs (`(ndim-1)*log(zz)`, `log(u)`) are taken here with NumPy so the device and
@@ -30,45 +30,78 @@ import numpy as np
 
 @dataclass
 class SweepDraws:
-    half_idx: np.ndarray  # [nsteps, T, 2, H] int32: walkers of split 0 / 1 (ascending)
-    zz: np.ndarray        # [nsteps, T, 2, H]
-    rint: np.ndarray      # [nsteps, T, 2, H] int32
-    factors: np.ndarray   # [nsteps, T, 2, H]  (ndim-1)*log(zz)
-    lnu: np.ndarray       # [nsteps, T, 2, H]  log(u)
+    half_idx: np.ndarray  # [nsteps, T_loc, 2, H] int32: walkers of split 0 / 1 (ascending)
+    zz: np.ndarray        # [nsteps, T_loc, 2, H]
+    rint: np.ndarray      # [nsteps, T_loc, 2, H] int32
+    factors: np.ndarray   # [nsteps, T_loc, 2, H]  (ndim-1)*log(zz)
+    lnu: np.ndarray       # [nsteps, T_loc, 2, H]  log(u)
     perm: np.ndarray      # [T-1, 2, W] int32: perm[j] couples temperature j+1 (row 0) with j (row 1)
     lnu_swap: np.ndarray  # [T-1, W]
 
+    FIELDS = ("half_idx", "zz", "rint", "factors", "lnu", "perm", "lnu_swap")
+
     def nbytes(self) -> int:
-        return sum(getattr(self, f).nbytes for f in
-                   ("half_idx", "zz", "rint", "factors", "lnu", "perm", "lnu_swap"))
+        return sum(getattr(self, f).nbytes for f in self.FIELDS)
 
 
-def draw_sweep(rng: np.random.RandomState, T: int, W: int, ndim: int, nsteps: int, a: float = 2.0,
-               swap: bool = True) -> SweepDraws:
+class DrawStreams:
+    """One `RandomState` per temperature (reddemcee keeps one emcee sampler, hence one random
+    state, per temperature) plus one for the swap sweep and one for the initial ensemble, all
+    derived from a single seed.  A rank of a sharded ladder only advances the streams of its
+    own temperatures; the swap stream is advanced identically on every rank."""
+
+    def __init__(self, seed, ntemps: int):
+        ss = np.random.SeedSequence(seed)
+        kids = ss.spawn(ntemps + 2)
+        mk = lambda k: np.random.RandomState(np.random.MT19937(k))
+        self.temp = [mk(k) for k in kids[:ntemps]]
+        self.swap = mk(kids[ntemps])
+        self.init = mk(kids[ntemps + 1])
+        self.ntemps = ntemps
+
+
+def draw_stretch(rng: np.random.RandomState, W: int, nsteps: int, a: float = 2.0):
+    """Draws of ONE temperature for `nsteps` RedBlue stretch steps, in emcee's order."""
+    H = W // 2
+    half_idx = np.empty((nsteps, 2, H), dtype=np.int32)
+    zz = np.empty((nsteps, 2, H))
+    rint = np.empty((nsteps, 2, H), dtype=np.int32)
+    u = np.empty((nsteps, 2, H))
+    base = np.arange(W) % 2
+    for s in range(nsteps):
+        inds = base.copy()
+        rng.shuffle(inds)
+        half_idx[s, 0] = np.flatnonzero(inds == 0)
+        half_idx[s, 1] = np.flatnonzero(inds == 1)
+        for split in (0, 1):
+            zz[s, split] = ((a - 1.0) * rng.rand(H) + 1) ** 2.0 / a
+            rint[s, split] = rng.randint(H, size=(H,))
+            u[s, split] = rng.rand(H)
+    return half_idx, zz, rint, u
+
+
+def draw_sweep(streams: DrawStreams, W: int, ndim: int, nsteps: int, a: float = 2.0,
+               temps: slice = None, swap: bool = True) -> SweepDraws:
+    """Draws of one sweep: stretch draws for the temperatures in `temps` (default: all), swap
+    draws for the whole ladder."""
     if W % 2:
         raise ValueError("nwalkers must be even (two equal halves, emcee RedBlueMove nsplits=2)")
+    T = streams.ntemps
+    tl = range(T)[temps] if temps is not None else range(T)
     H = W // 2
-    half_idx = np.empty((nsteps, T, 2, H), dtype=np.int32)
-    zz = np.empty((nsteps, T, 2, H))
-    rint = np.empty((nsteps, T, 2, H), dtype=np.int32)
-    u = np.empty((nsteps, T, 2, H))
-    base = np.arange(W) % 2
-    for t in range(T):
-        for s in range(nsteps):
-            inds = base.copy()
-            rng.shuffle(inds)
-            half_idx[s, t, 0] = np.flatnonzero(inds == 0)
-            half_idx[s, t, 1] = np.flatnonzero(inds == 1)
-            for split in (0, 1):
-                zz[s, t, split] = ((a - 1.0) * rng.rand(H) + 1) ** 2.0 / a
-                rint[s, t, split] = rng.randint(H, size=(H,))
-                u[s, t, split] = rng.rand(H)
+    half_idx = np.empty((nsteps, len(tl), 2, H), dtype=np.int32)
+    zz = np.empty((nsteps, len(tl), 2, H))
+    rint = np.empty((nsteps, len(tl), 2, H), dtype=np.int32)
+    u = np.empty((nsteps, len(tl), 2, H))
+    for j, t in enumerate(tl):
+        half_idx[:, j], zz[:, j], rint[:, j], u[:, j] = draw_stretch(streams.temp[t], W, nsteps, a)
     factors = (ndim - 1.0) * np.log(zz)
     with np.errstate(divide="ignore"):
         lnu = np.log(u)
     perm = np.empty((max(T - 1, 0), 2, W), dtype=np.int32)
     lnu_swap = np.empty((max(T - 1, 0), W))
     if swap:
+        rng = streams.swap
         for i in range(T - 1, 0, -1):
             perm[i - 1, 0] = rng.permutation(W)
             perm[i - 1, 1] = rng.permutation(W)

@@ -84,10 +84,17 @@ class LikelihoodEngine:
     def set_timing(self, on: bool):
         _lib.check(self._L.emp_set_timing(self._h, 1 if on else 0))
 
-    def last_logl_ms(self) -> float:
-        ms = ctypes.c_float()
-        _lib.check(self._L.emp_last_logl_ms(self._h, ctypes.byref(ms)))
-        return float(ms.value)
+    def timing_collect(self):
+        """(summed likelihood-kernel ms, launches) since the last collect; synchronises."""
+        ms, n = ctypes.c_double(), ctypes.c_int64()
+        _lib.check(self._L.emp_timing_collect(self._h, ctypes.byref(ms), ctypes.byref(n)))
+        return float(ms.value), int(n.value)
+
+    def counters(self):
+        """dict(proposals, in_prior, accepted, nan) of the PT steps run on this engine."""
+        out = (ctypes.c_uint64 * 4)()
+        _lib.check(self._L.emp_counters(self._h, out))
+        return dict(proposals=int(out[0]), in_prior=int(out[1]), accepted=int(out[2]), nan=int(out[3]))
 
     def nan_count(self) -> int:
         c = ctypes.c_uint32()
@@ -164,3 +171,10 @@ class LikelihoodEngine:
         _lib.check(self._L.emp_pt_gather_rows(
             self._h, n_rows, p_in.shape[-1], src.data_ptr(), p_in.data_ptr(), ll_in.data_ptr(),
             lp_in.data_ptr(), p_out.data_ptr(), ll_out.data_ptr(), lp_out.data_ptr()))
+
+
+def fp64_peak_tflops(device: int = 0) -> float:
+    """Measured FP64 FMA peak of the device (roofline denominator, bench.py)."""
+    v = ctypes.c_double()
+    _lib.check(_lib.lib().emp_fp64_peak(int(device), ctypes.byref(v)))
+    return float(v.value)

@@ -23,15 +23,14 @@ from typing import Optional
 import numpy as np
 
 from . import dist as _dist
-from .draws import SweepDraws, default_betas, draw_sweep, initial_positions
+from .draws import DrawStreams, SweepDraws, default_betas, draw_sweep, initial_positions
 
 
 class PTSampler:
     def __init__(self, nwalkers: int, ndim: int, log_like, log_prior=None, ntemps: int = 1, pool=None,
                  backend=None, betas=None, tsw_history: bool = True, smd_history: bool = True,
                  adapt_tau: float = 1000, adapt_nu: float = 1, adapt_mode: int = 0, a: float = 2.0,
-                 seed: Optional[int] = None, random_state: Optional[np.random.RandomState] = None,
-                 store: str = "device", thin_by: int = 1, adapt: bool = True, group=None):
+                 seed: Optional[int] = None, store: str = "device", thin_by: int = 1, adapt: bool = True, group=None):
         """`log_like` is the LikelihoodEngine (it carries the prior as well; `log_prior`,
         `pool` and `backend` are accepted for signature compatibility and ignored — the
         walkers are evaluated on the GPU, not through a multiprocessing pool)."""
@@ -55,7 +54,7 @@ class PTSampler:
                       else default_betas(ndim, ntemps))
         if len(self.betas) != self.ntemps:
             raise ValueError(f"betas should have {ntemps} items")
-        self.random = random_state if random_state is not None else np.random.RandomState(seed)
+        self.streams = DrawStreams(seed, self.ntemps)
         self.D_ = None
         self.store, self.thin_by = store, int(thin_by)
         self.torch = torch
@@ -73,13 +72,13 @@ class PTSampler:
     def initial_positions(self, spec, max_repeats: int = 100) -> np.ndarray:
         """set_init() + test_init() of the generated script (emp.py:617-684): redraw walkers whose
         prior is -inf, at most `max_repeats` rounds."""
-        p0 = initial_positions(self.random, spec, self.ntemps, self.nwalkers)
+        p0 = initial_positions(self.streams.init, spec, self.ntemps, self.nwalkers)
         for _ in range(max_repeats):
             lp = self.engine.my_prior(p0.reshape(-1, self.ndim)).reshape(self.ntemps, self.nwalkers)
             bad = ~np.isfinite(np.atleast_2d(lp))
             if not bad.any():
                 break
-            fresh = initial_positions(self.random, spec, self.ntemps, self.nwalkers)
+            fresh = initial_positions(self.streams.init, spec, self.ntemps, self.nwalkers)
             p0[bad] = fresh[bad]
         else:
             print("COULDNT FIND VALID INITIAL POSITION")
@@ -135,30 +134,41 @@ class PTSampler:
             self._stored = 0
 
     # ------------------------------------------------------------------------------
-    def sweep(self, draws: SweepDraws):
-        """nsteps stretch steps of every local temperature + one swap sweep + adaptation."""
-        torch = self.torch
+    def stage_draws(self, draws: SweepDraws, pinned: bool = False):
+        """Copy one sweep's draws to the device (async on the current stream).  `draws` holds the
+        stretch draws of THIS rank's temperatures and the swap draws of the whole ladder."""
+        out = {}
+        for f in SweepDraws.FIELDS:
+            a = getattr(draws, f)
+            if f in ("perm", "lnu_swap") and self.ntemps < 2:
+                out[f] = None
+                continue
+            t = self.torch.from_numpy(np.ascontiguousarray(a))
+            if pinned:
+                t = t.pin_memory()
+            out[f] = t.to(self.dev, non_blocking=True)
+        return out
+
+    def sweep(self, draws):
+        """nsteps stretch steps of every local temperature + one swap sweep + adaptation.
+        `draws`: SweepDraws (host) or the dict `stage_draws` returned (already on the device)."""
         eng = self.engine
         sl = self.shard.local_slice
-        t0 = _time.perf_counter()
-        d_half = self._upload(draws.half_idx[:, sl])
-        d_zz = self._upload(draws.zz[:, sl])
-        d_rint = self._upload(draws.rint[:, sl])
-        d_fac = self._upload(draws.factors[:, sl])
-        d_lnu = self._upload(draws.lnu[:, sl])
-        self.timings["h2d"] += _time.perf_counter() - t0
-        nsteps = draws.zz.shape[0]
+        if isinstance(draws, SweepDraws):
+            t0 = _time.perf_counter()
+            draws = self.stage_draws(draws)
+            self.timings["h2d"] += _time.perf_counter() - t0
+        nsteps = draws["zz"].shape[0]
+        betas_loc = self._betas_dev[sl]
         for s in range(nsteps):
-            eng.pt_stretch_step(self.p, self.logl, self.logp, self._betas_dev[sl], d_half[s], d_zz[s], d_rint[s],
-                                d_fac[s], d_lnu[s], self.accepted)
+            eng.pt_stretch_step(self.p, self.logl, self.logp, betas_loc, draws["half_idx"][s], draws["zz"][s],
+                                draws["rint"][s], draws["factors"][s], draws["lnu"][s], self.accepted)
             self._n_accepted += self.accepted
             self._n_steps += 1
         n_acc = None
         if self.ntemps > 1:
-            d_perm = self._upload(draws.perm)
-            d_lnus = self._upload(draws.lnu_swap)
             logl_all = self.shard.all_gather_rows(self.logl)  # [T, W]; NCCL all-gather when sharded
-            eng.pt_swap_plan(logl_all, self._betas_dev, d_perm, d_lnus, self._src, self._n_acc)
+            eng.pt_swap_plan(logl_all, self._betas_dev, draws["perm"], draws["lnu_swap"], self._src, self._n_acc)
             self._apply_plan()
             n_acc = self._n_acc.cpu().numpy()[: self.ntemps - 1]  # syncs: 4*(T-1) bytes
         self.time += 1
@@ -191,6 +201,11 @@ class PTSampler:
         self.logl, self._ll_alt = self._ll_alt, self.logl
         self.logp, self._lp_alt = self._lp_alt, self.logp
 
+    def draw(self, nsteps: int) -> SweepDraws:
+        """Host draws of one sweep for this rank (draws.py)."""
+        return draw_sweep(self.streams, self.nwalkers, self.ndim, nsteps, self.a,
+                          temps=self.shard.local_slice, swap=self.ntemps > 1)
+
     def run_mcmc(self, p0, nsweeps: int, nsteps: int = 1, progress: bool = False):
         if p0 is not None:
             self._init_state(p0)
@@ -206,8 +221,7 @@ class PTSampler:
                 pass
         for k in it:
             t0 = _time.perf_counter()
-            draws = draw_sweep(self.random, self.ntemps, self.nwalkers, self.ndim, nsteps, self.a,
-                               swap=self.ntemps > 1)
+            draws = self.draw(nsteps)
             self.timings["draws"] += _time.perf_counter() - t0
             self.sweep(draws)
             if self._chain is not None and (k % self.thin_by == 0):

@@ -228,10 +228,17 @@ int emp_nan_count(EmpHandle *h, uint32_t *count);
 /* ---- introspection -------------------------------------------------------- */
 /* Number of kernels this handle has launched since creation (bench.py gpu_launches). */
 int emp_launch_count(EmpHandle *h, int64_t *count);
-/* Time in ms of the last emp_logl_batch kernel (CUDA events on the handle's stream);
- * only valid after emp_synchronize.  Enabled by emp_set_timing(h, 1). */
+/* Per-launch device timing of the likelihood kernel: while enabled every launch is bracketed
+ * by CUDA events on the handle's stream; emp_timing_collect synchronises, returns the summed
+ * kernel time and the number of launches since the last collect, and resets. */
 int emp_set_timing(EmpHandle *h, int enable);
-int emp_last_logl_ms(EmpHandle *h, float *ms);
+int emp_timing_collect(EmpHandle *h, double *total_ms, int64_t *n_launches);
+/* Diagnostics of the PT step since creation: out4 = { proposals, proposals inside the prior
+ * support (the ones whose likelihood was evaluated), accepted, NaN likelihoods }. */
+int emp_counters(EmpHandle *h, uint64_t *out4);
+/* Measured FP64 FMA throughput of the device in TFLOP/s (8 independent DFMA chains per
+ * thread): the roofline denominator of this FP64-pipe-bound path. */
+int emp_fp64_peak(int device, double *tflops);
 
 #ifdef __cplusplus
 }
