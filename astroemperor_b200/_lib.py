@@ -10,7 +10,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libemperor_b200.so")
+# EMP_B200_LIB: developer override used to A/B kernel variants (scripts/build_variant.sh)
+LIB_PATH = os.environ.get("EMP_B200_LIB") or os.path.join(_HERE, "libemperor_b200.so")
 
 _lib = None
 
@@ -50,6 +51,7 @@ SYMBOLS = [
     ("emp_logl_batch", ctypes.c_int, [_P, _P, _I64, _P, _P]),
     ("emp_logl_batch_host", ctypes.c_int, [_P, _P, _I64, _P, _P]),
     ("emp_model_host", ctypes.c_int, [_P, _P, _P, _P]),
+    ("emp_kepler_solve_host", ctypes.c_int, [_P, _P, _I64, ctypes.c_int, _P, ctypes.c_int]),
     ("emp_pt_stretch_step", ctypes.c_int, [_P, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("emp_pt_swap_plan", ctypes.c_int, [_P, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     ("emp_pt_gather_rows", ctypes.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P]),

@@ -43,6 +43,7 @@ struct EmpHandle {
   double *d_t = nullptr, *d_y = nullptr, *d_e2 = nullptr;
   int32_t* d_ins = nullptr;
   double t0 = 0.0;
+  double t_absmax = 0.0;
   double ll_const = 0.0;
   // scratch for the host-buffer entry points and the PT step
   double *d_theta = nullptr, *d_ll = nullptr, *d_lp = nullptr;
@@ -138,6 +139,7 @@ extern "C" int emp_create(const EmpModelDesc* desc, const double* t, const doubl
   h->n = n;
   h->n_tiles = int32_t((n + kTilePoints - 1) / kTilePoints);
   h->t0 = t[0];
+  for (int64_t i = 0; i < n; ++i) h->t_absmax = fmax(h->t_absmax, fabs(t[i]));
   h->ll_const = -0.5 * log(2.0 * M_PI) * double(n);  // 00.like:1
 
   CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -265,6 +267,8 @@ static int launch_logl(EmpHandle* h, const double* theta_dev, int64_t n_eval, do
   P.logl = logl_dev;
   P.t0 = h->t0;
   P.ll_const = h->ll_const;
+  P.t_absmax = h->t_absmax;
+  P.H = make_hot_consts();
   const unsigned grid = unsigned((n_eval + kWalkerWarps - 1) / kWalkerWarps);
   cudaEvent_t e0 = h->ev0, e1 = h->ev1;
   if (h->timing) {
@@ -340,7 +344,7 @@ extern "C" int emp_model_host(EmpHandle* h, const double* theta_host, double* mo
   int blocks = int((h->n + 255) / 256);
   if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms;
   model_rv_kernel<<<blocks, 256, 0, h->stream>>>(h->d_desc, h->d_theta, h->d_t, h->d_y, h->d_e2, h->d_ins, h->n,
-                                                 h->t0, d_model, d_err2);
+                                                 h->t0, h->t_absmax, d_model, d_err2, make_hot_consts());
   h->launches += 1;
   if (h->desc.ma_mode == EMP_MA_GLOBAL && h->desc.ma_order > 0) {
     model_ma_kernel<<<1, 32, 0, h->stream>>>(h->d_desc, h->d_theta, h->d_t, h->d_y, h->n, d_model);
@@ -525,5 +529,38 @@ extern "C" int emp_fp64_peak(int device, double* tflops) {
   cudaEventDestroy(e1);
   cudaFree(d_out);
   *tflops = best;
+  return EMP_OK;
+}
+
+// ---- kepler.solve drop-in --------------------------------------------
+__global__ void kepler_solve_kernel(const double* __restrict__ M, const double* __restrict__ ecc, int64_t n,
+                                    int ecc_scalar, double* __restrict__ E, const HotConsts H) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    E[i] = kepler_solve(M[i], ecc[ecc_scalar ? 0 : i], H);
+}
+
+extern "C" int emp_kepler_solve_host(const double* M, const double* ecc, int64_t n, int ecc_is_scalar, double* E,
+                                     int device) {
+  if (!M || !ecc || !E || n < 0) return fail(EMP_EINVAL, "bad argument");
+  if (n == 0) return EMP_OK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(EMP_ENODEV, "no CUDA device (there is no CPU fallback)");
+  CUDA_TRY(cudaSetDevice(device));
+  double *dM = nullptr, *de = nullptr, *dE = nullptr;
+  const int64_t ne = ecc_is_scalar ? 1 : n;
+  cudaError_t e = cudaMalloc(&dM, n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&de, ne * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&dE, n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpy(dM, M, n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(de, ecc, ne * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    int blocks = int(std::min<int64_t>((n + 255) / 256, 148 * 8));
+    kepler_solve_kernel<<<blocks, 256>>>(dM, de, n, ecc_is_scalar, dE, make_hot_consts());
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(E, dE, n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(dM); cudaFree(de); cudaFree(dE);
+  if (e != cudaSuccess) return fail(EMP_ECUDA, cudaGetErrorString(e));
   return EMP_OK;
 }

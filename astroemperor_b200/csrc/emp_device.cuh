@@ -29,23 +29,30 @@ constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52: (x + kMagic) - kMa
 constexpr double kF1 = 3.0 * kPi / (kPi - 6.0 / kPi);
 constexpr double kF2 = 1.6 / (kPi - 6.0 / kPi);
 
-// Hot-loop FP64 literals live in constant memory so that DFMA/DADD take them as a
-// constant-bank operand (a 64-bit immediate would cost two UMOVs per use).
+// Hot-loop FP64 literals travel in the KERNEL PARAMETER bank (c[0x0]) so that DFMA/DADD take them
+// as a direct constant operand: a 64-bit immediate costs two UMOVs per use and a user
+// __constant__ array (bank 3) costs an LDC per use (profiles/r01_sass_notes.md).
 //   (v - sin v)/v^3 = 1/3! - w/5! + w^2/7! - ...   (8 terms: next term < 1e-18 relative on [0, pi/4])
-//   (1 - cos v)/v^2 = 1/2! - w/4! + w^2/6! - ...   (9 terms)
-__constant__ double kSinC[8] = {-1.0 / 355687428096000.0, 1.0 / 1307674368000.0, -1.0 / 6227020800.0,
-                                1.0 / 39916800.0,         -1.0 / 362880.0,       1.0 / 5040.0,
-                                -1.0 / 120.0,             1.0 / 6.0};
-__constant__ double kCosC[9] = {1.0 / 6402373705728000.0, -1.0 / 20922789888000.0, 1.0 / 87178291200.0,
-                                -1.0 / 479001600.0,       1.0 / 3628800.0,         -1.0 / 40320.0,
-                                1.0 / 720.0,              -1.0 / 24.0,             0.5};
-// [0] pi [1] 2pi [2] pi/2 [3] pi/4 [4] 1/(2pi) [5] rint magic [6] F1 [7] 1/6 [8] 1/24 [9] 1 - pi/2
-__constant__ double kC[10] = {kPi, kTwoPi, kPi2, kPi4, kInvTwoPi, kMagic, kF1, 1.0 / 6.0, 1.0 / 24.0, 1.0 - kPi2};
+//   (1 - cos v)/v^2 = 1/2! - w/4! + w^2/6! - ...   (9 terms), both stored highest degree first
+struct HotConsts {
+  double sinc[8];
+  double cosc[9];
+  double c[10];  // [0] pi [1] 2pi [2] pi/2 [3] pi/4 [4] 1/(2pi) [5] rint magic [6] F1 [7] 1/6 [8] 1/24 [9] 1-pi/2
+};
+__host__ __device__ inline HotConsts make_hot_consts() {
+  HotConsts h = {{-1.0 / 355687428096000.0, 1.0 / 1307674368000.0, -1.0 / 6227020800.0, 1.0 / 39916800.0,
+                  -1.0 / 362880.0, 1.0 / 5040.0, -1.0 / 120.0, 1.0 / 6.0},
+                 {1.0 / 6402373705728000.0, -1.0 / 20922789888000.0, 1.0 / 87178291200.0, -1.0 / 479001600.0,
+                  1.0 / 3628800.0, -1.0 / 40320.0, 1.0 / 720.0, -1.0 / 24.0, 0.5},
+                 {kPi, kTwoPi, kPi2, kPi4, kInvTwoPi, kMagic, kF1, 1.0 / 6.0, 1.0 / 24.0, 1.0 - kPi2}};
+  return h;
+}
 
 // Per (walker, Keplerian) constants, computed once in the kernel prologue.
 struct KepConst {
   double freq;    // 2 pi / per
-  double ph;      // phase, or t_p for kep03/kep04
+  double tpv;     // t_p for kep03/kep04, else 0:   M = freq*(t - tpv) + phv reproduces both
+  double phv;     // phase, or 0 for kep03/kep04    templates' roundings (x - 0 and x + 0 are exact)
   double e;       // eccentricity
   double ome;     // 1 - e
   double c2;      // kF2 / (1 + e)
@@ -53,7 +60,8 @@ struct KepConst {
   double a1;      // A cos w
   double a2;      // -A sin w sqrt(1 - e^2)
   double a3;      // A e cos w
-  double use_tp;  // != 0: M = freq * (t - ph)
+  float ef, omef, c2f, ome3f;  // FP32 copies for the starter
+  int slow_mod, _pad;          // |M| may exceed 1e12 somewhere in the data set: use the fmod path
 };
 constexpr int kKepConstDoubles = sizeof(KepConst) / sizeof(double);
 
@@ -105,7 +113,7 @@ __device__ inline void kep_elements(int model, const double* th, double& per, do
   }
 }
 
-__device__ inline void kep_constants(int model, const double* th, KepConst& k) {
+__device__ inline void kep_constants(int model, const double* th, double t_absmax, KepConst& k) {
   double per, A, ph, e, w;
   bool use_tp;
   kep_elements(model, th, per, A, ph, e, w, use_tp);
@@ -113,7 +121,8 @@ __device__ inline void kep_constants(int model, const double* th, KepConst& k) {
   sincos(w, &sw, &cw);
   double ome = 1.0 - e;
   k.freq = kTwoPi / per;
-  k.ph = ph;
+  k.tpv = use_tp ? ph : 0.0;
+  k.phv = use_tp ? 0.0 : ph;
   k.e = e;
   k.ome = ome;
   k.c2 = kF2 / (1.0 + e);
@@ -121,14 +130,21 @@ __device__ inline void kep_constants(int model, const double* th, KepConst& k) {
   k.a1 = A * cw;
   k.a2 = -A * sw * sqrt(ome * (1.0 + e));
   k.a3 = A * e * cw;
-  k.use_tp = use_tp ? 1.0 : 0.0;
+  k.ef = float(e);
+  k.omef = float(ome);
+  k.c2f = float(k.c2);
+  k.ome3f = float(k.ome3);
+  // the exact rint/FMA reduction needs |M| < 2^51 * 2pi; decide once per (walker, planet)
+  const double m_bound = fabs(k.freq) * (t_absmax + fabs(k.tpv)) + fabs(k.phv);
+  k.slow_mod = (m_bound < 1.0e12) ? 0 : 1;  // also catches NaN / inf parameters
+  k._pad = 0;
 }
 
 // ---- mean anomaly, reduced to [0, pi] exactly like NumPy's remainder ------------------
 __device__ __forceinline__ double mean_anomaly(const KepConst& k, double t) {
-  // two roundings, as `freq * X_ + phase` (kep00.model:5) / `freq * (X_ - tp)` (kep03.model:4)
-  return (k.use_tp != 0.0) ? __dmul_rn(k.freq, __dsub_rn(t, k.ph))
-                           : __dadd_rn(__dmul_rn(k.freq, t), k.ph);
+  // `freq * X_ + phase` (kep00.model:5) / `freq * (X_ - tp)` (kep03.model:4) with the same roundings:
+  // t - 0 and x + 0 are exact, so one branch-free form serves both templates
+  return __dadd_rn(__dmul_rn(k.freq, __dsub_rn(t, k.tpv)), k.phv);
 }
 
 __device__ __noinline__ double mod_two_pi_slow(double M) {
@@ -144,82 +160,165 @@ __device__ __noinline__ double mod_two_pi_slow(double M) {
 // r = M mod 2pi in [0, 2pi] with Python semantics. Every step is exact: k = rint(M/2pi),
 // M - k*c has at most 53 significant bits (multiple of ulp(c), |.| < 8), so the FMA and
 // the conditional +c reproduce fmod()+fix-up bit for bit.
-__device__ __forceinline__ double mod_two_pi(double M) {
-  double kd = __dsub_rn(__dadd_rn(__dmul_rn(M, kC[4]), kC[5]), kC[5]);
-  double r = __fma_rn(-kd, kC[1], M);
-  if (r < 0.0) r = __dadd_rn(r, kC[1]);
-  if (!(fabs(M) < 1.0e12)) r = mod_two_pi_slow(M);
-  return r;
+__device__ __forceinline__ double mod_two_pi(double M, const HotConsts& H) {
+  double kd = __dsub_rn(__dadd_rn(__dmul_rn(M, H.c[4]), H.c[5]), H.c[5]);
+  double r = __fma_rn(-kd, H.c[1], M);
+  if (r < 0.0) r = __dadd_rn(r, H.c[1]);
+  return r;  // valid for |M| < 1e12 (KepConst::slow_mod routes everything else to fmod)
 }
 
 // ---- x - sin x and 1 - cos x on [0, pi] (Nijenhuis-style folding, Taylor core) ----------
-__device__ __forceinline__ void sin_cos_reduc(double x, double& sn, double& cs) {
-  bool bigg = x > kC[2];
-  double u = bigg ? kC[0] - x : x;
-  bool big = u > kC[3];
-  double v = big ? kC[2] - u : u;
+__device__ __forceinline__ void sin_cos_reduc(double x, double& sn, double& cs, const HotConsts& H) {
+  bool bigg = x > H.c[2];
+  double u = bigg ? H.c[0] - x : x;
+  bool big = u > H.c[3];
+  double v = big ? H.c[2] - u : u;
   double w = v * v;
-  double ps = kSinC[0];
-#pragma unroll
-  for (int i = 1; i < 8; ++i) ps = fma(ps, w, kSinC[i]);
-  double pc = kCosC[0];
-#pragma unroll
-  for (int i = 1; i < 9; ++i) pc = fma(pc, w, kCosC[i]);
+  // Estrin evaluation (depth 4 instead of 8): coefficients are stored highest degree first
+  const double w2 = w * w, w4 = w2 * w2;
+  const double s01 = fma(H.sinc[6], w, H.sinc[7]), s23 = fma(H.sinc[4], w, H.sinc[5]);
+  const double s45 = fma(H.sinc[2], w, H.sinc[3]), s67 = fma(H.sinc[0], w, H.sinc[1]);
+  const double ps = fma(fma(s67, w2, s45), w4, fma(s23, w2, s01));
+  const double c01 = fma(H.cosc[7], w, H.cosc[8]), c23 = fma(H.cosc[5], w, H.cosc[6]);
+  const double c45 = fma(H.cosc[3], w, H.cosc[4]), c67 = fma(H.cosc[1], w, H.cosc[2]);
+  const double pc = fma(fma(H.cosc[0], w4, fma(c67, w2, c45)), w4, fma(c23, w2, c01));
   double ss = ps * (v * w);
   double cc = pc * w;
   double s1 = big ? (u - 1.0) + cc : ss;
-  double c1 = big ? (kC[9] + u) + ss : cc;
-  sn = bigg ? fma(2.0, x, -kC[0]) + s1 : s1;
+  double c1 = big ? (H.c[9] + u) + ss : cc;
+  sn = bigg ? fma(2.0, x, -H.c[0]) + s1 : s1;
   cs = bigg ? 2.0 - c1 : c1;
 }
 
-// One Keplerian's RV at time t (everything of kep00.model:4-8 for one point).
-__device__ __forceinline__ double kep_rv(const KepConst& k, double t) {
-  const double M = mean_anomaly(k, t);
-  const double r0 = mod_two_pi(M);
-  const bool high = r0 > kC[0];
-  const double Mr = high ? __dsub_rn(kC[1], r0) : r0;
+// ---- approximate-reciprocal helpers (MUFU seeds + Newton steps, no slow-path branches) -----
+__device__ __forceinline__ double rcp_seed(double x) {  // MUFU.RCP64H, relative error 2^-23
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  return y;
+}
+template <int N>
+__device__ __forceinline__ double rcp_nr(double x) {  // N Newton steps: 2^-46, 2^-92 (-> ~1 ulp)
+  double y = rcp_seed(x);
+#pragma unroll
+  for (int i = 0; i < N; ++i) y = fma(y, fma(-x, y, 1.0), y);
+  return y;
+}
+__device__ __forceinline__ float f32_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float f32_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float f32_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float f32_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-  // Markley starter (kepler.py get_markley_starter), one division
+// Markley (1995) starter in FP64 (cold path: M ~ 0 or a non-finite FP32 result)
+__device__ __noinline__ double markley_starter_f64(double Mr, double e, double ome) {
   const double M2 = Mr * Mr;
-  const double alpha = fma(k.c2, kC[0] - Mr, kC[6]);
-  const double d = fma(alpha, k.e, k.ome3);
+  const double alpha = fma(kF2 / (1.0 + e), kPi - Mr, kF1);
+  const double d = fma(alpha, e, 3.0 * ome);
   const double ad = alpha * d;
-  const double r = fma(3.0 * ad, d - k.ome, M2) * Mr;
-  const double q = fma(2.0 * ad, k.ome, -M2);
+  const double r = fma(3.0 * ad, d - ome, M2) * Mr;
+  const double q = fma(2.0 * ad, ome, -M2);
   const double q2 = q * q;
-  const double x = fabs(r) + sqrt(fma(q2, q, r * r));
-  const double cb = cbrt(x);
+  const double cb = cbrt(fabs(r) + sqrt(fma(q2, q, r * r)));
   const double w = cb * cb;
   const double den0 = fma(w, w + q, q2);
-  const double E0 = fma(2.0 * r, w, Mr * den0) / (den0 * d);
+  return fma(2.0 * r, w, Mr * den0) / (den0 * d);
+}
 
-  // single high-order refinement (kepler.py refine_estimate)
+// Same starter in FP32 on the FMA/MUFU pipes (they issue in the slots the half-rate FP64 pipe
+// leaves free).  The starter is only an initial guess with an intrinsic error of ~4e-4; its
+// FP32 rounding (1e-7) changes the refined root by < 1e-18 (tests/test_kepler_device.py).
+__device__ __forceinline__ double markley_starter(double Mr, const KepConst& k) {
+  const float M = __double2float_rn(Mr);
+  const float M2 = M * M;
+  const float alpha = fmaf(k.c2f, 3.14159274f - M, 7.64804745f /* F1 */);
+  const float d = fmaf(alpha, k.ef, k.ome3f);
+  const float ad = alpha * d;
+  const float r = fmaf(3.0f * ad, d - k.omef, M2) * M;
+  const float q = fmaf(2.0f * ad, k.omef, -M2);
+  const float q2 = q * q;
+  const float x = fabsf(r) + f32_sqrt(fmaf(q2, q, r * r));
+  const float w = f32_ex2(0.666666687f * f32_lg2(x));  // x^(2/3)
+  const float den0 = fmaf(w, w + q, q2);
+  const float E0f = fmaf(2.0f * r, w, M * den0) * f32_rcp(den0 * d);
+  double E0 = double(E0f);
+  if (!(M > 1e-15f) || !(E0f == E0f) || !(fabsf(E0f) < 4.0f)) E0 = markley_starter_f64(Mr, k.e, k.ome);
+  return E0;
+}
+
+// Kepler's equation for a folded mean anomaly Mr in [0, pi]: returns the pre-refinement
+// estimate E0 and the correction dE (E = E0 + dE), plus sin E and 1 - cos E of the refined E.
+__device__ __forceinline__ void kepler_refined(double Mr, const KepConst& k, const HotConsts& H, double& E0_out,
+                                               double& dE_out, double& s1_out, double& cE1_out);
+
+// One Keplerian's RV at time t (everything of kep00.model:4-8 for one point).
+template <bool kSlow = false>
+__device__ __forceinline__ double kep_rv(const KepConst& k, double t, const HotConsts& H) {
+  const double M = mean_anomaly(k, t);
+  const double r0 = kSlow ? mod_two_pi_slow(M) : mod_two_pi(M, H);
+  const bool high = r0 > H.c[0];
+  const double Mr = high ? __dsub_rn(H.c[1], r0) : r0;
+  double E0, dE, s1, cE1;
+  kepler_refined(Mr, k, H, E0, dE, s1, cE1);
+  const double den = fma(k.e, cE1, k.ome);                     // 1 - e cos E1
+  const double a2s = high ? -k.a2 : k.a2;                      // sin(2pi - E) = -sin E
+  const double num = fma(k.a1, k.ome - cE1, a2s * s1);
+  return fma(num, rcp_nr<2>(den), k.a3);
+}
+
+// kepler.solve(M, ecc) for one element (A13 of SURVEY.md §8a): E in [0, 2pi]
+__device__ __forceinline__ double kepler_solve(double M, double ecc, const HotConsts& H) {
+  KepConst k;
+  k.e = ecc;
+  k.ome = 1.0 - ecc;
+  k.ef = float(ecc);
+  k.omef = float(k.ome);
+  k.c2f = float(kF2 / (1.0 + ecc));
+  k.ome3f = 3.0f * k.omef;
+  const double r0 = (fabs(M) < 1.0e12) ? mod_two_pi(M, H) : mod_two_pi_slow(M);
+  const bool high = r0 > H.c[0];
+  const double Mr = high ? __dsub_rn(H.c[1], r0) : r0;
+  double E0, dE, s1, cE1;
+  kepler_refined(Mr, k, H, E0, dE, s1, cE1);
+  const double E = E0 + dE;
+  return high ? H.c[1] - E : E;
+}
+
+__device__ __forceinline__ void kepler_refined(double Mr, const KepConst& k, const HotConsts& H, double& E0_out,
+                                               double& dE_out, double& s1_out, double& cE1_out) {
+  const double E0 = markley_starter(Mr, k);
+
+  // single high-order refinement (kepler.py refine_estimate).  d3 and d4 only feed small
+  // correction terms: a 2^-23 reciprocal for d3 and a 2^-46 one for d4 leave dE exact to
+  // < 1e-19; dE itself and the final quotient use a fully converged reciprocal.
   double sE, cE;
-  sin_cos_reduc(E0, sE, cE);
+  sin_cos_reduc(E0, sE, cE, H);
   const double s0 = E0 - sE;  // sin E0
   const double f0 = fma(k.e, sE, fma(E0, k.ome, -Mr));
   const double f1 = fma(k.e, cE, k.ome);
   const double f2 = k.e * s0;
   const double f3 = 1.0 - f1;
-  const double d3 = -f0 * f1 / fma(f1, f1, -0.5 * f0 * f2);
-  const double f36 = f3 * kC[7], f22 = 0.5 * f2;
-  const double d4 = -f0 / fma(d3 * d3, f36, fma(d3, f22, f1));
+  const double d3 = -f0 * f1 * rcp_seed(fma(f1, f1, -0.5 * f0 * f2));
+  const double f36 = f3 * H.c[7], f22 = 0.5 * f2;
+  const double d4 = -f0 * rcp_nr<1>(fma(d3 * d3, f36, fma(d3, f22, f1)));
   const double d42 = d4 * d4;
-  const double dE = -f0 / fma(-d42 * d4, f2 * kC[8], fma(d42, f36, fma(d4, f22, f1)));
+  const double dE = -f0 * rcp_nr<2>(fma(-d42 * d4, f2 * H.c[8], fma(d42, f36, fma(d4, f22, f1))));
 
   // rotate (sin E0, 1 - cos E0) by dE: |dE| <= 5e-4, 4th order is exact to < 1e-20
   const double dE2 = dE * dE;
-  const double sd = fma(-dE * dE2, kC[7], dE);                 // sin dE
-  const double cdm = dE2 * fma(dE2, -kC[8], 0.5);              // 1 - cos dE
+  const double sd = fma(-dE * dE2, H.c[7], dE);                 // sin dE
+  const double cdm = dE2 * fma(dE2, -H.c[8], 0.5);              // 1 - cos dE
   const double c0 = 1.0 - cE;                                  // cos E0
   const double s1 = s0 + fma(c0, sd, -s0 * cdm);               // sin E1
   const double cE1 = cE + fma(s0, sd, c0 * cdm);               // 1 - cos E1
+  E0_out = E0;
+  dE_out = dE;
+  s1_out = s1;
+  cE1_out = cE1;
+}
 
-  const double den = fma(k.e, cE1, k.ome);                     // 1 - e cos E1
-  const double a2s = high ? -k.a2 : k.a2;                      // sin(2pi - E) = -sin E
-  const double num = fma(k.a1, k.ome - cE1, a2s * s1);
-  return num / den + k.a3;
+// cold path for absurd frequencies (|M| >= 1e12): same arithmetic behind a generic fmod reduction
+__device__ __noinline__ double kep_rv_slow(const KepConst& k, double t) {
+  const HotConsts H = make_hot_consts();  // literals: keeps the caller free of a stack copy
+  return kep_rv<true>(k, t, H);
 }
 
 // ---- priors: support/priors/{Uniform,Normal,Jeffreys,Isotropic,Fixed}.prior ------------

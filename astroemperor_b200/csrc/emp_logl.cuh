@@ -48,6 +48,8 @@ struct LoglParams {
   double* logl;
   double t0;                  // X_[0] (acc.model uses X_ - X_[0])
   double ll_const;            // -0.5*log(2*pi)*ndat  (00.like:1)
+  double t_absmax;            // max |t|: bounds the mean anomaly per (walker, planet)
+  HotConsts H;                // FP64 literals of the hot loop, read as c[0x0][..] operands
 };
 
 constexpr size_t kLoglSmemBytes =
@@ -64,10 +66,11 @@ __device__ __forceinline__ void load_full_theta(const EmpModelDesc* __restrict__
 }
 
 // Keplerian / instrument constants of one walker from its full theta
-__device__ __forceinline__ void walker_constants(const EmpModelDesc* __restrict__ d, WalkerConst& wc, int lane) {
+__device__ __forceinline__ void walker_constants(const EmpModelDesc* __restrict__ d, WalkerConst& wc, int lane,
+                                                 double t_absmax) {
   if (lane < d->n_kep) {
     KepConst kc;
-    kep_constants(d->kep_model[lane], wc.th + d->kep_off[lane], kc);
+    kep_constants(d->kep_model[lane], wc.th + d->kep_off[lane], t_absmax, kc);
     wc.kep[lane] = kc;
   }
   if (lane < d->n_ins) {
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
   if (active) {
     slot = P.eval_index[first + warp];
     load_full_theta(d, P.theta + slot * d->ndim_free, wc.th, lane);
-    walker_constants(d, wc, lane);
+    walker_constants(d, wc, lane, P.t_absmax);
   }
   __syncthreads();  // publishes the barrier inits to all warps
 
@@ -194,8 +197,13 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
         double m0 = 0.0, m1 = 0.0;
         for (int k = 0; k < K; ++k) {
           const KepConst& kc = wc.kep[k];
-          m0 += kep_rv(kc, t2.x);
-          m1 += kep_rv(kc, t2.y);
+          if (kc.slow_mod == 0) {
+            m0 += kep_rv(kc, t2.x, P.H);
+            m1 += kep_rv(kc, t2.y, P.H);
+          } else {
+            m0 += kep_rv_slow(kc, t2.x);
+            m1 += kep_rv_slow(kc, t2.y);
+          }
         }
         if (acc_order > 0) {
           m0 += accel_term(wc.acc, acc_order, __dsub_rn(t2.x, P.t0));
@@ -266,8 +274,8 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
         }
 
         // chi^2 and log-det: sum(r^2/err2 + log err2)  (00.like:5); logs taken on 4-point products
-        chi += d0 * d0 / w0;
-        chi += d1 * d1 / w1;
+        chi = fma(d0 * d0, rcp_nr<2>(w0), chi);
+        chi = fma(d1 * d1, rcp_nr<2>(w1), chi);
         prod *= w0 * w1;
         if (++nprod == 2) { lsum += log(prod); prod = 1.0; nprod = 0; }
       }
@@ -288,16 +296,17 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
 __global__ void model_rv_kernel(const EmpModelDesc* __restrict__ d, const double* __restrict__ theta,
                                 const double* __restrict__ t, const double* __restrict__ y,
                                 const double* __restrict__ e2, const int32_t* __restrict__ ins, int64_t n,
-                                double t0, double* __restrict__ model, double* __restrict__ err2) {
+                                double t0, double t_absmax, double* __restrict__ model, double* __restrict__ err2,
+                                const HotConsts H) {
   __shared__ WalkerConst wc;
   if (threadIdx.x < 32) {
     load_full_theta(d, theta, wc.th, threadIdx.x);
-    walker_constants(d, wc, threadIdx.x);
+    walker_constants(d, wc, threadIdx.x, t_absmax);
   }
   __syncthreads();
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
     double m = 0.0;
-    for (int k = 0; k < d->n_kep; ++k) m += kep_rv(wc.kep[k], t[i]);
+    for (int k = 0; k < d->n_kep; ++k) m += wc.kep[k].slow_mod ? kep_rv_slow(wc.kep[k], t[i]) : kep_rv(wc.kep[k], t[i], H);
     if (d->acc_order > 0) m += accel_term(wc.acc, d->acc_order, __dsub_rn(t[i], t0));
     m += wc.gamma[ins[i]];
     model[i] = m;

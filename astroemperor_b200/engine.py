@@ -178,3 +178,15 @@ def fp64_peak_tflops(device: int = 0) -> float:
     v = ctypes.c_double()
     _lib.check(_lib.lib().emp_fp64_peak(int(device), ctypes.byref(v)))
     return float(v.value)
+
+
+def kepler_solve(M, ecc, device: int = 0):
+    """Device drop-in for `kepler.solve(M, ecc)` (kepler.py; kep00.model:6): E, elementwise."""
+    M = np.ascontiguousarray(M, dtype=np.float64)
+    ecc = np.asarray(ecc, dtype=np.float64)
+    scalar = ecc.ndim == 0 or ecc.size == 1
+    ecc = np.ascontiguousarray(ecc.reshape(-1) if scalar else np.broadcast_to(ecc, M.shape))
+    E = np.empty_like(M)
+    _lib.check(_lib.lib().emp_kepler_solve_host(M.ctypes.data, ecc.ctypes.data, M.size, 1 if scalar else 0,
+                                                E.ctypes.data, int(device)))
+    return E

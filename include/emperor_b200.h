@@ -180,6 +180,12 @@ int emp_logl_batch_host(EmpHandle *h, const double *theta_host, int64_t n_eval, 
  * Used by the reference's post-processing (emp.py:1546-1558). */
 int emp_model_host(EmpHandle *h, const double *theta_host, double *model_host, double *err2_host);
 
+/* kepler.solve(M, ecc) (kepler.py 0.0.7; call sites support/models/kep00.model:6 ... akep00.model:5,
+ * emp_model.py:1325): eccentric anomaly E[i] of M[i], ecc[i] (or ecc[0] if ecc_is_scalar), host
+ * buffers, same solver the likelihood kernel inlines. */
+int emp_kepler_solve_host(const double *M, const double *ecc, int64_t n, int ecc_is_scalar, double *E,
+                          int device);
+
 /* ---- parallel-tempering step -------------------------------------------- */
 
 /* One emcee RedBlue stretch-move step of every temperature held by this handle

@@ -118,3 +118,24 @@ def test_high_eccentricity_and_large_mean_anomaly():
     assert ok.sum() > 200
     rel = np.abs(ll[ok] - ref[ok]) / np.abs(ref[ok])
     assert rel.max() < 1e-10, rel.max()
+
+
+def test_absurd_frequency_takes_fmod_path():
+    """|M| >= 1e12 (period 1e-10 d): the per-(walker, planet) flag routes to the generic fmod
+    reduction; still the oracle's value (both reduce the same doubly-rounded M exactly)."""
+    from oracle.rv_oracle import RVOracle
+    g, spec = load_golden("c1_51peg_k1_p0")
+    for p in spec.blocks[0].params:
+        if p.name.startswith("Period"):
+            p.limits = [1e-11, 5.0]
+            p.prargs = float(np.log(1 / (5.0 - 1e-11)))
+    cm = spec.compile()
+    fin = np.isfinite(g["logp"])
+    th = np.tile(g["thetas"][fin][:1], (8, 1))
+    th[:, 0] = [1e-10, 3e-10, 1e-9, 4.2, 1e-10, 2.0, 7e-11, 4.23]
+    eng = _engine(cm, g)
+    ll, lp = eng.logl_batch(th)
+    orc = RVOracle(cm, g["t"], g["y"], g["yerr"], g["flag"])
+    ref, _ = orc.logl_logp_batch(th)
+    assert np.all(np.isfinite(ll))
+    assert np.max(np.abs(ll - ref) / np.abs(ref)) < 1e-10
