@@ -289,7 +289,8 @@ static int launch_logl(EmpHandle* h, const double* theta_dev, int64_t n_eval, do
   h->launches += 1;
   CUDA_TRY(cudaGetLastError());
   if (h->desc.am_enabled) {
-    int rc = am_launch(&h->am, h->d_desc, theta_dev, n_eval, logl_dev, h->stream, &h->launches);
+    int rc = am_launch(&h->am, h->d_desc, theta_dev, n_eval, h->d_index, h->d_nact, logl_dev, h->stream,
+                       &h->launches);
     if (rc) return rc;
   }
   return EMP_OK;

@@ -301,6 +301,12 @@ class CompiledModel:
             raise UnsupportedModelError("model has no OffsetBlock")
         if self.am_enabled and any(m != 5 for m in self.kep_model):
             raise UnsupportedModelError("astrometry needs AstrometryKeplerianBlock (akep00.model)")
+        if self.am_enabled and "AstrometryJitter" not in order_types:
+            raise UnsupportedModelError("astrometry needs an AstrometryJitterBlock (emp.py:1300-1311)")
+        if self.am_enabled and self.ndim_free != self.ndim_full:
+            # loglike_AM indexes the UN-expanded theta with full-theta slices (a00.like:7,
+            # emp_model.py:1633-1637): with a fixed parameter the reference reads the wrong entries
+            raise UnsupportedModelError("astrometric models with fixed parameters are undefined in the reference")
 
     def _check_order(self, types):
         """The device kernel evaluates acc -> offset -> jitter -> MA like the

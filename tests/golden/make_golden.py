@@ -259,7 +259,7 @@ def make_case(name, case):
             out.update({f"am_{k}": v for k, v in am.items()})
             # the longdouble result, split so float64 fixtures keep its extra bits
             with np.errstate(all="ignore"):
-                ll_am = np.array([ns["loglike_AM"](np.insert(th, [], [])) if np.isfinite(p) else -np.inf
+                ll_am = np.array([ns["loglike_AM"](th) if np.isfinite(p) else -np.inf
                                   for th, p in zip(thetas, lp)], dtype=np.longdouble)
             out["logl_am_hi"] = ll_am.astype(np.float64)
             out["logl_am_lo"] = (ll_am - out["logl_am_hi"].astype(np.longdouble)).astype(np.float64)
