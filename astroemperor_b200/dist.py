@@ -38,6 +38,26 @@ class LadderShard:
         self.n_local = ntemps // self.world
         self.t0 = self.rank * self.n_local
         self.local_slice = slice(self.t0, self.t0 + self.n_local)
+        self._warm = False
+
+    def warm_up(self, device):
+        """Open the NCCL point-to-point channels to every peer once (lazy connection setup would
+        otherwise land inside the first swap sweep that moves a walker across a shard edge)."""
+        if self.world == 1 or self._warm:
+            return
+        torch, td = self.torch, self.td
+        ops, bufs = [], []
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            snd = torch.zeros(8, dtype=torch.float64, device=device)
+            rcv = torch.empty(8, dtype=torch.float64, device=device)
+            bufs += [snd, rcv]
+            ops.append(td.P2POp(td.isend, snd, self._global_rank(r), group=self.group))
+            ops.append(td.P2POp(td.irecv, rcv, self._global_rank(r), group=self.group))
+        for req in td.batch_isend_irecv(ops):
+            req.wait()
+        self._warm = True
 
     def owner(self, t):
         return t // self.n_local

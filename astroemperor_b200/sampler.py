@@ -107,8 +107,11 @@ class PTSampler:
         self._src = torch.empty((self.ntemps, self.nwalkers), dtype=torch.int32, device=self.dev)
         self._n_acc = torch.zeros((max(self.ntemps - 1, 1),), dtype=torch.int32, device=self.dev)
         self._betas_dev = self._upload(self.betas)
+        self.shard.warm_up(self.dev)
 
     def _alloc_store(self, nsweeps):
+        """Make room for `nsweeps` more stored samples (capacity grows geometrically so repeated
+        run_mcmc calls do not re-allocate and copy the chain every time)."""
         torch = self.torch
         n = (nsweeps + self.thin_by - 1) // self.thin_by
         Tl, W, nd = self.shard.n_local, self.nwalkers, self.ndim
@@ -119,38 +122,61 @@ class PTSampler:
         else:
             self._chain = None
             return
+        if self._chain is None:
+            self._stored = 0
+        need = self._stored + n
+        cap = 0 if self._chain is None else self._chain.shape[0]
+        if need <= cap:
+            return
+        new_cap = max(need, 2 * cap)
         kw = dict(dtype=torch.float64, device=dev)
         if pin:
             kw["pin_memory"] = True
-        new_chain = torch.empty((n, Tl, W, nd), **kw)
-        new_ll = torch.empty((n, Tl, W), **kw)
-        new_lp = torch.empty((n, Tl, W), **kw)
-        if self._chain is not None:
-            self._chain = torch.cat([self._chain[:self._stored], new_chain])
-            self._ll = torch.cat([self._ll[:self._stored], new_ll])
-            self._lp = torch.cat([self._lp[:self._stored], new_lp])
-        else:
-            self._chain, self._ll, self._lp = new_chain, new_ll, new_lp
-            self._stored = 0
+        new = [torch.empty((new_cap, Tl, W, nd), **kw), torch.empty((new_cap, Tl, W), **kw),
+               torch.empty((new_cap, Tl, W), **kw)]
+        if self._chain is not None and self._stored:
+            for dst, src in zip(new, (self._chain, self._ll, self._lp)):
+                dst[: self._stored].copy_(src[: self._stored])
+        self._chain, self._ll, self._lp = new
 
     # ------------------------------------------------------------------------------
     def stage_draws(self, draws: SweepDraws, pinned: bool = False):
         """Copy one sweep's draws to the device (async on the current stream).  `draws` holds the
-        stretch draws of THIS rank's temperatures and the swap draws of the whole ladder."""
-        out = {}
-        for f in SweepDraws.FIELDS:
-            a = getattr(draws, f)
-            if f in ("perm", "lnu_swap") and self.ntemps < 2:
-                out[f] = None
-                continue
-            t = self.torch.from_numpy(np.ascontiguousarray(a))
-            if pinned:
-                t = t.pin_memory()
-            out[f] = t.to(self.dev, non_blocking=True)
+        stretch draws of THIS rank's temperatures and the swap draws of the whole ladder.
+        pinned=True packs all seven arrays into one reusable pinned staging buffer and issues a
+        single H2D copy (double-buffered: the previous sweep may still be reading its draws)."""
+        torch = self.torch
+        fields = [(f, getattr(draws, f)) for f in SweepDraws.FIELDS
+                  if not (f in ("perm", "lnu_swap") and self.ntemps < 2)]
+        out = {f: None for f in SweepDraws.FIELDS}
+        if not pinned:
+            for f, a in fields:
+                out[f] = torch.from_numpy(np.ascontiguousarray(a)).to(self.dev, non_blocking=True)
+            return out
+        offs, total = [], 0
+        for f, a in fields:
+            offs.append(total)
+            total += (a.nbytes + 255) // 256 * 256
+        if getattr(self, "_stage_cap", 0) < total:
+            self._stage_host = [torch.empty(total, dtype=torch.uint8).pin_memory() for _ in range(2)]
+            self._stage_dev = [torch.empty(total, dtype=torch.uint8, device=self.dev) for _ in range(2)]
+            self._stage_evt = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_cap, self._stage_i = total, 0
+        i = self._stage_i = 1 - self._stage_i
+        self._stage_evt[i].synchronize()  # the H2D that last used this pinned buffer has finished
+        host, dev = self._stage_host[i], self._stage_dev[i]
+        hv = host.numpy()
+        for (f, a), o in zip(fields, offs):
+            hv[o:o + a.nbytes] = np.ascontiguousarray(a).reshape(-1).view(np.uint8)
+        dev[:total].copy_(host[:total], non_blocking=True)
+        self._stage_evt[i].record()
+        for (f, a), o in zip(fields, offs):
+            tdt = torch.int32 if a.dtype == np.int32 else torch.float64
+            out[f] = dev[o:o + a.nbytes].view(tdt).view(a.shape)
         return out
 
-    def sweep(self, draws):
-        """nsteps stretch steps of every local temperature + one swap sweep + adaptation.
+    def sweep_begin(self, draws):
+        """Enqueue nsteps stretch steps of every local temperature + one swap sweep (asynchronous).
         `draws`: SweepDraws (host) or the dict `stage_draws` returned (already on the device)."""
         eng = self.engine
         sl = self.shard.local_slice
@@ -165,12 +191,25 @@ class PTSampler:
                                 draws["rint"][s], draws["factors"][s], draws["lnu"][s], self.accepted)
             self._n_accepted += self.accepted
             self._n_steps += 1
-        n_acc = None
+        self._pending_swap = False
         if self.ntemps > 1:
             logl_all = self.shard.all_gather_rows(self.logl)  # [T, W]; NCCL all-gather when sharded
             eng.pt_swap_plan(logl_all, self._betas_dev, draws["perm"], draws["lnu_swap"], self._src, self._n_acc)
             self._apply_plan()
-            n_acc = self._n_acc.cpu().numpy()[: self.ntemps - 1]  # syncs: 4*(T-1) bytes
+            if not hasattr(self, "_n_acc_host"):
+                self._n_acc_host = self.torch.empty(self._n_acc.shape, dtype=self.torch.int32).pin_memory()
+                self._n_acc_evt = self.torch.cuda.Event()
+            self._n_acc_host.copy_(self._n_acc, non_blocking=True)  # 4*(T-1) bytes
+            self._n_acc_evt.record()
+            self._pending_swap = True
+
+    def sweep_end(self):
+        """Wait for the swap counts of the sweep begun last and adapt the ladder (host, like the
+        oracle: bit-identical beta history)."""
+        n_acc = None
+        if self._pending_swap:
+            self._n_acc_evt.synchronize()
+            n_acc = self._n_acc_host.numpy()[: self.ntemps - 1].copy()
         self.time += 1
         self.iteration += 1
         if n_acc is not None:
@@ -182,6 +221,11 @@ class PTSampler:
                 self._betas_dev = self._upload(self.betas)
         self._beta_hist.append(self.betas.copy())
         return n_acc
+
+    def sweep(self, draws):
+        """One full sweep: stretch steps + swap sweep + ladder adaptation."""
+        self.sweep_begin(draws)
+        return self.sweep_end()
 
     def _apply_plan(self):
         eng, sh = self.engine, self.shard
@@ -206,7 +250,12 @@ class PTSampler:
         return draw_sweep(self.streams, self.nwalkers, self.ndim, nsteps, self.a,
                           temps=self.shard.local_slice, swap=self.ntemps > 1)
 
-    def run_mcmc(self, p0, nsweeps: int, nsteps: int = 1, progress: bool = False):
+    def run_mcmc(self, p0, nsweeps: int, nsteps: int = 1, progress: bool = False, on_sweep=None):
+        """sampler.run_mcmc(p1, nsweeps=, nsteps=, progress=) (support/endit_reddemcee.scr:3).
+        While the device runs sweep k the host generates the draws of sweep k+1 (same thread: a
+        background thread only fights the main thread for the GIL and stalls the launches);
+        they are staged through a reusable pinned buffer.  `on_sweep(sampler, k)` is called after
+        every sweep (bench.py uses it to read logL back)."""
         if p0 is not None:
             self._init_state(p0)
         elif not hasattr(self, "p"):
@@ -219,17 +268,26 @@ class PTSampler:
                 it = tqdm(it, total=nsweeps)
             except Exception:
                 pass
-        for k in it:
+        def draw():
             t0 = _time.perf_counter()
-            draws = self.draw(nsteps)
+            d = self.draw(nsteps)
             self.timings["draws"] += _time.perf_counter() - t0
-            self.sweep(draws)
+            return d
+
+        draws = draw() if nsweeps > 0 else None
+        for k in it:
+            self.sweep_begin(self.stage_draws(draws, pinned=True))
+            if k + 1 < nsweeps:  # the host draws the next sweep while the device runs this one
+                draws = draw()
+            self.sweep_end()
             if self._chain is not None and (k % self.thin_by == 0):
                 j = self._stored
                 self._chain[j].copy_(self.p, non_blocking=True)
                 self._ll[j].copy_(self.logl, non_blocking=True)
                 self._lp[j].copy_(self.logp, non_blocking=True)
                 self._stored += 1
+            if on_sweep is not None:
+                on_sweep(self, k)
         self.torch.cuda.synchronize(self.dev)
         return self.p
 

@@ -171,6 +171,10 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-evals", type=int, default=0, help="walkers in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--burn", type=int, default=40,
+                    help="untimed sweeps before the warm-up so that the ensemble has left its uniform "
+                         "initial state (a young chain proposes ~40%% of its moves outside the prior box, "
+                         "which are never evaluated and would flatter the step time)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -202,7 +206,9 @@ def main():
         td.broadcast_object_list(obj, src=0)
         p0 = obj[0]
     samp._init_state(p0)
-    samp._alloc_store(args.steps * 2 + args.warmup * 2)
+    samp._alloc_store(2 * args.steps + args.warmup + 4)
+    for _ in range(args.burn):
+        samp.sweep(samp.draw(1))
     peak_tf = fp64_peak_tflops(local_rank)
 
     def barrier():
@@ -242,32 +248,38 @@ def main():
     eng.set_timing(False)
     launches = eng.launch_count - l0
     c1 = eng.counters()
+    per_rank = [[ms, kern_ms, float(c1["in_prior"] - c0["in_prior"])]]
     if world > 1:
-        tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        td.all_reduce(tms, op=td.ReduceOp.MAX)
-        ms = float(tms.item())
+        mine = torch.tensor(per_rank[0], dtype=torch.float64, device="cuda")
+        allr = torch.empty((world, 3), dtype=torch.float64, device="cuda")
+        td.all_gather_into_tensor(allr, mine)
+        per_rank = allr.cpu().tolist()
+        ms = max(r[0] for r in per_rank)  # max over ranks
     value = T * W * N * args.steps / (ms * 1e-3)
     del staged
 
-    # ---------------- e2e: host draws -> pinned -> H2D -> step -> D2H --------------------------
+    # ---------------- e2e: the user's call (PTSampler.run_mcmc) with host buffers -----------------
+    # every sweep: host RNG draws -> pinned staging -> H2D -> step -> D2H read of logL[T,W]
     ll_host = torch.empty((samp.shard.n_local, W), dtype=torch.float64).pin_memory()
-    for _ in range(2):
-        samp.sweep(samp.stage_draws(samp.draw(1), pinned=True)); store()
+    io = {"d2h": 0}
+
+    def read_back(s, k):
+        ll_host.copy_(s.logl, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        io["d2h"] += ll_host.numel() * 8 + 4 * (T - 1)
+
+    samp.run_mcmc(None, nsweeps=2, nsteps=1, on_sweep=read_back)  # warm the staging buffers / thread
+    io["d2h"] = 0
+    h2d = samp.draw(1).nbytes() * args.steps  # same size every sweep
     barrier()
-    h2d = d2h = 0
     te0 = time.perf_counter()
     ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ee0.record()
-    for k in range(args.steps):
-        d = samp.draw(1)
-        h2d += d.nbytes()
-        samp.sweep(samp.stage_draws(d, pinned=True)); store()
-        ll_host.copy_(samp.logl, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        d2h += ll_host.numel() * 8 + 4 * (T - 1)
+    samp.run_mcmc(None, nsweeps=args.steps, nsteps=1, on_sweep=read_back)
     ee1.record()
     barrier()
     te1 = time.perf_counter()
+    d2h = io["d2h"]
     e2e_ms = max(ee0.elapsed_time(ee1), (te1 - te0) * 1e3)  # host-bound loops are wall-clock bound
     if world > 1:
         tms = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
@@ -309,8 +321,10 @@ def main():
            "e2e": {"value": e2e_value, "unit": "walker*temp*datapoint/s", "h2d_bytes_per_step": h2d // args.steps,
                    "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_ms / args.steps,
                    "includes": "host RNG draws, pinned staging, H2D, step, D2H of logL[T,W]"},
-           "gpu_launches": launches, "roofline": roofline,
+           "gpu_launches": launches, "burn_in_sweeps": args.burn, "roofline": roofline,
            "clocks": clocks.summary(tw0, tw1),
+           "per_rank": [{"ms_per_step": r[0] / args.steps, "kernel_ms_per_step": r[1] / args.steps,
+                         "evaluated_per_step": r[2] / args.steps} for r in per_rank],
            "acceptance_fraction": (c1["accepted"] - c0["accepted"]) / max(c1["proposals"] - c0["proposals"], 1)}
 
     if not args.no_cpu_baseline:
