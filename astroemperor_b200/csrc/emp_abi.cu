@@ -412,6 +412,18 @@ extern "C" int emp_pt_swap_plan(EmpHandle* h, int32_t T, int32_t W, const double
   if (T < 1 || W < 1) return fail(EMP_EINVAL, "bad T/W");
   if (T > 1 && (!perm || !lnu)) return fail(EMP_EINVAL, "NULL draws");
   CUDA_TRY(cudaSetDevice(h->device));
+  const size_t plan_smem = size_t(W) * 24;
+  if (plan_smem <= 200 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      CUDA_TRY(cudaFuncSetAttribute(pt_swap_plan_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    pt_swap_plan_smem_kernel<<<1, 1024, plan_smem, h->stream>>>(T, W, logl_all, betas, perm, lnu, src, n_acc);
+    h->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return EMP_OK;
+  }
   if (2 * int64_t(W) > h->cap_llwork) {
     cudaFree(h->d_llwork);
     h->d_llwork = nullptr;

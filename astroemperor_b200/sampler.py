@@ -30,7 +30,8 @@ class PTSampler:
     def __init__(self, nwalkers: int, ndim: int, log_like, log_prior=None, ntemps: int = 1, pool=None,
                  backend=None, betas=None, tsw_history: bool = True, smd_history: bool = True,
                  adapt_tau: float = 1000, adapt_nu: float = 1, adapt_mode: int = 0, a: float = 2.0,
-                 seed: Optional[int] = None, store: str = "device", thin_by: int = 1, adapt: bool = True, group=None):
+                 seed: Optional[int] = None, store: str = "device", thin_by: int = 1, adapt: bool = True, group=None,
+                 layout: str = "strided", exchange: str = "allgather"):
         """`log_like` is the LikelihoodEngine (it carries the prior as well; `log_prior`,
         `pool` and `backend` are accepted for signature compatibility and ignored — the
         walkers are evaluated on the GPU, not through a multiprocessing pool)."""
@@ -59,7 +60,10 @@ class PTSampler:
         self.store, self.thin_by = store, int(thin_by)
         self.torch = torch
         self.dev = self.engine.torch_device
-        self.shard = _dist.LadderShard(self.ntemps, group=group)
+        self.shard = _dist.LadderShard(self.ntemps, group=group, layout=layout)
+        if exchange not in ("allgather", "p2p"):
+            raise ValueError("exchange must be 'allgather' or 'p2p'")
+        self.exchange = exchange
         self.iteration = 0  # sweeps done
         self.time = 0
         self._chain = self._ll = self._lp = None
@@ -185,30 +189,55 @@ class PTSampler:
             draws = self.stage_draws(draws)
             self.timings["h2d"] += _time.perf_counter() - t0
         nsteps = draws["zz"].shape[0]
-        betas_loc = self._betas_dev[sl]
+        betas_loc = self._betas_dev[sl].contiguous()
+        self._mark("start")
         for s in range(nsteps):
             eng.pt_stretch_step(self.p, self.logl, self.logp, betas_loc, draws["half_idx"][s], draws["zz"][s],
                                 draws["rint"][s], draws["factors"][s], draws["lnu"][s], self.accepted)
             self._n_accepted += self.accepted
             self._n_steps += 1
-        self._pending_swap = False
-        if self.ntemps > 1:
-            logl_all = self.shard.all_gather_rows(self.logl)  # [T, W]; NCCL all-gather when sharded
-            eng.pt_swap_plan(logl_all, self._betas_dev, draws["perm"], draws["lnu_swap"], self._src, self._n_acc)
-            self._apply_plan()
-            if not hasattr(self, "_n_acc_host"):
-                self._n_acc_host = self.torch.empty(self._n_acc.shape, dtype=self.torch.int32).pin_memory()
-                self._n_acc_evt = self.torch.cuda.Event()
-            self._n_acc_host.copy_(self._n_acc, non_blocking=True)  # 4*(T-1) bytes
-            self._n_acc_evt.record()
-            self._pending_swap = True
+        self._swap_draws = (draws["perm"], draws["lnu_swap"]) if self.ntemps > 1 else None
+        self._mark("stretch")
+
+    def _mark(self, name):
+        """Optional device-side phase timing (self.profile = True): CUDA events on the stream, read
+        back by phase_times(); costs nothing when disabled."""
+        if not getattr(self, "profile", False):
+            return
+        ev = self.torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self._phase_events = getattr(self, "_phase_events", [])
+        self._phase_events.append((name, ev))
+
+    def phase_times(self):
+        """{phase: total ms} since the last call (synchronises)."""
+        self.torch.cuda.synchronize(self.dev)
+        out, evs = {}, getattr(self, "_phase_events", [])
+        for (n0, e0), (n1, e1) in zip(evs[:-1], evs[1:]):
+            if n1 != "start":
+                out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        self._phase_events = []
+        return out
 
     def sweep_end(self):
-        """Wait for the swap counts of the sweep begun last and adapt the ladder (host, like the
-        oracle: bit-identical beta history)."""
+        """Swap sweep of the sweep begun last (all-gather of logL when sharded, plan, row exchange),
+        then the ladder adaptation on the host from the T-1 swap counts (like the oracle:
+        bit-identical beta history).  Everything that synchronises with the device lives here so
+        that the caller can do host work (next sweep's draws) between sweep_begin and sweep_end."""
         n_acc = None
-        if self._pending_swap:
-            self._n_acc_evt.synchronize()
+        if self._swap_draws is not None:
+            perm, lnu_swap = self._swap_draws
+            self._mark("host_gap")  # device idle time while the host was busy between begin and end
+            logl_all = self.shard.all_gather_rows(self.logl)  # [T, W]; NCCL all-gather when sharded
+            self._mark("allgather")
+            self.engine.pt_swap_plan(logl_all, self._betas_dev, perm, lnu_swap, self._src, self._n_acc)
+            self._mark("plan")
+            self._apply_plan()
+            self._mark("apply")
+            if not hasattr(self, "_n_acc_host"):
+                self._n_acc_host = self.torch.empty(self._n_acc.shape, dtype=self.torch.int32).pin_memory()
+            self._n_acc_host.copy_(self._n_acc, non_blocking=True)  # 4*(T-1) bytes
+            self.torch.cuda.current_stream(self.dev).synchronize()
             n_acc = self._n_acc_host.numpy()[: self.ntemps - 1].copy()
         self.time += 1
         self.iteration += 1
@@ -233,13 +262,26 @@ class PTSampler:
             eng.pt_gather_rows(self._src.view(-1), self.p.view(-1, self.ndim), self.logl.view(-1),
                                self.logp.view(-1), self._p_alt.view(-1, self.ndim), self._ll_alt.view(-1),
                                self._lp_alt.view(-1))
-        else:
+        elif self.exchange == "p2p":
+            # point-to-point exchange of exactly the rows that change rank (dist.exchange_rows)
             rows = self.torch.cat([self.p.view(-1, self.ndim), self.logl.view(-1, 1), self.logp.view(-1, 1)], 1)
             staged, src_local = sh.exchange_rows(self._src, rows, self.nwalkers)
             pin = staged[:, : self.ndim].contiguous()
             llin = staged[:, self.ndim].contiguous()
             lpin = staged[:, self.ndim + 1].contiguous()
             eng.pt_gather_rows(src_local, pin, llin, lpin, self._p_alt.view(-1, self.ndim),
+                               self._ll_alt.view(-1), self._lp_alt.view(-1))
+        else:
+            # all-gather the ensemble over NVLink and gather locally: no host synchronisation, no
+            # index compaction; T*W*(ndim+2)*8 bytes per sweep (150 MB at 256 x 2048 x 35, ~0.3 ms
+            # of NVSwitch all-gather) buys back ~1.5 ms of latency-bound list building
+            W, nl = self.nwalkers, sh.n_local * self.nwalkers
+            p_all, ll_all, lp_all = sh.all_gather_flat(self.p.view(-1, self.ndim), self.logl.view(-1),
+                                                       self.logp.view(-1))
+            sg = self._src[sh.local_slice].reshape(-1).to(self.torch.int64)
+            st, sw = sg // W, sg % W
+            pos = (sh.owner_of_temp(st) * nl + sh.local_of_temp(st) * W + sw).to(self.torch.int32)
+            eng.pt_gather_rows(pos, p_all, ll_all, lp_all, self._p_alt.view(-1, self.ndim),
                                self._ll_alt.view(-1), self._lp_alt.view(-1))
         self.p, self._p_alt = self._p_alt, self.p
         self.logl, self._ll_alt = self._ll_alt, self.logl

@@ -232,6 +232,8 @@ def main():
         samp.sweep(samp.draw(1)); store()
     staged = [samp.stage_draws(samp.draw(1)) for _ in range(args.steps)]
     eng.set_timing(True)
+    samp.profile = True
+    samp.phase_times()
     c0 = eng.counters()
     l0 = eng.launch_count
     barrier()
@@ -246,6 +248,8 @@ def main():
     ms = ev0.elapsed_time(ev1)
     kern_ms, kern_n = eng.timing_collect()
     eng.set_timing(False)
+    phases = samp.phase_times()
+    samp.profile = False
     launches = eng.launch_count - l0
     c1 = eng.counters()
     per_rank = [[ms, kern_ms, float(c1["in_prior"] - c0["in_prior"])]]
@@ -323,6 +327,7 @@ def main():
                    "includes": "host RNG draws, pinned staging, H2D, step, D2H of logL[T,W]"},
            "gpu_launches": launches, "burn_in_sweeps": args.burn, "roofline": roofline,
            "clocks": clocks.summary(tw0, tw1),
+           "phase_ms_per_step_rank0": {k: v / args.steps for k, v in phases.items()},
            "per_rank": [{"ms_per_step": r[0] / args.steps, "kernel_ms_per_step": r[1] / args.steps,
                          "evaluated_per_step": r[2] / args.steps} for r in per_rank],
            "acceptance_fraction": (c1["accepted"] - c0["accepted"]) / max(c1["proposals"] - c0["proposals"], 1)}

@@ -137,7 +137,7 @@ def test_unsupported_blocks_raise():
 
 
 # ------------------------------------------------------------ ladder sharding ----
-def _dist_worker(rank, world, port, T, W, C, seed, q):
+def _dist_worker(rank, world, port, T, W, C, seed, layout, q):
     import torch
     import torch.distributed as td
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -154,7 +154,7 @@ def _dist_worker(rank, world, port, T, W, C, seed, q):
         lnu = np.log(rng.uniform(size=(T - 1, W)))
         p = rows.copy()
         _, src, _ = swap_sweep(p, ll.copy(), np.zeros((T, W)), betas, perm, lnu)  # p is now the expected result
-        sh = LadderShard(T)
+        sh = LadderShard(T, layout=layout)
         assert sh.world == world and sh.n_local == T // world
         local = torch.from_numpy(rows[sh.local_slice].reshape(-1, C).copy())
         # all-gather of the local logL reproduces the global array
@@ -164,18 +164,25 @@ def _dist_worker(rank, world, port, T, W, C, seed, q):
         new = staged[src_local.long()].numpy().reshape(sh.n_local, W, C)
         ok = np.array_equal(new, p[sh.local_slice])
         n_remote = staged.shape[0] - local.shape[0]
+        # the all-gather variant of the same step (sampler._apply_plan, exchange="allgather")
+        (allr,) = sh.all_gather_flat(local)
+        sg = torch.from_numpy(src)[sh.local_slice].reshape(-1).long()
+        st, sw = sg // W, sg % W
+        pos = sh.owner_of_temp(st) * (sh.n_local * W) + sh.local_of_temp(st) * W + sw
+        ok = ok and np.array_equal(allr[pos].numpy().reshape(sh.n_local, W, C), p[sh.local_slice])
         q.put((rank, ok, n_remote))
     finally:
         td.destroy_process_group()
 
 
-@pytest.mark.parametrize("T,W", [(4, 16), (6, 10)])
-def test_sharded_swap_exchange_two_ranks_gloo(T, W):
+@pytest.mark.parametrize("T,W,layout", [(4, 16, "contiguous"), (6, 10, "contiguous"), (4, 16, "strided"),
+                                        (8, 10, "strided")])
+def test_sharded_swap_exchange_two_ranks_gloo(T, W, layout):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000) + T
-    procs = [ctx.Process(target=_dist_worker, args=(r, 2, port, T, W, 5, 3, q)) for r in range(2)]
+    port = 29500 + (os.getpid() % 2000) + T + (17 if layout == "strided" else 0)
+    procs = [ctx.Process(target=_dist_worker, args=(r, 2, port, T, W, 5, 3, layout, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
