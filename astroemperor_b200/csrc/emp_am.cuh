@@ -131,13 +131,14 @@ __device__ inline void lin_prop_pa(const double* obs, double time_refed, double*
 __device__ __forceinline__ void am_orbit(const AmPlanet& p, double t, const HotConsts& H, double& ras, double& dec,
                                          double& plx) {
   const double M = __dadd_rn(__dmul_rn(p.k.freq, t), p.pha);
-  const double r0 = (fabs(M) < 1.0e12) ? mod_two_pi(M, H) : mod_two_pi_slow(M);
-  const bool high = r0 > H.c[0];
-  const double Mr = high ? __dsub_rn(H.c[1], r0) : r0;
+  int sign_hi;
+  const double Mr = (fabs(M) < 1.0e12) ? fold_anomaly(M, H, sign_hi) : fold_anomaly_slow(M, sign_hi);
   double E0, dE, s1, cE1;
-  kepler_refined(Mr, p.k, H, E0, dE, s1, cE1);
+  bool bad = false;
+  kepler_refined<false>(Mr, p.k, H, E0, dE, s1, cE1, bad);
+  if (bad) kepler_refined<true>(Mr, p.k, H, E0, dE, s1, cE1, bad);
   const double X = p.k.ome - cE1;              // cos E - e
-  const double Y = p.sq * (high ? -s1 : s1);   // sqrt(1-e^2) sin E
+  const double Y = p.sq * flip_sign(s1, sign_hi);  // sqrt(1-e^2) sin E
   ras += p.beta * (p.B * X + p.G * Y);
   dec += p.beta * (p.A * X + p.F * Y);
   plx += p.plxfac * (p.C * X + p.Hc * Y);

@@ -167,12 +167,34 @@ __device__ __forceinline__ double mod_two_pi(double M, const HotConsts& H) {
   return r;  // valid for |M| < 1e12 (KepConst::slow_mod routes everything else to fmod)
 }
 
+// Folded mean anomaly Mr in [0, pi] and the sign bit of the fold (0x80000000 when the solver's
+// E must be reflected to 2pi - E).  The centred remainder r = M - rint(M/2pi)*2pi is exact, and
+// kepler.py's "wrap to [0, 2pi), reflect if > pi" is exactly (|r|, r < 0): for r < 0 the wrap
+// gives r + 2pi (exact) and the reflection 2pi - (r + 2pi) = -r (exact).  No compare, no select.
+__device__ __forceinline__ double fold_anomaly(double M, const HotConsts& H, int& sign_hi) {
+  const double kd = __dsub_rn(__dadd_rn(__dmul_rn(M, H.c[4]), H.c[5]), H.c[5]);
+  const double r = __fma_rn(-kd, H.c[1], M);
+  sign_hi = __double2hiint(r) & 0x80000000;
+  return fabs(r);
+}
+__device__ __forceinline__ double fold_anomaly_slow(double M, int& sign_hi) {  // generic fmod path
+  const double r0 = mod_two_pi_slow(M);
+  const bool high = r0 > kPi;
+  sign_hi = high ? 0x80000000 : 0;
+  return high ? __dsub_rn(kTwoPi, r0) : r0;
+}
+__device__ __forceinline__ double flip_sign(double x, int sign_hi) {
+  return __hiloint2double(__double2hiint(x) ^ sign_hi, __double2loint(x));
+}
+
 // ---- x - sin x and 1 - cos x on [0, pi] (Nijenhuis-style folding, Taylor core) ----------
 __device__ __forceinline__ void sin_cos_reduc(double x, double& sn, double& cs, const HotConsts& H) {
-  bool bigg = x > H.c[2];
-  double u = bigg ? H.c[0] - x : x;
-  bool big = u > H.c[3];
-  double v = big ? H.c[2] - u : u;
+  // (selects, not c - |x - c|: the folded value must stay EXACT for small x, where E - sin E
+  // needs its full relative accuracy)
+  const bool bigg = x > H.c[2];
+  const double u = bigg ? H.c[0] - x : x;
+  const bool big = u > H.c[3];
+  const double v = big ? H.c[2] - u : u;
   double w = v * v;
   // Estrin evaluation (depth 4 instead of 8): coefficients are stored highest degree first
   const double w2 = w * w, w4 = w2 * w2;
@@ -226,7 +248,7 @@ __device__ __noinline__ double markley_starter_f64(double Mr, double e, double o
 // Same starter in FP32 on the FMA/MUFU pipes (they issue in the slots the half-rate FP64 pipe
 // leaves free).  The starter is only an initial guess with an intrinsic error of ~4e-4; its
 // FP32 rounding (1e-7) changes the refined root by < 1e-18 (tests/test_kepler_device.py).
-__device__ __forceinline__ double markley_starter(double Mr, const KepConst& k) {
+__device__ __forceinline__ double markley_starter(double Mr, const KepConst& k, bool& bad) {
   const float M = __double2float_rn(Mr);
   const float M2 = M * M;
   const float alpha = fmaf(k.c2f, 3.14159274f - M, 7.64804745f /* F1 */);
@@ -239,28 +261,32 @@ __device__ __forceinline__ double markley_starter(double Mr, const KepConst& k) 
   const float w = f32_ex2(0.666666687f * f32_lg2(x));  // x^(2/3)
   const float den0 = fmaf(w, w + q, q2);
   const float E0f = fmaf(2.0f * r, w, M * den0) * f32_rcp(den0 * d);
-  double E0 = double(E0f);
-  if (!(M > 1e-15f) || !(E0f == E0f) || !(fabsf(E0f) < 4.0f)) E0 = markley_starter_f64(Mr, k.e, k.ome);
-  return E0;
+  // no branch here: a slow-path call in the middle of the point's arithmetic is a scheduling
+  // barrier that keeps the compiler from interleaving the two points a lane works on.  The caller
+  // redoes flagged points (M ~ 0, NaN, out of range) on the cold FP64 path afterwards.
+  bad = !(M > 1e-15f) || !(fabsf(E0f) < 4.0f);
+  return double(E0f);
 }
 
 // Kepler's equation for a folded mean anomaly Mr in [0, pi]: returns the pre-refinement
 // estimate E0 and the correction dE (E = E0 + dE), plus sin E and 1 - cos E of the refined E.
+template <bool kCold>
 __device__ __forceinline__ void kepler_refined(double Mr, const KepConst& k, const HotConsts& H, double& E0_out,
-                                               double& dE_out, double& s1_out, double& cE1_out);
+                                               double& dE_out, double& s1_out, double& cE1_out, bool& bad);
 
 // One Keplerian's RV at time t (everything of kep00.model:4-8 for one point).
-template <bool kSlow = false>
-__device__ __forceinline__ double kep_rv(const KepConst& k, double t, const HotConsts& H) {
+// kCold = false: branch-free fast path, `bad` tells the caller to redo the point with kCold = true
+// (FP64 starter, fmod reduction where the walker needs it).
+template <bool kCold>
+__device__ __forceinline__ double kep_rv(const KepConst& k, double t, const HotConsts& H, bool& bad) {
   const double M = mean_anomaly(k, t);
-  const double r0 = kSlow ? mod_two_pi_slow(M) : mod_two_pi(M, H);
-  const bool high = r0 > H.c[0];
-  const double Mr = high ? __dsub_rn(H.c[1], r0) : r0;
+  int sign_hi;
+  const double Mr = (kCold && k.slow_mod) ? fold_anomaly_slow(M, sign_hi) : fold_anomaly(M, H, sign_hi);
   double E0, dE, s1, cE1;
-  kepler_refined(Mr, k, H, E0, dE, s1, cE1);
+  kepler_refined<kCold>(Mr, k, H, E0, dE, s1, cE1, bad);
   const double den = fma(k.e, cE1, k.ome);                     // 1 - e cos E1
-  const double a2s = high ? -k.a2 : k.a2;                      // sin(2pi - E) = -sin E
-  const double num = fma(k.a1, k.ome - cE1, a2s * s1);
+  const double s1s = flip_sign(s1, sign_hi);                   // sin(2pi - E) = -sin E
+  const double num = fma(k.a1, k.ome - cE1, k.a2 * s1s);
   return fma(num, rcp_nr<2>(den), k.a3);
 }
 
@@ -273,18 +299,20 @@ __device__ __forceinline__ double kepler_solve(double M, double ecc, const HotCo
   k.omef = float(k.ome);
   k.c2f = float(kF2 / (1.0 + ecc));
   k.ome3f = 3.0f * k.omef;
-  const double r0 = (fabs(M) < 1.0e12) ? mod_two_pi(M, H) : mod_two_pi_slow(M);
-  const bool high = r0 > H.c[0];
-  const double Mr = high ? __dsub_rn(H.c[1], r0) : r0;
+  int sign_hi;
+  const double Mr = (fabs(M) < 1.0e12) ? fold_anomaly(M, H, sign_hi) : fold_anomaly_slow(M, sign_hi);
   double E0, dE, s1, cE1;
-  kepler_refined(Mr, k, H, E0, dE, s1, cE1);
+  bool bad = false;
+  kepler_refined<false>(Mr, k, H, E0, dE, s1, cE1, bad);
+  if (bad) kepler_refined<true>(Mr, k, H, E0, dE, s1, cE1, bad);
   const double E = E0 + dE;
-  return high ? H.c[1] - E : E;
+  return sign_hi ? H.c[1] - E : E;
 }
 
+template <bool kCold>
 __device__ __forceinline__ void kepler_refined(double Mr, const KepConst& k, const HotConsts& H, double& E0_out,
-                                               double& dE_out, double& s1_out, double& cE1_out) {
-  const double E0 = markley_starter(Mr, k);
+                                               double& dE_out, double& s1_out, double& cE1_out, bool& bad) {
+  const double E0 = kCold ? markley_starter_f64(Mr, k.e, k.ome) : markley_starter(Mr, k, bad);
 
   // single high-order refinement (kepler.py refine_estimate).  d3 and d4 only feed small
   // correction terms: a 2^-23 reciprocal for d3 and a 2^-46 one for d4 leave dE exact to
@@ -315,10 +343,20 @@ __device__ __forceinline__ void kepler_refined(double Mr, const KepConst& k, con
   cE1_out = cE1;
 }
 
-// cold path for absurd frequencies (|M| >= 1e12): same arithmetic behind a generic fmod reduction
-__device__ __noinline__ double kep_rv_slow(const KepConst& k, double t) {
+// cold path: FP64 starter (M ~ 0 / non-finite FP32 starter) and, for walkers with absurd
+// frequencies (|M| >= 1e12), the generic fmod reduction.  Same arithmetic otherwise.
+__device__ __noinline__ double kep_rv_cold(const KepConst& k, double t) {
   const HotConsts H = make_hot_consts();  // literals: keeps the caller free of a stack copy
-  return kep_rv<true>(k, t, H);
+  bool bad = false;
+  return kep_rv<true>(k, t, H, bad);
+}
+
+// fast path + immediate fix-up (for the kernels that are not throughput critical)
+__device__ __forceinline__ double kep_rv_checked(const KepConst& k, double t, const HotConsts& H) {
+  bool bad = false;
+  double r = kep_rv<false>(k, t, H, bad);
+  if (bad || k.slow_mod) r = kep_rv_cold(k, t);
+  return r;
 }
 
 // ---- priors: support/priors/{Uniform,Normal,Jeffreys,Isotropic,Fixed}.prior ------------

@@ -197,13 +197,15 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
         double m0 = 0.0, m1 = 0.0;
         for (int k = 0; k < K; ++k) {
           const KepConst& kc = wc.kep[k];
-          if (kc.slow_mod == 0) {
-            m0 += kep_rv(kc, t2.x, P.H);
-            m1 += kep_rv(kc, t2.y, P.H);
-          } else {
-            m0 += kep_rv_slow(kc, t2.x);
-            m1 += kep_rv_slow(kc, t2.y);
+          bool b0 = false, b1 = false;
+          double r0 = kep_rv<false>(kc, t2.x, P.H, b0);  // straight-line code for both points:
+          double r1 = kep_rv<false>(kc, t2.y, P.H, b1);  // the scheduler interleaves the two chains
+          if (__any_sync(0xffffffffu, b0 || b1 || kc.slow_mod)) {  // rare: redo on the cold path
+            if (b0 || kc.slow_mod) r0 = kep_rv_cold(kc, t2.x);
+            if (b1 || kc.slow_mod) r1 = kep_rv_cold(kc, t2.y);
           }
+          m0 += r0;
+          m1 += r1;
         }
         if (acc_order > 0) {
           m0 += accel_term(wc.acc, acc_order, __dsub_rn(t2.x, P.t0));
@@ -306,7 +308,7 @@ __global__ void model_rv_kernel(const EmpModelDesc* __restrict__ d, const double
   __syncthreads();
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
     double m = 0.0;
-    for (int k = 0; k < d->n_kep; ++k) m += wc.kep[k].slow_mod ? kep_rv_slow(wc.kep[k], t[i]) : kep_rv(wc.kep[k], t[i], H);
+    for (int k = 0; k < d->n_kep; ++k) m += kep_rv_checked(wc.kep[k], t[i], H);
     if (d->acc_order > 0) m += accel_term(wc.acc, d->acc_order, __dsub_rn(t[i], t0));
     m += wc.gamma[ins[i]];
     model[i] = m;
