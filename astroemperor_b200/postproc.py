@@ -1,0 +1,156 @@
+"""Host-side reductions over the stored chains.
+
+These are the read-back calls the reference's parent process makes on the sampler after a
+run (`emp.py:1375-1385` autocorrelation time, `emp.py:1432-1447` evidence, `emp.py:722-762`
+HDF5 dump).  They run once per run on [T, n, W] arrays that were copied back from the GPU;
+plain NumPy, not part of the hot path.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+# ---- integrated autocorrelation time (emcee 3 `autocorr.integrated_time`, Sokal window) -------
+def _next_pow_two(n):
+    i = 1
+    while i < n:
+        i = i << 1
+    return i
+
+
+def function_1d(x):
+    """Normalised autocorrelation function of a 1-D series (FFT)."""
+    x = np.atleast_1d(x)
+    n = _next_pow_two(len(x))
+    f = np.fft.fft(x - np.mean(x), n=2 * n)
+    acf = np.fft.ifft(f * np.conjugate(f))[: len(x)].real
+    acf /= acf[0]
+    return acf
+
+
+def _auto_window(taus, c):
+    m = np.arange(len(taus)) < c * taus
+    if np.any(m):
+        return int(np.argmin(m))
+    return len(taus) - 1
+
+
+def integrated_time(x, c=5, tol=50, quiet=False):
+    """x [n_steps, n_walkers, ndim] -> tau [ndim] (emcee's estimator: walker-averaged ACF,
+    automated windowing M >= c*tau).  Raises unless the chain is longer than tol*tau, or warns
+    when `quiet`."""
+    x = np.atleast_1d(x)
+    if x.ndim == 1:
+        x = x[:, None, None]
+    if x.ndim == 2:
+        x = x[:, :, None]
+    n_t, n_w, n_d = x.shape
+    tau_est = np.empty(n_d)
+    windows = np.empty(n_d, dtype=int)
+    for d in range(n_d):
+        f = np.zeros(n_t)
+        for k in range(n_w):
+            f += function_1d(x[:, k, d])
+        f /= n_w
+        taus = 2.0 * np.cumsum(f) - 1.0
+        windows[d] = _auto_window(taus, c)
+        tau_est[d] = taus[windows[d]]
+    flag = tol * tau_est > n_t
+    if np.any(flag) and tol > 0:
+        msg = (f"The chain is shorter than {tol} times the integrated autocorrelation time for "
+               f"{int(np.sum(flag))} parameter(s). Use this estimate with caution; N/{tol} = {n_t / tol:.0f}; "
+               f"tau: {tau_est}")
+        if not quiet:
+            raise RuntimeError(msg)
+        import warnings
+        warnings.warn(msg)
+    return tau_est
+
+
+# ---- evidence ---------------------------------------------------------------------------------
+def _sorted_by_beta(betas, *arrs):
+    order = np.argsort(betas)
+    return (np.asarray(betas)[order],) + tuple(np.asarray(a)[order] for a in arrs)
+
+
+def evidence_ti(logl, betas):
+    """Thermodynamic integration: logZ = int_0^1 <logL>_beta dbeta, trapezoid over the ladder
+    (logl [T, n_samples]).  Error = |full - every-other-rung| (ptemcee convention)."""
+    mean_ll = np.mean(np.reshape(logl, (len(betas), -1)), axis=1)
+    b, m = _sorted_by_beta(betas, mean_ll)
+    if b[0] > 0:
+        b, m = np.concatenate([[0.0], b]), np.concatenate([[m[0]], m])
+    trap = np.trapezoid if hasattr(np, "trapezoid") else np.trapz
+    logz = float(trap(m, b))
+    b2, m2 = b[::2], m[::2]
+    if b2[-1] != b[-1]:
+        b2, m2 = np.append(b2, b[-1]), np.append(m2, m[-1])
+    return logz, abs(logz - float(trap(m2, b2)))
+
+
+def evidence_ss(logl, betas, n_batches=8):
+    """Stepping-stone estimator (Xie et al. 2011): logZ = sum_i log < exp((b_{i+1}-b_i) logL) >_{b_i}
+    over the ladder from the hottest to the coldest rung; error from `n_batches` batch means."""
+    ll = np.reshape(logl, (len(betas), -1))
+    b, ll = _sorted_by_beta(betas, ll)
+
+    def ss(sub):
+        tot = 0.0
+        lo_b, lo_l = b, sub
+        if b[0] > 0:  # bridge from beta = 0 with the hottest samples
+            lo_b = np.concatenate([[0.0], b])
+            lo_l = np.concatenate([sub[:1], sub])
+        for i in range(len(lo_b) - 1):
+            x = (lo_b[i + 1] - lo_b[i]) * lo_l[i]
+            mx = np.max(x)
+            tot += mx + np.log(np.mean(np.exp(x - mx)))
+        return tot
+
+    logz = ss(ll)
+    n = ll.shape[1]
+    if n >= 2 * n_batches:
+        parts = [ss(ll[:, k * (n // n_batches):(k + 1) * (n // n_batches)]) for k in range(n_batches)]
+        err = float(np.std(parts, ddof=1) / np.sqrt(n_batches))
+    else:
+        err = float("nan")
+    return float(logz), err
+
+
+# ---- chain sink in the reference's backend layout (emp.py:722-762) ------------------------------
+def save_backend(sampler, name, discard=0):
+    """Dump the run in the layout EMPEROR writes after a reddemcee run: per temperature
+    `chain[iter, W, ndim]`, `log_like`, `log_prob`, `beta_history`, `accepted` (+ `tsw_history`,
+    `smd_history`, `iteration`).  With h5py installed it writes `<name>.h5` and `<name>_<t>.h5`
+    groups named 'mcmc' like `reddemcee.hdf.PTHDFBackend`; without it (this image) an `.npz`
+    with the same dataset names."""
+    chain = sampler.get_chain(discard=discard)           # [T, n, W, ndim]
+    ll = sampler.get_log_like(discard=discard)
+    lpost = sampler.get_log_prob(discard=discard)
+    betas = sampler.get_betas(discard=discard)           # [n, T]
+    accepted = sampler.acceptance_fraction * max(sampler._n_steps, 1)
+    tsw, smd = sampler.get_tsw(discard=discard), sampler.get_smd(discard=discard)
+    T, n = chain.shape[0], chain.shape[1]
+    try:
+        import h5py
+    except ImportError:
+        h5py = None
+    if h5py is None:
+        path = name + ".npz"
+        np.savez_compressed(path, chain=chain, log_like=ll, log_prob=lpost, beta_history=betas,
+                            accepted=accepted, tsw_history=tsw, smd_history=smd, iteration=n)
+        return path
+    with h5py.File(name + ".h5", "w") as f:
+        g = f.create_group("mcmc")
+        g.attrs["iteration"], g.attrs["ntemps"] = n, T
+        g.create_dataset("tsw_history", data=tsw)
+        g.create_dataset("smd_history", data=smd)
+    for t in range(T):
+        with h5py.File(f"{name}_{t}.h5", "w") as f:
+            g = f.create_group("mcmc")
+            g.attrs["iteration"] = n
+            g.create_dataset("chain", data=chain[t])
+            g.create_dataset("log_like", data=ll[t])
+            g.create_dataset("log_prob", data=lpost[t])
+            g.create_dataset("beta_history", data=betas[:, t])
+            g.create_dataset("accepted", data=accepted[t])
+    return name + ".h5"

@@ -234,6 +234,8 @@ class PTSampler:
             self._mark("plan")
             self._apply_plan()
             self._mark("apply")
+            if self.smd_history_bool and self.D_ is not None:
+                self._record_smd()
             if not hasattr(self, "_n_acc_host"):
                 self._n_acc_host = self.torch.empty(self._n_acc.shape, dtype=self.torch.int32).pin_memory()
             self._n_acc_host.copy_(self._n_acc, non_blocking=True)  # 4*(T-1) bytes
@@ -368,8 +370,29 @@ class PTSampler:
     def get_tsw(self, discard=0):
         return np.array(self._tsw_hist)[discard:]
 
+    def _record_smd(self):
+        """Swap mean distance of this sweep (consumers emp.py:961-965, 1985-1990): for every
+        temperature the mean, over the slots that received a walker from a hotter rung, of the
+        distance between the walker that left and the one that arrived, in units of the prior
+        widths `sampler.D_` (emp.py:595-602).  Device-side torch arithmetic on [T_loc, W, ndim]."""
+        torch, sh, W = self.torch, self.shard, self.nwalkers
+        if getattr(self, "_D_dev", None) is None or self._D_dev.shape[0] != self.ndim:
+            self._D_dev = self._upload(np.asarray(self.D_, dtype=np.float64))
+        src_t = self._src[sh.local_slice].to(torch.int64) // W                      # [T_loc, W]
+        dest_t = torch.arange(self.ntemps, device=self.dev)[sh.local_slice].unsqueeze(1)
+        came_down = src_t > dest_t
+        dist = (((self.p - self._p_alt) / self._D_dev) ** 2).sum(-1).sqrt()           # new vs old content
+        num = (dist * came_down).sum(1)
+        cnt = came_down.sum(1).clamp(min=1)
+        self._smd_hist.append(num / cnt)
+
     def get_smd(self, discard=0):
-        return np.array(self._smd_hist)[discard:]
+        """[n_sweeps, T-1] swap mean distances (rung j <-> j+1); needs `sampler.D_`."""
+        if not self._smd_hist:
+            return np.zeros((0, max(self.ntemps - 1, 0)))
+        x = self.torch.stack(self._smd_hist)                                         # [n, T_loc]
+        x = self.shard.gather_to_all(x, dim=1) if self.shard.world > 1 else x
+        return x.cpu().numpy()[discard:, : self.ntemps - 1]
 
     @property
     def acceptance_fraction(self):
@@ -385,22 +408,37 @@ class PTSampler:
             p, ll, lp = (self.shard.gather_to_all(x, dim=0) for x in (p, ll, lp))
         return p.cpu().numpy(), ll.cpu().numpy(), lp.cpu().numpy()
 
-    def get_evidence_ti(self, discard=0):
-        """Thermodynamic-integration log-evidence: trapezoid of <logL>_beta over beta
-        (the simplest of the estimators emp.py:1432-1447 falls back through)."""
-        ll = self.get_log_like(discard=discard)  # [T, n, W]
-        mean_ll = ll.reshape(ll.shape[0], -1).mean(axis=1)
-        b = self.betas
-        order = np.argsort(b)
-        b, m = b[order], mean_ll[order]
-        if b[0] > 0:
-            b, m = np.concatenate([[0.0], b]), np.concatenate([[m[0]], m])
-        logz = float(np.trapezoid(m, b)) if hasattr(np, "trapezoid") else float(np.trapz(m, b))
-        b2, m2 = b[::2], m[::2]
-        if b2[-1] != b[-1]:
-            b2, m2 = np.append(b2, b[-1]), np.append(m2, m[-1])
-        logz2 = float(np.trapezoid(m2, b2)) if hasattr(np, "trapezoid") else float(np.trapz(m2, b2))
-        return logz, abs(logz - logz2)
+    # ---- post-run reductions (emp.py:1375-1385, 1432-1447; host NumPy, postproc.py) ----------
+    def get_evidence_ti(self, discard=0, pchip=False):
+        """Thermodynamic-integration log-evidence: trapezoid of <logL>_beta over beta (the
+        estimator emp.py:1432-1447 falls back to; `pchip` is accepted and ignored)."""
+        from .postproc import evidence_ti
+        return evidence_ti(self.get_log_like(discard=discard), self.betas)
+
+    def get_evidence_ss(self, discard=0):
+        """Stepping-stone log-evidence with a batch-means error."""
+        from .postproc import evidence_ss
+        return evidence_ss(self.get_log_like(discard=discard), self.betas)
+
+    def get_evidence_hybrid(self, discard=0):
+        """reddemcee's 'hybrid' estimator is not recoverable offline: this returns the
+        stepping-stone value with the TI/SS discrepancy added in quadrature to its error."""
+        z_ss, e_ss = self.get_evidence_ss(discard=discard)
+        z_ti, e_ti = self.get_evidence_ti(discard=discard)
+        err = float(np.sqrt(np.nan_to_num(e_ss) ** 2 + (z_ss - z_ti) ** 2))
+        return z_ss, err
+
+    def get_autocorr_time(self, discard=0, thin=1, quiet=False, tol=50, c=5):
+        """[T, ndim] integrated autocorrelation times of the stored chains (emcee's estimator),
+        in units of stored samples x thin."""
+        from .postproc import integrated_time
+        ch = self.get_chain(discard=discard, thin=thin)  # [T, n, W, ndim]
+        return np.array([thin * integrated_time(ch[t], c=c, tol=tol, quiet=quiet) for t in range(ch.shape[0])])
+
+    def save_backend(self, name, discard=0):
+        """Chain sink in the layout EMPEROR writes after a run (emp.py:722-762)."""
+        from .postproc import save_backend
+        return save_backend(self, name, discard=discard)
 
 
 def _adapt_ladder(betas, ratios, time, adapt_tau, adapt_nu):

@@ -112,3 +112,39 @@ def test_swap_moves_walkers_down_several_rungs():
     n_o, src_o, _ = swap_sweep(p, ll.copy(), np.zeros((T, W)), betas, perm, lnu)
     assert np.array_equal(src.cpu().numpy(), src_o) and np.array_equal(n_acc.cpu().numpy(), n_o)
     assert (T - 1) * W + 2 in src_o[0]  # the hot walker reached the coldest chain
+
+
+def test_postprocessing_reductions_and_smd(tmp_path):
+    """smd history, autocorrelation time, TI / stepping-stone evidence,
+    chain sink in the reference's backend layout."""
+    T = 24  # fixed ladder down to beta = 1e-7 so that the estimators see (almost) the prior
+    g, spec, eng, samp, orc, p0 = _setup("c1_51peg_k0", T, 32, seed=2, betas=np.geomspace(1, 1e-7, T), adapt=False)
+    samp.D_ = spec.prior_widths()
+    samp.run_mcmc(p0, nsweeps=400, nsteps=2, progress=False)
+    smd = samp.get_smd()
+    assert smd.shape == (400, T - 1) and np.all(smd >= 0) and smd[5:].mean() > 0
+    tau = samp.get_autocorr_time(discard=100, quiet=True)
+    assert tau.shape == (T, eng.ndim) and np.all(np.isfinite(tau)) and np.all(tau > 0)
+    with pytest.raises(RuntimeError):
+        samp.get_autocorr_time(discard=380, quiet=False, tol=1000)
+    z_ti, e_ti = samp.get_evidence_ti(discard=100)
+    z_ss, e_ss = samp.get_evidence_ss(discard=100)
+    z_hy, e_hy = samp.get_evidence_hybrid(discard=100)
+    assert np.isfinite([z_ti, z_ss, z_hy, e_ti, e_hy]).all() and z_hy == z_ss
+    # 2-parameter model (offset + jitter): evidence by brute-force quadrature over the prior box
+    fp = spec.free_params()
+    g0 = np.linspace(fp[0].limits[0], fp[0].limits[1], 1201)
+    g1 = np.linspace(fp[1].limits[0], fp[1].limits[1], 1201)
+    G0, G1 = np.meshgrid(g0, g1, indexing="ij")
+    ll, lp = eng.logl_batch(np.column_stack([G0.ravel(), G1.ravel()]))
+    post = (ll + lp).reshape(G0.shape)
+    mx = post.max()
+    trap = np.trapezoid if hasattr(np, "trapezoid") else np.trapz
+    logz_ref = mx + np.log(trap(trap(np.exp(post - mx), g1, axis=1), g0))
+    print(f"logZ: stepping-stone {z_ss:.3f} +- {e_ss:.3f}, TI {z_ti:.3f} +- {e_ti:.3f}, quadrature {logz_ref:.3f}")
+    assert abs(z_ss - logz_ref) < 0.5 and abs(z_ti - logz_ref) < 2.0, (z_ss, z_ti, logz_ref)
+    path = samp.save_backend(str(tmp_path / "run"), discard=10)
+    assert path.endswith((".npz", ".h5"))
+    if path.endswith(".npz"):
+        d = np.load(path)
+        assert d["chain"].shape == (T, 390, 32, eng.ndim) and d["beta_history"].shape == (390, T)
