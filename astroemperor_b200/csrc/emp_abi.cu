@@ -83,6 +83,13 @@ static int validate_desc(const EmpModelDesc* d) {
   if (d->ma_order < 0 || d->ma_order > EMP_MAX_MA) return fail(EMP_EINVAL, "bad ma_order");
   if (d->ma_mode < EMP_MA_NONE || d->ma_mode > EMP_MA_GLOBAL) return fail(EMP_EINVAL, "bad ma_mode");
   if (d->n_prior_ops < 0 || d->n_prior_ops > EMP_MAX_PRIOR_OPS) return fail(EMP_EINVAL, "bad n_prior_ops");
+  if (d->n_periodic < 0 || d->n_periodic > EMP_MAX_PERIODIC) return fail(EMP_EINVAL, "bad n_periodic");
+  for (int b = 0; b < d->n_periodic; ++b) {
+    const int np = d->periodic_kind[b] == 0 ? 3 : 5;
+    if (d->periodic_kind[b] < 0 || d->periodic_kind[b] > 1 || d->periodic_off[b] < 0 ||
+        d->periodic_off[b] + np > d->ndim_full)
+      return fail(EMP_EINVAL, "bad periodic block");
+  }
   for (int k = 0; k < d->n_kep; ++k) {
     int m = d->kep_model[k];
     if (m < 0 || m > 7) return fail(EMP_EINVAL, "bad kep_model");
@@ -350,6 +357,11 @@ extern "C" int emp_model_host(EmpHandle* h, const double* theta_host, double* mo
   if (h->desc.ma_mode == EMP_MA_GLOBAL && h->desc.ma_order > 0) {
     model_ma_kernel<<<1, 32, 0, h->stream>>>(h->d_desc, h->d_theta, h->d_t, h->d_y, h->n, d_model);
     h->launches += 1;
+    if (h->desc.n_periodic > 0) {
+      model_periodic_kernel<<<blocks, 256, 0, h->stream>>>(h->d_desc, h->d_theta, h->d_t, h->n, h->t_absmax, d_model,
+                                                           make_hot_consts());
+      h->launches += 1;
+    }
   }
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(model_host, d_model, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);

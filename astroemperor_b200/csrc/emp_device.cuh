@@ -359,6 +359,27 @@ __device__ __forceinline__ double kep_rv_checked(const KepConst& k, double t, co
   return r;
 }
 
+// ---- A cos(freq t + phase): support/models/sinusoid00.model, magneticcycle00.model -------------
+struct PeriodicTerm {
+  double freq, phase, amp;
+  double slow;  // != 0: |freq t + phase| may exceed 1e12 -> library cos()
+};
+__device__ inline PeriodicTerm make_periodic(double freq, double phase, double amp, double t_absmax) {
+  PeriodicTerm p;
+  p.freq = freq; p.phase = phase; p.amp = amp;
+  p.slow = (fabs(freq) * t_absmax + fabs(phase) < 1.0e12) ? 0.0 : 1.0;
+  return p;
+}
+__device__ __forceinline__ double periodic_value(const PeriodicTerm& p, double t, const HotConsts& H) {
+  const double M = __dadd_rn(__dmul_rn(p.freq, t), p.phase);  // freq * X_ + phase
+  if (p.slow != 0.0) return p.amp * cos(M);
+  int sign_hi;
+  const double r = fold_anomaly(M, H, sign_hi);  // cos(M) = cos(|r|), r in [0, pi] exactly reduced
+  double sn, cs;
+  sin_cos_reduc(r, sn, cs, H);                   // cs = 1 - cos r
+  return p.amp * (1.0 - cs);
+}
+
 // ---- priors: support/priors/{Uniform,Normal,Jeffreys,Isotropic,Fixed}.prior ------------
 __device__ inline double prior_value(const EmpPriorOp& o, double x) {
   if (o.prior == EMP_PRIOR_FIXED) return 0.0;

@@ -35,6 +35,8 @@ struct WalkerConst {
   double jit2[EMP_MAX_INS];
   double acc[EMP_MAX_ACC];
   double ma[2 * EMP_MAX_MA];
+  PeriodicTerm per[2 * EMP_MAX_PERIODIC];  // A cos(freq t + phase) terms of Sinusoid / MagneticCycle blocks
+  int n_per, _pad;
 };
 
 struct LoglParams {
@@ -80,6 +82,19 @@ __device__ __forceinline__ void walker_constants(const EmpModelDesc* __restrict_
   }
   if (lane < d->acc_order) wc.acc[lane] = wc.th[d->acc_off + lane];
   if (lane < 2 * d->ma_order) wc.ma[lane] = wc.th[d->ma_off + lane];
+  if (lane == 0) {
+    int n = 0;
+    for (int b = 0; b < d->n_periodic; ++b) {
+      const double* th = wc.th + d->periodic_off[b];
+      if (d->periodic_kind[b] == 0) {  // sinusoid00.model: per, A, phase
+        wc.per[n++] = make_periodic(kTwoPi / th[0], th[2], th[1], t_absmax);
+      } else {                         // magneticcycle00.model: per, A1, A2, phase1, phase2
+        wc.per[n++] = make_periodic(kPi / th[0], th[3], th[1], t_absmax);
+        wc.per[n++] = make_periodic(kTwoPi / th[0], th[4], th[2], t_absmax);
+      }
+    }
+    wc.n_per = n;
+  }
   __syncwarp();
 }
 
@@ -275,6 +290,14 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
           }
         }
 
+        // Sinusoid / MagneticCycle blocks come after the MA block in the reference's model
+        // (emp.py:2646-2650): they are not part of the MA residuals, only of the final one
+        for (int q = 0; q < wc.n_per; ++q) {
+          const PeriodicTerm& pt = wc.per[q];
+          if (v0) d0 -= periodic_value(pt, t2.x, P.H);
+          if (v1) d1 -= periodic_value(pt, t2.y, P.H);
+        }
+
         // chi^2 and log-det: sum(r^2/err2 + log err2)  (00.like:5); logs taken on 4-point products
         chi = fma(d0 * d0, rcp_nr<2>(w0), chi);
         chi = fma(d1 * d1, rcp_nr<2>(w1), chi);
@@ -311,9 +334,25 @@ __global__ void model_rv_kernel(const EmpModelDesc* __restrict__ d, const double
     for (int k = 0; k < d->n_kep; ++k) m += kep_rv_checked(wc.kep[k], t[i], H);
     if (d->acc_order > 0) m += accel_term(wc.acc, d->acc_order, __dsub_rn(t[i], t0));
     m += wc.gamma[ins[i]];
+    if (d->ma_mode != EMP_MA_GLOBAL || d->ma_order == 0)  // else added after the MA pass (model_periodic_kernel)
+      for (int q = 0; q < wc.n_per; ++q) m += periodic_value(wc.per[q], t[i], H);
     model[i] = m;
     err2[i] = e2[i] + wc.jit2[ins[i]];
   }
+}
+
+// periodic terms of a model with a global MA block: added after model_ma_kernel
+__global__ void model_periodic_kernel(const EmpModelDesc* __restrict__ d, const double* __restrict__ theta,
+                                      const double* __restrict__ t, int64_t n, double t_absmax,
+                                      double* __restrict__ model, const HotConsts H) {
+  __shared__ WalkerConst wc;
+  if (threadIdx.x < 32) {
+    load_full_theta(d, theta, wc.th, threadIdx.x);
+    walker_constants(d, wc, threadIdx.x, t_absmax);
+  }
+  __syncthreads();
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    for (int q = 0; q < wc.n_per; ++q) model[i] += periodic_value(wc.per[q], t[i], H);
 }
 
 __global__ void model_ma_kernel(const EmpModelDesc* __restrict__ d, const double* __restrict__ theta,

@@ -108,6 +108,25 @@ def keplerian_block(data: RVData, number: int, parameterisation: int, ecc_limits
                      number=number, additional=addi)
 
 
+def periodic_blocks(data: RVData, sinusoid=0, magnetic_cycle=0) -> List[BlockSpec]:
+    """SinusoidBlock / MagneticCycleBlock + SmartSetter.set_Sinusoid / set_MagneticCycle
+    (block_repo.py:81-107, 302-347, 804-833)."""
+    amp = np.std(data.y) * np.sqrt(4)
+    per = data.t.max() - data.t.min()
+    blocks = []
+    if sinusoid:
+        names = [f"Period {sinusoid}", f"Amplitude {sinusoid}", f"Phase {sinusoid}"]
+        lims = [[1.5, per], [1e-6, amp], TWO_PI_LIMITS]
+        blocks.append(BlockSpec(type_="Sinusoid", number=sinusoid,
+                                params=[_param(n, "Uniform", l, None) for n, l in zip(names, lims)]))
+    if magnetic_cycle:
+        names = ["Period S1", "Amplitude S1", "Amplitude S2", "Phase S1", "Phase S2"]
+        lims = [[1.5, per], [1e-6, amp], [1e-6, amp], TWO_PI_LIMITS, TWO_PI_LIMITS]
+        blocks.append(BlockSpec(type_="MagneticCycle", number=magnetic_cycle,
+                                params=[_param(n, "Uniform", l, None) for n, l in zip(names, lims)]))
+    return blocks
+
+
 def instrument_blocks(data: RVData, acceleration=0, jitter=True, moav=None,
                       jitter_prargs=(5, 5)) -> List[BlockSpec]:
     """_autorun_add_RV_ins (emp.py:2628-2651) + SmartSetter.set_{Acceleration,Offset,Jitter,MOAV}."""
@@ -176,10 +195,11 @@ def finalize(spec: ModelSpec) -> ModelSpec:
 def default_spec(data: RVData, kplan: int, parameterisation: int = 0, acceleration: int = 0,
                  jitter: bool = True, moav: Optional[dict] = None, conditions: Sequence = (),
                  eccentricity_limits=(0, 1), eccentricity_prargs=(0, 0.1), jitter_prargs=(5, 5),
-                 astrometry: bool = False) -> ModelSpec:
+                 astrometry: bool = False, sinusoid: int = 0, magnetic_cycle: int = 0) -> ModelSpec:
     blocks = [keplerian_block(data, k + 1, parameterisation, list(eccentricity_limits),
                               list(eccentricity_prargs), astrometry=astrometry) for k in range(kplan)]
     blocks += instrument_blocks(data, acceleration, jitter, moav, jitter_prargs)
+    blocks += periodic_blocks(data, sinusoid, magnetic_cycle)  # after MOAV (emp.py:2646-2650)
     if astrometry:
         blocks += astrometry_blocks()
     spec = ModelSpec(blocks=blocks, nins=data.nins)
@@ -199,6 +219,8 @@ class Simulation:
         self.acceleration = 0
         self.switch_jitter = True
         self.moav = {"order": 0, "global": False}
+        self.sinusoid = 0
+        self.magnetic_cycle = 0
         self.eccentricity_limits = [0, 1]
         self.eccentricity_prargs = [0, 0.1]
         self.jitter_prargs = [5, 5]
@@ -247,7 +269,8 @@ class Simulation:
         return default_spec(self.data, kplan, self.keplerian_parameterisation, self.acceleration,
                             self.switch_jitter, self.moav if self.moav.get("order") else None, self.conds,
                             self.eccentricity_limits, self.eccentricity_prargs, self.jitter_prargs,
-                            astrometry=self.am_data is not None)
+                            astrometry=self.am_data is not None, sinusoid=self.sinusoid,
+                            magnetic_cycle=self.magnetic_cycle)
 
     def run(self, kplan: int):
         """_run_engine_reddemcee (emp.py:2559-2582) without the script / child process."""

@@ -21,12 +21,13 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 # ---- limits of the C descriptor (include/emperor_b200.h) --------------------
-EMP_ABI_VERSION = 3
+EMP_ABI_VERSION = 4
 EMP_MAX_KEP = 10
 EMP_MAX_INS = 16
 EMP_MAX_DIM = 128
 EMP_MAX_ACC = 4
 EMP_MAX_MA = 4
+EMP_MAX_PERIODIC = 4
 EMP_MAX_PRIOR_OPS = 2 * EMP_MAX_DIM + 2 * EMP_MAX_KEP + 8
 
 PRIOR_KINDS = {"Uniform": 0, "Normal": 1, "Jeffreys": 2, "Isotropic": 3, "Fixed": 4}
@@ -191,7 +192,8 @@ class EmpModelDescC(ctypes.Structure):
         ("ma_mode", ctypes.c_int32), ("ma_order", ctypes.c_int32), ("ma_off", ctypes.c_int32),
         ("am_enabled", ctypes.c_int32), ("am_offset_off", ctypes.c_int32),
         ("am_jitter_off", ctypes.c_int32), ("n_prior_ops", ctypes.c_int32),
-        ("_pad0", ctypes.c_int32),
+        ("n_periodic", ctypes.c_int32), ("periodic_kind", ctypes.c_int32 * EMP_MAX_PERIODIC),
+        ("periodic_off", ctypes.c_int32 * EMP_MAX_PERIODIC),
         ("free_to_full", ctypes.c_int32 * EMP_MAX_DIM),
         ("full_init", ctypes.c_double * EMP_MAX_DIM),
         ("prior_ops", _PriorOpC * EMP_MAX_PRIOR_OPS),
@@ -225,6 +227,7 @@ class CompiledModel:
         self.jitter_off = 0
         self.ma_mode, self.ma_order, self.ma_off = MA_NONE, 0, 0
         self.am_enabled, self.am_offset_off, self.am_jitter_off = 0, 0, 0
+        self.periodic: List[tuple] = []  # (kind, offset): 0 sinusoid00.model, 1 magneticcycle00.model
         self.prior_ops: List[tuple] = []
 
         off = 0
@@ -265,6 +268,14 @@ class CompiledModel:
                     raise UnsupportedModelError(f"MA order {self.ma_order} > {EMP_MAX_MA}")
                 if self.ma_order > 0:
                     self.ma_mode = MA_GLOBAL if b.moav_global else MA_REFERENCE_NOOP
+            elif b.type_ in ("Sinusoid", "MagneticCycle"):
+                seen_tail = True
+                kind = 0 if b.type_ == "Sinusoid" else 1
+                if n != (3, 5)[kind]:
+                    raise UnsupportedModelError(f"{b.type_} block with {n} parameters")
+                self.periodic.append((kind, off))
+                if len(self.periodic) > EMP_MAX_PERIODIC:
+                    raise UnsupportedModelError(f"more than {EMP_MAX_PERIODIC} Sinusoid/MagneticCycle blocks")
             elif b.type_ == "AstrometryOffset":
                 seen_tail = True
                 self.am_enabled, self.am_offset_off = 1, off
@@ -272,7 +283,7 @@ class CompiledModel:
                 seen_tail = True
                 self.am_jitter_off = off
             else:
-                # Sinusoid, MagneticCycle, StellarActivity, Celerite2: SURVEY.md §2 rows 19, 23
+                # StellarActivity, Celerite2: SURVEY.md §2 rows 19, 23
                 raise UnsupportedModelError(f"block type '{b.type_}' is outside the device hot path")
 
             # --- prior program, in the order emp.py:200-246 writes it
@@ -314,6 +325,10 @@ class CompiledModel:
         residual must see every mean-model term, so MOAV has to come last of the
         RV blocks."""
         rv = [t for t in types if t in ("Acceleration", "Offset", "Jitter", "MOAV")]
+        seq = [t for t in types if t in ("MOAV", "Sinusoid", "MagneticCycle")]
+        if "MOAV" in seq and seq.index("MOAV") != 0:
+            # the reference computes the MA residuals before the periodic terms are added
+            raise UnsupportedModelError("Sinusoid/MagneticCycle blocks before MOAV are not supported")
         if "MOAV" in rv and rv.index("MOAV") < max(
                 (i for i, t in enumerate(rv) if t in ("Acceleration", "Offset")), default=-1):
             raise UnsupportedModelError("MOAV block before Offset/Acceleration is not supported")
@@ -335,6 +350,9 @@ class CompiledModel:
         if len(self.prior_ops) > EMP_MAX_PRIOR_OPS:
             raise UnsupportedModelError("prior program too long")
         d.n_prior_ops = len(self.prior_ops)
+        d.n_periodic = len(self.periodic)
+        for j, (kind, o) in enumerate(self.periodic):
+            d.periodic_kind[j], d.periodic_off[j] = kind, o
         for j, f in enumerate(self.free_to_full):
             d.free_to_full[j] = int(f)
         for j, v in enumerate(self.full_init):

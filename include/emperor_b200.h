@@ -28,13 +28,14 @@
 extern "C" {
 #endif
 
-#define EMP_ABI_VERSION 3
+#define EMP_ABI_VERSION 4
 
 #define EMP_MAX_KEP 10   /* Keplerian blocks                                  */
 #define EMP_MAX_INS 16   /* instruments (offset / jitter entries)             */
 #define EMP_MAX_DIM 128  /* length of the full parameter vector (free+fixed)  */
 #define EMP_MAX_ACC 4    /* polynomial acceleration order                     */
 #define EMP_MAX_MA 4     /* moving-average order                              */
+#define EMP_MAX_PERIODIC 4 /* Sinusoid / MagneticCycle blocks                  */
 #define EMP_MAX_PRIOR_OPS (2 * EMP_MAX_DIM + 2 * EMP_MAX_KEP + 8)
 
 /* error codes */
@@ -114,7 +115,12 @@ typedef struct EmpModelDesc {
   int32_t am_offset_off; /* AstrometryOffsetBlock: 5 params                    */
   int32_t am_jitter_off; /* AstrometryJitterBlock: J_H, J_G                    */
   int32_t n_prior_ops;
-  int32_t _pad0;
+  /* periodic blocks, evaluated AFTER the MA block like the reference orders them
+   * (emp.py:2628-2651): support/models/sinusoid00.model (per, A, phase) and
+   * magneticcycle00.model (per, A1, A2, phase1, phase2) */
+  int32_t n_periodic;
+  int32_t periodic_kind[EMP_MAX_PERIODIC]; /* 0 = sinusoid, 1 = magnetic cycle */
+  int32_t periodic_off[EMP_MAX_PERIODIC];
   int32_t free_to_full[EMP_MAX_DIM]; /* full index of free parameter j         */
   double full_init[EMP_MAX_DIM];     /* fixed values at their full index, 0 elsewhere */
   EmpPriorOp prior_ops[EMP_MAX_PRIOR_OPS];

@@ -146,6 +146,19 @@ class RVOracle:
                         MA = macoef * np.exp(-dt / matime) * res_[i - 1 - c]
                         model0[i] += MA
                         residuals[i] -= MA
+        for kind, off in getattr(cm, "periodic", []):
+            if kind == 0:  # support/models/sinusoid00.model
+                per, A, phase = theta[off:off + 3]
+                freq = 2. * np.pi / per
+                M = freq * X_ + phase
+                model0 += A * np.cos(M)
+            else:  # support/models/magneticcycle00.model
+                per, A1, A2, phase1, phase2 = theta[off:off + 5]
+                freq2 = 2. * np.pi / per
+                freq1 = np.pi / per
+                M1 = freq1 * X_ + phase1
+                M2 = freq2 * X_ + phase2
+                model0 += A1 * np.cos(M1) + A2 * np.cos(M2)
         # cm.ma_mode == 1 (support/models/moav00.model): `model0[mask][i] += MA`
         # writes into a temporary copy, so the block has NO effect on model0 / err20
         # (SURVEY.md §0 fact 3); nothing to do.

@@ -205,6 +205,13 @@ CASES = {
                                    n_theta=48),
     "synth_k1_p1_ma2_global": dict(star="synth", cfg=_cfg(1, 1, moav={"order": 2, "global": True}),
                                    n_theta=48),
+    # periodic blocks (sinusoid00.model, magneticcycle00.model); with a global MA block they are
+    # added AFTER the MA residuals were formed (block order of emp.py:2628-2651)
+    "synth_k1_p0_sinusoid": dict(star="synth", cfg=_cfg(1, 0, extra=lambda sim: setattr(sim, "sinusoid", 1)),
+                                 n_theta=48),
+    "synth_k1_p1_magcycle_ma1_global": dict(star="synth", cfg=_cfg(
+        1, 1, moav={"order": 1, "global": True},
+        extra=lambda sim: (setattr(sim, "magnetic_cycle", 1), setattr(sim, "sinusoid", 2))), n_theta=48),
     # no jitter block
     "synth_k1_p0_nojit": dict(star="synth", cfg=_cfg(1, 0, jitter=False), n_theta=32),
     # GJ876: 8 instruments, 770 points

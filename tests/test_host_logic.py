@@ -72,6 +72,9 @@ MIRROR_CASES = {
     "synth_k1_p0_nojit": dict(kplan=1, jitter=False),
     "gj876_k2_p1": dict(kplan=2, parameterisation=1),
     "c4_synth5p_4ins_ma_global_n600": dict(kplan=5, moav={"order": 1, "global": True}),
+    "synth_k1_p0_sinusoid": dict(kplan=1, sinusoid=1),
+    "synth_k1_p1_magcycle_ma1_global": dict(kplan=1, parameterisation=1, moav={"order": 1, "global": True},
+                                            magnetic_cycle=1, sinusoid=2),
 }
 
 

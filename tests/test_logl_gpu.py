@@ -38,7 +38,8 @@ def test_logl_logp_match_golden(name):
 
 
 @pytest.mark.parametrize("name", ["c1_51peg_k1_p0", "synth_k1_p0_acc2_fixed", "synth_k1_p1_ma2_global",
-                                  "c4_synth5p_4ins_ma_global_n600"])
+                                  "c4_synth5p_4ins_ma_global_n600", "synth_k1_p0_sinusoid",
+                                  "synth_k1_p1_magcycle_ma1_global"])
 def test_my_model_matches_golden(name):
     g, spec = load_golden(name)
     eng = _engine(spec, g)
