@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
   const int K = d->n_kep;
   const int acc_order = d->acc_order;
   const int ma_order = (d->ma_mode == EMP_MA_GLOBAL) ? d->ma_order : 0;
+  const int n_per = active ? wc.n_per : 0;
 
   double chi = 0.0, lsum = 0.0, prod = 1.0;
   int nprod = 0;
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
 
         // Sinusoid / MagneticCycle blocks come after the MA block in the reference's model
         // (emp.py:2646-2650): they are not part of the MA residuals, only of the final one
-        for (int q = 0; q < wc.n_per; ++q) {
+        for (int q = 0; q < n_per; ++q) {
           const PeriodicTerm& pt = wc.per[q];
           if (v0) d0 -= periodic_value(pt, t2.x, P.H);
           if (v1) d1 -= periodic_value(pt, t2.y, P.H);
