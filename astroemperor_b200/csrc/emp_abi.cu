@@ -17,6 +17,10 @@
 
 using namespace emp;
 
+#ifndef EMP_LOGL_GROUPS
+#define EMP_LOGL_GROUPS 2  // 64-point groups a likelihood warp works on at once (A/B: scripts/build_variant.sh)
+#endif
+
 static thread_local std::string g_last_error;
 
 static int fail(int code, const std::string& msg) {
@@ -42,6 +46,8 @@ struct EmpHandle {
   char* d_tiles = nullptr;
   double *d_t = nullptr, *d_y = nullptr, *d_e2 = nullptr;
   int32_t* d_ins = nullptr;
+  double2* d_grid_sc = nullptr;  // sin/cos grid of the Kepler core (emp_device.cuh kep_rv_grid)
+  float2* d_grid_scf = nullptr;
   double t0 = 0.0;
   double t_absmax = 0.0;
   double ll_const = 0.0;
@@ -194,7 +200,21 @@ extern "C" int emp_create(const EmpModelDesc* desc, const double* t, const doubl
   CUDA_TRY(cudaMalloc(&h->d_cnt, 4 * sizeof(unsigned long long)));
   CUDA_TRY(cudaMemset(h->d_cnt, 0, 4 * sizeof(unsigned long long)));
 
-  CUDA_TRY(cudaFuncSetAttribute(logl_rv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  {
+    // (sin, cos)(k 2^-7) correctly rounded from long double; the FP32 copies are rounded from those
+    std::vector<double2> sc(kGridN);
+    std::vector<float2> scf(kGridN);
+    for (int k = 0; k < kGridN; ++k) {
+      const long double x = (long double)k / 128.0L;
+      sc[k] = make_double2(double(sinl(x)), double(cosl(x)));
+      scf[k] = make_float2(float(sc[k].x), float(sc[k].y));
+    }
+    CUDA_TRY(cudaMalloc(&h->d_grid_sc, kGridN * sizeof(double2)));
+    CUDA_TRY(cudaMalloc(&h->d_grid_scf, kGridN * sizeof(float2)));
+    CUDA_TRY(cudaMemcpy(h->d_grid_sc, sc.data(), kGridN * sizeof(double2), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d_grid_scf, scf.data(), kGridN * sizeof(float2), cudaMemcpyHostToDevice));
+  }
+  CUDA_TRY(cudaFuncSetAttribute(logl_rv_kernel<EMP_LOGL_GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 int(kLoglSmemBytes)));
   if (desc->am_enabled) {
     rc = am_upload(am, &h->am);
@@ -213,6 +233,8 @@ extern "C" int emp_destroy(EmpHandle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_tiles); cudaFree(h->d_t); cudaFree(h->d_y); cudaFree(h->d_e2); cudaFree(h->d_ins);
+  cudaFree(h->d_grid_sc); cudaFree(h->d_grid_scf); cudaFree(h->d_index); cudaFree(h->d_nact); cudaFree(h->d_cnt);
+  for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
   cudaFree(h->d_desc); cudaFree(h->d_theta); cudaFree(h->d_ll); cudaFree(h->d_lp);
   cudaFree(h->d_q); cudaFree(h->d_llq); cudaFree(h->d_lpq); cudaFree(h->d_llwork); cudaFree(h->d_nan);
   am_free(&h->am);
@@ -275,6 +297,8 @@ static int launch_logl(EmpHandle* h, const double* theta_dev, int64_t n_eval, do
   P.t0 = h->t0;
   P.ll_const = h->ll_const;
   P.t_absmax = h->t_absmax;
+  P.grid_sc = h->d_grid_sc;
+  P.grid_scf = h->d_grid_scf;
   P.H = make_hot_consts();
   const unsigned grid = unsigned((n_eval + kWalkerWarps - 1) / kWalkerWarps);
   cudaEvent_t e0 = h->ev0, e1 = h->ev1;
@@ -291,7 +315,7 @@ static int launch_logl(EmpHandle* h, const double* theta_dev, int64_t n_eval, do
     h->tev_used += 2;
     CUDA_TRY(cudaEventRecord(e0, h->stream));
   }
-  logl_rv_kernel<<<grid, kLoglThreads, kLoglSmemBytes, h->stream>>>(P);
+  logl_rv_kernel<EMP_LOGL_GROUPS><<<grid, kLoglThreads, kLoglSmemBytes, h->stream>>>(P);
   if (h->timing) CUDA_TRY(cudaEventRecord(e1, h->stream));
   h->launches += 1;
   CUDA_TRY(cudaGetLastError());

@@ -29,6 +29,11 @@ constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52: (x + kMagic) - kMa
 constexpr double kF1 = 3.0 * kPi / (kPi - 6.0 / kPi);
 constexpr double kF2 = 1.6 / (kPi - 6.0 / kPi);
 
+// Grid-anchored Kepler core (likelihood kernel v6): sin/cos of the grid points
+// k * 2^-7, k = 0..511 (covers [0, 4) > pi), as correctly rounded FP64 pairs and FP32 pairs.
+constexpr int kGridN = 512;
+constexpr double kGridEccMax = 0.98;  // beyond it the walker/planet takes the kepler.py-style refinement
+
 // Hot-loop FP64 literals travel in the KERNEL PARAMETER bank (c[0x0]) so that DFMA/DADD take them
 // as a direct constant operand: a 64-bit immediate costs two UMOVs per use and a user
 // __constant__ array (bank 3) costs an LDC per use (profiles/r01_sass_notes.md).
@@ -38,13 +43,15 @@ struct HotConsts {
   double sinc[8];
   double cosc[9];
   double c[10];  // [0] pi [1] 2pi [2] pi/2 [3] pi/4 [4] 1/(2pi) [5] rint magic [6] F1 [7] 1/6 [8] 1/24 [9] 1-pi/2
+  double g[4];   // grid core: [0] 1/120 [1] 1/720 [2] 2^45 [3] spare
 };
 __host__ __device__ inline HotConsts make_hot_consts() {
   HotConsts h = {{-1.0 / 355687428096000.0, 1.0 / 1307674368000.0, -1.0 / 6227020800.0, 1.0 / 39916800.0,
                   -1.0 / 362880.0, 1.0 / 5040.0, -1.0 / 120.0, 1.0 / 6.0},
                  {1.0 / 6402373705728000.0, -1.0 / 20922789888000.0, 1.0 / 87178291200.0, -1.0 / 479001600.0,
                   1.0 / 3628800.0, -1.0 / 40320.0, 1.0 / 720.0, -1.0 / 24.0, 0.5},
-                 {kPi, kTwoPi, kPi2, kPi4, kInvTwoPi, kMagic, kF1, 1.0 / 6.0, 1.0 / 24.0, 1.0 - kPi2}};
+                 {kPi, kTwoPi, kPi2, kPi4, kInvTwoPi, kMagic, kF1, 1.0 / 6.0, 1.0 / 24.0, 1.0 - kPi2},
+                 {1.0 / 120.0, 1.0 / 720.0, 35184372088832.0, 0.0}};
   return h;
 }
 
@@ -61,7 +68,8 @@ struct KepConst {
   double a2;      // -A sin w sqrt(1 - e^2)
   double a3;      // A e cos w
   float ef, omef, c2f, ome3f;  // FP32 copies for the starter
-  int slow_mod, _pad;          // |M| may exceed 1e12 somewhere in the data set: use the fmod path
+  int slow_mod;                // |M| may exceed 1e12 somewhere in the data set: use the fmod path
+  int robust;                  // e outside [0, kGridEccMax]: the grid-anchored core is not used
 };
 constexpr int kKepConstDoubles = sizeof(KepConst) / sizeof(double);
 
@@ -137,7 +145,7 @@ __device__ inline void kep_constants(int model, const double* th, double t_absma
   // the exact rint/FMA reduction needs |M| < 2^51 * 2pi; decide once per (walker, planet)
   const double m_bound = fabs(k.freq) * (t_absmax + fabs(k.tpv)) + fabs(k.phv);
   k.slow_mod = (m_bound < 1.0e12) ? 0 : 1;  // also catches NaN / inf parameters
-  k._pad = 0;
+  k.robust = (e >= 0.0 && e <= kGridEccMax) ? 0 : 1;
 }
 
 // ---- mean anomaly, reduced to [0, pi] exactly like NumPy's remainder ------------------
@@ -357,6 +365,91 @@ __device__ __forceinline__ double kep_rv_checked(const KepConst& k, double t, co
   double r = kep_rv<false>(k, t, H, bad);
   if (bad || k.slow_mod) r = kep_rv_cold(k, t);
   return r;
+}
+
+// walkers/planets the grid core does not take (e > kGridEccMax, e < 0, NaN): kepler.py-style
+// refinement, out of line so that its registers do not weigh on the hot loop
+__device__ __noinline__ double kep_rv_robust(const KepConst& k, double t) {
+  const HotConsts H = make_hot_consts();
+  return kep_rv_checked(k, t, H);
+}
+
+// ---- grid-anchored Kepler core (likelihood kernel v6) ----------------------------------------
+// Same root as kepler.solve (Kepler's equation has ONE root), reached with
+// ~half the FP64 instructions of the series-based refinement:
+//   1. FP32 Markley starter E0 (error <= 4e-4), snapped to the grid: k = rint(128 E0), El = E0 - k/128
+//      (exact in FP32, |El| <= 2^-8).  sin/cos of the grid point Eh = k/128 come from a table in shared
+//      memory (FP64 pair + FP32 pair).
+//   2. In delta-space (E = Eh + delta) Kepler's equation is a polynomial with small terms,
+//        g(delta) = delta - a sin(delta) + b (1 - cos(delta)) - c,  a = e cos Eh, b = e sin Eh,
+//        c = (M - Eh) + b   <- the only cancellation, done once in FP64,
+//      so one FP32 Halley step from El lands within ~1e-9 of the root (no cancellation left for
+//      FP32 to spoil: every term is O(delta)).
+//   3. FP64: sin/cos(delta) by 3-term polynomials (|delta| < 4.4e-3), residual and slope at delta,
+//      one Newton correction dd (|dd| ~ 1e-9, so a 2^-46 reciprocal is exact enough) and a
+//      first-order rotation by dd give sin E, cos E of the root to ~1 ulp.
+//   4. RV term as in kep_rv: [a1 (cos E - e) + a2 sin E] / (1 - e cos E) + a3; the reciprocal of the
+//      denominator is one Newton step from the slope's reciprocal (they differ by ~1e-8 relative).
+// CPU emulation vs an 80-bit solution, e in [0, 0.98]: max |dE| 1.1e-15, max |dRV/A| 6e-15
+// (the oracle's own figures: 7.5e-16 and 5.2e-15) — scripts/kepler_v6_emulation.py.
+__device__ __forceinline__ float markley_starter_f32(float M, const KepConst& k) {
+  const float M2 = M * M;
+  const float alpha = fmaf(k.c2f, 3.14159274f - M, 7.64804745f /* F1 */);
+  const float d = fmaf(alpha, k.ef, k.ome3f);
+  const float ad = alpha * d;
+  const float r = fmaf(3.0f * ad, d - k.omef, M2) * M;
+  const float q = fmaf(2.0f * ad, k.omef, -M2);
+  const float q2 = q * q;
+  const float x = fabsf(r) + f32_sqrt(fmaf(q2, q, r * r));
+  const float w = f32_ex2(0.666666687f * f32_lg2(x));  // x^(2/3)
+  const float den0 = fmaf(w, w + q, q2);
+  return fmaf(2.0f * r, w, M * den0) * f32_rcp(den0 * d);
+}
+
+__device__ __forceinline__ double kep_rv_grid(const KepConst& k, double t, const HotConsts& H,
+                                              const double2* __restrict__ tab, const float2* __restrict__ tabf,
+                                              bool& bad) {
+  const double M = mean_anomaly(k, t);
+  int sign_hi;
+  const double Mr = fold_anomaly(M, H, sign_hi);
+  const float Mf = __double2float_rn(Mr);
+  const float E0f = markley_starter_f32(Mf, k);
+  bad = !(Mf > 1e-15f) || !(E0f >= 0.0f && E0f < 3.99f);
+  // grid point: the low mantissa bits of E0*128 + 1.5*2^23 are rint(128 E0)
+  const float km = fmaf(E0f, 128.0f, 12582912.0f);
+  const float El = fmaf(km - 12582912.0f, -0.0078125f, E0f);
+  const int ki = __float_as_int(km) & (kGridN - 1);
+  const double2 sc = tab[ki];   // (sin Eh, cos Eh)
+  const float2 scf = tabf[ki];
+  const double Eh = __hiloint2double(0x42C00000, ki) - H.g[2];  // (2^45 + k 2^-7) - 2^45, exact
+  const double c = fma(k.e, sc.x, Mr - Eh);
+  // FP32 Halley step in delta-space
+  const float cf = __double2float_rn(c);
+  const float af = k.ef * scf.y, bf = k.ef * scf.x;
+  const float f1f = 1.0f - af;
+  const float g0 = fmaf(El, fmaf(El, fmaf(El, af * 0.166666672f, 0.5f * bf), f1f), -cf);
+  const float g1 = fmaf(El, fmaf(El, 0.5f * af, bf), f1f);
+  const float g2 = fmaf(El, af, bf);
+  const float r = f32_rcp(g1);
+  const float dn = g0 * r;
+  const float d1 = fmaf(-0.5f * dn * dn, g2 * r, El - dn);
+  // FP64 correction
+  const double df = double(d1);
+  const double d2 = df * df;
+  const double sl = fma(df * d2, fma(d2, H.g[0], -H.c[7]), df);          // sin(delta)
+  const double cm = d2 * fma(d2, fma(d2, H.g[1], -H.c[8]), 0.5);          // 1 - cos(delta)
+  const double w1 = fma(sc.y, sl, -sc.x * cm);                            // sin E_f - sin Eh
+  const double w2 = fma(sc.x, sl, sc.y * cm);                             // cos Eh - cos E_f
+  const double sEf = sc.x + w1, cEf = sc.y - w2;
+  const double g = fma(-k.e, w1, df - c);                                 // E_f - e sin E_f - M
+  const double gp = fma(-k.e, cEf, 1.0);                                  // 1 - e cos E_f
+  const double y1 = rcp_nr<1>(gp);
+  const double dd = -g * y1;
+  const double sE = fma(cEf, dd, sEf), cE = fma(-sEf, dd, cEf);
+  const double den = fma(-k.e, cE, 1.0);
+  const double y2 = fma(y1, fma(-den, y1, 1.0), y1);                      // 1/den: Newton from 1/gp
+  const double num = fma(k.a1, cE - k.e, k.a2 * flip_sign(sE, sign_hi));  // sin(2pi - E) = -sin E
+  return fma(num, y2, k.a3);
 }
 
 // ---- A cos(freq t + phase): support/models/sinusoid00.model, magneticcycle00.model -------------

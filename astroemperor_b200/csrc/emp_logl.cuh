@@ -35,6 +35,7 @@ struct WalkerConst {
   double jit2[EMP_MAX_INS];
   double acc[EMP_MAX_ACC];
   double ma[2 * EMP_MAX_MA];
+  double ma_itau[EMP_MAX_MA];              // 1 / tau_c
   PeriodicTerm per[2 * EMP_MAX_PERIODIC];  // A cos(freq t + phase) terms of Sinusoid / MagneticCycle blocks
   int n_per, _pad;
 };
@@ -51,11 +52,18 @@ struct LoglParams {
   double t0;                  // X_[0] (acc.model uses X_ - X_[0])
   double ll_const;            // -0.5*log(2*pi)*ndat  (00.like:1)
   double t_absmax;            // max |t|: bounds the mean anomaly per (walker, planet)
+  const double2* grid_sc;     // [kGridN] (sin, cos)(k 2^-7), correctly rounded FP64
+  const float2* grid_scf;     // the same pairs rounded to FP32
   HotConsts H;                // FP64 literals of the hot loop, read as c[0x0][..] operands
 };
 
-constexpr size_t kLoglSmemBytes =
-    size_t(kStages) * kTileBytes + 2 * kStages * sizeof(uint64_t) + kWalkerWarps * sizeof(WalkerConst);
+// dynamic shared memory: tile ring | mbarriers | sin/cos grid (FP64 pairs, FP32 pairs) | walker constants
+constexpr size_t kSmemBarOff = size_t(kStages) * kTileBytes;
+constexpr size_t kSmemTabOff = kSmemBarOff + 64;
+constexpr size_t kSmemTabfOff = kSmemTabOff + kGridN * sizeof(double2);
+constexpr size_t kSmemWalkerOff = kSmemTabfOff + kGridN * sizeof(float2);
+constexpr size_t kLoglSmemBytes = kSmemWalkerOff + kWalkerWarps * sizeof(WalkerConst);
+static_assert(2 * kStages * sizeof(uint64_t) <= 64 && kSmemTabOff % 16 == 0, "shared-memory layout");
 
 // theta[ndim_free] -> full theta in shared memory (emp_model.py:709-711)
 __device__ __forceinline__ void load_full_theta(const EmpModelDesc* __restrict__ d,
@@ -82,6 +90,7 @@ __device__ __forceinline__ void walker_constants(const EmpModelDesc* __restrict_
   }
   if (lane < d->acc_order) wc.acc[lane] = wc.th[d->acc_off + lane];
   if (lane < 2 * d->ma_order) wc.ma[lane] = wc.th[d->ma_off + lane];
+  if (lane < d->ma_order) wc.ma_itau[lane] = 1.0 / wc.th[d->ma_off + 2 * lane + 1];
   if (lane == 0) {
     int n = 0;
     for (int b = 0; b < d->n_periodic; ++b) {
@@ -128,12 +137,118 @@ __device__ __forceinline__ double accel_term(const double* acc, int order, doubl
 }
 
 // ---- launch 2: likelihood -------------------------------------------------------------------
+// per-lane running sums and the warp-uniform MA state
+struct LaneAcc {
+  double chi, lsum, prod;
+  int nprod;
+  double r_carry, t_prev;                    // MA(1) carry: previous residual and timestamp
+  double rh[EMP_MAX_MA], thist[EMP_MAX_MA];  // MA(order >= 2) history, newest first
+};
+
+// Everything after the Keplerian sum for one group of 64 points (lane owns points 2*lane, 2*lane+1 of
+// the group): acceleration, offsets, jitter, MA recurrence, periodic terms, chi^2 and log-det.
+__device__ __forceinline__ void tail64(const WalkerConst& wc, const LoglParams& P, LaneAcc& A, int lane, int it,
+                                       int cnt, int64_t base, const unsigned char* tb, double2 t2, double m0,
+                                       double m1, int acc_order, int ma_order, int n_per) {
+  const double2* ys = reinterpret_cast<const double2*>(tb + kTilePoints * 8);
+  const double2* es = reinterpret_cast<const double2*>(tb + kTilePoints * 16);
+  const int2* is = reinterpret_cast<const int2*>(tb + kTilePoints * 24);
+  const int li = it * 32 + lane;
+  const int p0 = it * 64 + 2 * lane;
+  const bool v0 = p0 < cnt, v1 = (p0 + 1) < cnt;
+  if (acc_order > 0) {
+    m0 += accel_term(wc.acc, acc_order, __dsub_rn(t2.x, P.t0));
+    m1 += accel_term(wc.acc, acc_order, __dsub_rn(t2.y, P.t0));
+  }
+  const int2 in2 = is[li];
+  const double2 y2 = ys[li];
+  const double2 e2 = es[li];
+  m0 += wc.gamma[in2.x];
+  m1 += wc.gamma[in2.y];
+  double d0 = v0 ? y2.x - m0 : 0.0;
+  double d1 = v1 ? y2.y - m1 : 0.0;
+  const double w0 = v0 ? e2.x + wc.jit2[in2.x] : 1.0;
+  const double w1 = v1 ? e2.y + wc.jit2[in2.y] : 1.0;
+
+  if (ma_order == 1) {
+    // moav01.model: r_i = d_i - phi*exp(-|t_i - t_{i-1}|/tau) * r_{i-1}, sequential in i.
+    // Evaluated as a warp scan over the affine maps r -> a*r + b (exact algebra).
+    const double phi = wc.ma[0], itau = wc.ma_itau[0];
+    const double tl = __shfl_up_sync(0xffffffffu, t2.y, 1);
+    const double tp0 = (lane == 0) ? A.t_prev : tl;
+    const bool first_pt = (base + p0) == 0;  // i == 0: no MA term (`if i > c`)
+    double a0 = (v0 && !first_pt) ? -phi * exp(-fabs(t2.x - tp0) * itau) : 0.0;
+    double a1 = v1 ? -phi * exp(-fabs(t2.y - t2.x) * itau) : 0.0;
+    // compose the lane's two maps, then inclusive scan across lanes
+    double Am = a1 * a0, Bm = fma(a1, d0, d1);
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const double Ap = __shfl_up_sync(0xffffffffu, Am, off);
+      const double Bp = __shfl_up_sync(0xffffffffu, Bm, off);
+      if (lane >= off) { Bm = fma(Am, Bp, Bm); Am = Am * Ap; }
+    }
+    const double r_last = fma(Am, A.r_carry, Bm);  // residual at this lane's 2nd point
+    double r_prev = __shfl_up_sync(0xffffffffu, r_last, 1);
+    if (lane == 0) r_prev = A.r_carry;
+    d0 = fma(a0, r_prev, d0);
+    d1 = fma(a1, d0, d1);
+    // carry to the next 64 points: last VALID point of this group
+    const int last_lane = min(31, (cnt - it * 64 - 1) >> 1);
+    const bool last_is_second = ((cnt - it * 64) >= 2 * (last_lane + 1));
+    A.r_carry = __shfl_sync(0xffffffffu, last_is_second ? d1 : d0, last_lane);
+    A.t_prev = __shfl_sync(0xffffffffu, last_is_second ? t2.y : t2.x, last_lane);
+  } else if (ma_order >= 2) {
+    // general order: serial recurrence over the 64 points (rare configuration), every lane
+    // runs the same uniform loop on shuffled values so no shared scratch is needed.
+    for (int j = 0; j < 64; ++j) {
+      const int src = j >> 1;
+      const double dj = __shfl_sync(0xffffffffu, (j & 1) ? d1 : d0, src);
+      const double tj = __shfl_sync(0xffffffffu, (j & 1) ? t2.y : t2.x, src);
+      const bool vj = (it * 64 + j) < cnt;
+      const int64_t gi = base + it * 64 + j;
+      double r = dj;
+      if (vj) {
+#pragma unroll
+        for (int c = 0; c < EMP_MAX_MA; ++c) {
+          if (c < ma_order && gi > c) {
+            const double ma = wc.ma[2 * c] * exp(-fabs(tj - A.thist[c]) / wc.ma[2 * c + 1]) * A.rh[c];
+            r -= ma;
+          }
+        }
+#pragma unroll
+        for (int c = EMP_MAX_MA - 1; c > 0; --c) { A.rh[c] = A.rh[c - 1]; A.thist[c] = A.thist[c - 1]; }
+        A.rh[0] = r;
+        A.thist[0] = tj;
+        if (src == lane) { if (j & 1) d1 = r; else d0 = r; }
+      }
+    }
+  }
+
+  // Sinusoid / MagneticCycle blocks come after the MA block in the reference's model
+  // (emp.py:2646-2650): they are not part of the MA residuals, only of the final one
+  for (int q = 0; q < n_per; ++q) {
+    const PeriodicTerm& pt = wc.per[q];
+    if (v0) d0 -= periodic_value(pt, t2.x, P.H);
+    if (v1) d1 -= periodic_value(pt, t2.y, P.H);
+  }
+
+  // chi^2 and log-det: sum(r^2/err2 + log err2)  (00.like:5); logs taken on 4-point products
+  A.chi = fma(d0 * d0, rcp_nr<2>(w0), A.chi);
+  A.chi = fma(d1 * d1, rcp_nr<2>(w1), A.chi);
+  A.prod *= w0 * w1;
+  if (++A.nprod == 2) { A.lsum += log(A.prod); A.prod = 1.0; A.nprod = 0; }
+}
+
+// kGroups = groups of 64 points a warp works on at once: 2*kGroups independent Kepler chains per lane
+template <int kGroups>
 __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* tiles_s = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + size_t(kStages) * kTileBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kSmemBarOff);
   uint64_t* empty_bar = full_bar + kStages;
-  WalkerConst* wcs = reinterpret_cast<WalkerConst*>(empty_bar + kStages);
+  double2* tab = reinterpret_cast<double2*>(smem + kSmemTabOff);
+  float2* tabf = reinterpret_cast<float2*>(smem + kSmemTabfOff);
+  WalkerConst* wcs = reinterpret_cast<WalkerConst*>(smem + kSmemWalkerOff);
 
   const int n_active = *P.n_active;
   const int first = blockIdx.x * kWalkerWarps;
@@ -156,6 +271,11 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
       tma_bulk_g2s(tiles_s + size_t(i) * kTileBytes, P.tiles + size_t(i) * kTileBytes, kTileBytes, &full_bar[i]);
     }
   }
+  // sin/cos grid of the Kepler core (12 KB, L2-resident)
+  for (int i = threadIdx.x; i < kGridN; i += kLoglThreads) {
+    tab[i] = P.grid_sc[i];
+    tabf[i] = P.grid_scf[i];
+  }
 
   // ---- prologue: per-walker constants -------------------------------------------------------
   const bool active = (first + warp) < n_active;
@@ -166,21 +286,17 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
     load_full_theta(d, P.theta + slot * d->ndim_free, wc.th, lane);
     walker_constants(d, wc, lane, P.t_absmax);
   }
-  __syncthreads();  // publishes the barrier inits to all warps
+  __syncthreads();  // publishes the barrier inits and the grid to all warps
 
   const int K = d->n_kep;
   const int acc_order = d->acc_order;
   const int ma_order = (d->ma_mode == EMP_MA_GLOBAL) ? d->ma_order : 0;
   const int n_per = active ? wc.n_per : 0;
 
-  double chi = 0.0, lsum = 0.0, prod = 1.0;
-  int nprod = 0;
-  // MA(1) carry (warp-uniform): previous residual and previous timestamp
-  double r_carry = 0.0, t_prev = 0.0;
-  // MA(order>=2) history, newest first (warp-uniform)
-  double rh[EMP_MAX_MA], thist[EMP_MAX_MA];
+  LaneAcc A;
+  A.chi = 0.0; A.lsum = 0.0; A.prod = 1.0; A.nprod = 0; A.r_carry = 0.0; A.t_prev = 0.0;
 #pragma unroll
-  for (int c = 0; c < EMP_MAX_MA; ++c) { rh[c] = 0.0; thist[c] = 0.0; }
+  for (int c = 0; c < EMP_MAX_MA; ++c) { A.rh[c] = 0.0; A.thist[c] = 0.0; }
 
   for (int i = 0; i < n_tiles; ++i) {
     const int s = i % kStages;
@@ -198,112 +314,53 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
     if (active) {
       const unsigned char* tb = tiles_s + size_t(s) * kTileBytes;
       const double2* ts = reinterpret_cast<const double2*>(tb);
-      const double2* ys = reinterpret_cast<const double2*>(tb + kTilePoints * 8);
-      const double2* es = reinterpret_cast<const double2*>(tb + kTilePoints * 16);
-      const int2* is = reinterpret_cast<const int2*>(tb + kTilePoints * 24);
       const int64_t base = int64_t(i) * kTilePoints;
       const int64_t rem = P.n_points - base;
       const int cnt = rem < kTilePoints ? int(rem) : kTilePoints;
       const int iters = (cnt + 63) >> 6;
-      for (int it = 0; it < iters; ++it) {
-        const int li = it * 32 + lane;
-        const double2 t2 = ts[li];
-        const int p0 = it * 64 + 2 * lane;
-        const bool v0 = p0 < cnt, v1 = (p0 + 1) < cnt;
-        double m0 = 0.0, m1 = 0.0;
+      for (int it = 0; it < iters; it += kGroups) {
+        // (a tile always holds kTilePoints/64 full groups: padding replicates the last timestamp)
+        double2 t2[kGroups];
+        double m[2 * kGroups];
+#pragma unroll
+        for (int u = 0; u < kGroups; ++u) {
+          t2[u] = ts[(it + u) * 32 + lane];
+          m[2 * u] = 0.0;
+          m[2 * u + 1] = 0.0;
+        }
         for (int k = 0; k < K; ++k) {
           const KepConst& kc = wc.kep[k];
-          bool b0 = false, b1 = false;
-          double r0 = kep_rv<false>(kc, t2.x, P.H, b0);  // straight-line code for both points:
-          double r1 = kep_rv<false>(kc, t2.y, P.H, b1);  // the scheduler interleaves the two chains
-          if (__any_sync(0xffffffffu, b0 || b1 || kc.slow_mod)) {  // rare: redo on the cold path
-            if (b0 || kc.slow_mod) r0 = kep_rv_cold(kc, t2.x);
-            if (b1 || kc.slow_mod) r1 = kep_rv_cold(kc, t2.y);
-          }
-          m0 += r0;
-          m1 += r1;
-        }
-        if (acc_order > 0) {
-          m0 += accel_term(wc.acc, acc_order, __dsub_rn(t2.x, P.t0));
-          m1 += accel_term(wc.acc, acc_order, __dsub_rn(t2.y, P.t0));
-        }
-        const int2 in2 = is[li];
-        const double2 y2 = ys[li];
-        const double2 e2 = es[li];
-        m0 += wc.gamma[in2.x];
-        m1 += wc.gamma[in2.y];
-        double d0 = v0 ? y2.x - m0 : 0.0;
-        double d1 = v1 ? y2.y - m1 : 0.0;
-        const double w0 = v0 ? e2.x + wc.jit2[in2.x] : 1.0;
-        const double w1 = v1 ? e2.y + wc.jit2[in2.y] : 1.0;
-
-        if (ma_order == 1) {
-          // moav01.model: r_i = d_i - phi*exp(-|t_i - t_{i-1}|/tau) * r_{i-1}, sequential in i.
-          // Evaluated as a warp scan over the affine maps r -> a*r + b (exact algebra).
-          const double phi = wc.ma[0], tau = wc.ma[1];
-          const double tl = __shfl_up_sync(0xffffffffu, t2.y, 1);
-          const double tp0 = (lane == 0) ? t_prev : tl;
-          const bool first_pt = (base + p0) == 0;  // i == 0: no MA term (`if i > c`)
-          double a0 = (v0 && !first_pt) ? -phi * exp(-fabs(t2.x - tp0) / tau) : 0.0;
-          double a1 = v1 ? -phi * exp(-fabs(t2.y - t2.x) / tau) : 0.0;
-          // compose the lane's two maps, then inclusive scan across lanes
-          double A = a1 * a0, B = fma(a1, d0, d1);
+          if ((kc.slow_mod | kc.robust) == 0) {  // warp-uniform
+            double r[2 * kGroups];
+            bool anybad = false;
 #pragma unroll
-          for (int off = 1; off < 32; off <<= 1) {
-            const double Ap = __shfl_up_sync(0xffffffffu, A, off);
-            const double Bp = __shfl_up_sync(0xffffffffu, B, off);
-            if (lane >= off) { B = fma(A, Bp, B); A = A * Ap; }
-          }
-          const double r_last = fma(A, r_carry, B);        // residual at this lane's 2nd point
-          double r_prev = __shfl_up_sync(0xffffffffu, r_last, 1);
-          if (lane == 0) r_prev = r_carry;
-          d0 = fma(a0, r_prev, d0);
-          d1 = fma(a1, d0, d1);
-          // carry to the next 64 points: last VALID point of this iteration
-          const int last_lane = min(31, (cnt - it * 64 - 1) >> 1);
-          const bool last_is_second = ((cnt - it * 64) >= 2 * (last_lane + 1));
-          r_carry = __shfl_sync(0xffffffffu, last_is_second ? d1 : d0, last_lane);
-          t_prev = __shfl_sync(0xffffffffu, last_is_second ? t2.y : t2.x, last_lane);
-        } else if (ma_order >= 2) {
-          // general order: serial recurrence over the 64 points (rare configuration), every lane
-          // runs the same uniform loop on shuffled values so no shared scratch is needed.
-          for (int j = 0; j < 64; ++j) {
-            const int src = j >> 1;
-            const double dj = __shfl_sync(0xffffffffu, (j & 1) ? d1 : d0, src);
-            const double tj = __shfl_sync(0xffffffffu, (j & 1) ? t2.y : t2.x, src);
-            const bool vj = (it * 64 + j) < cnt;
-            const int64_t gi = base + it * 64 + j;
-            double r = dj;
-            if (vj) {
+            for (int u = 0; u < kGroups; ++u) {  // straight-line code: the scheduler interleaves the chains
+              bool b0, b1;
+              r[2 * u] = kep_rv_grid(kc, t2[u].x, P.H, tab, tabf, b0);
+              r[2 * u + 1] = kep_rv_grid(kc, t2[u].y, P.H, tab, tabf, b1);
+              anybad = anybad || b0 || b1;
+            }
+            if (__any_sync(0xffffffffu, anybad)) {  // rare (M ~ 0): redo the group on the checked path
 #pragma unroll
-              for (int c = 0; c < EMP_MAX_MA; ++c) {
-                if (c < ma_order && gi > c) {
-                  const double ma = wc.ma[2 * c] * exp(-fabs(tj - thist[c]) / wc.ma[2 * c + 1]) * rh[c];
-                  r -= ma;
-                }
+              for (int u = 0; u < kGroups; ++u) {
+                r[2 * u] = kep_rv_robust(kc, t2[u].x);
+                r[2 * u + 1] = kep_rv_robust(kc, t2[u].y);
               }
+            }
 #pragma unroll
-              for (int c = EMP_MAX_MA - 1; c > 0; --c) { rh[c] = rh[c - 1]; thist[c] = thist[c - 1]; }
-              rh[0] = r;
-              thist[0] = tj;
-              if (src == lane) { if (j & 1) d1 = r; else d0 = r; }
+            for (int j = 0; j < 2 * kGroups; ++j) m[j] += r[j];
+          } else {
+#pragma unroll
+            for (int u = 0; u < kGroups; ++u) {
+              m[2 * u] += kep_rv_robust(kc, t2[u].x);
+              m[2 * u + 1] += kep_rv_robust(kc, t2[u].y);
             }
           }
         }
-
-        // Sinusoid / MagneticCycle blocks come after the MA block in the reference's model
-        // (emp.py:2646-2650): they are not part of the MA residuals, only of the final one
-        for (int q = 0; q < n_per; ++q) {
-          const PeriodicTerm& pt = wc.per[q];
-          if (v0) d0 -= periodic_value(pt, t2.x, P.H);
-          if (v1) d1 -= periodic_value(pt, t2.y, P.H);
-        }
-
-        // chi^2 and log-det: sum(r^2/err2 + log err2)  (00.like:5); logs taken on 4-point products
-        chi = fma(d0 * d0, rcp_nr<2>(w0), chi);
-        chi = fma(d1 * d1, rcp_nr<2>(w1), chi);
-        prod *= w0 * w1;
-        if (++nprod == 2) { lsum += log(prod); prod = 1.0; nprod = 0; }
+#pragma unroll
+        for (int u = 0; u < kGroups; ++u)
+          if (it + u < iters)
+            tail64(wc, P, A, lane, it + u, cnt, base, tb, t2[u], m[2 * u], m[2 * u + 1], acc_order, ma_order, n_per);
       }
     }
     __syncwarp();
@@ -311,8 +368,8 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
   }
 
   if (active) {
-    lsum += log(prod);
-    const double tot = warp_sum(chi + lsum);
+    A.lsum += log(A.prod);
+    const double tot = warp_sum(A.chi + A.lsum);
     if (lane == 0) P.logl[slot] = fma(-0.5, tot, P.ll_const);
   }
 }
