@@ -47,7 +47,7 @@ struct EmpHandle {
   double *d_t = nullptr, *d_y = nullptr, *d_e2 = nullptr;
   int32_t* d_ins = nullptr;
   double2* d_grid_sc = nullptr;  // sin/cos grid of the Kepler core (emp_device.cuh kep_rv_grid)
-  float2* d_grid_scf = nullptr;
+  float4* d_grid_scf = nullptr;
   double t0 = 0.0;
   double t_absmax = 0.0;
   double ll_const = 0.0;
@@ -203,16 +203,16 @@ extern "C" int emp_create(const EmpModelDesc* desc, const double* t, const doubl
   {
     // (sin, cos)(k 2^-7) correctly rounded from long double; the FP32 copies are rounded from those
     std::vector<double2> sc(kGridN);
-    std::vector<float2> scf(kGridN);
+    std::vector<float4> scf(kGridN);
     for (int k = 0; k < kGridN; ++k) {
       const long double x = (long double)k / 128.0L;
       sc[k] = make_double2(double(sinl(x)), double(cosl(x)));
-      scf[k] = make_float2(float(sc[k].x), float(sc[k].y));
+      scf[k] = make_float4(float(sc[k].x), float(sc[k].y), float(0.5 * sc[k].x), float(sc[k].y / 6.0));
     }
     CUDA_TRY(cudaMalloc(&h->d_grid_sc, kGridN * sizeof(double2)));
-    CUDA_TRY(cudaMalloc(&h->d_grid_scf, kGridN * sizeof(float2)));
+    CUDA_TRY(cudaMalloc(&h->d_grid_scf, kGridN * sizeof(float4)));
     CUDA_TRY(cudaMemcpy(h->d_grid_sc, sc.data(), kGridN * sizeof(double2), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(h->d_grid_scf, scf.data(), kGridN * sizeof(float2), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d_grid_scf, scf.data(), kGridN * sizeof(float4), cudaMemcpyHostToDevice));
   }
   CUDA_TRY(cudaFuncSetAttribute(logl_rv_kernel<EMP_LOGL_GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 int(kLoglSmemBytes)));

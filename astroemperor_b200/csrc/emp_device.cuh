@@ -44,6 +44,7 @@ struct HotConsts {
   double cosc[9];
   double c[10];  // [0] pi [1] 2pi [2] pi/2 [3] pi/4 [4] 1/(2pi) [5] rint magic [6] F1 [7] 1/6 [8] 1/24 [9] 1-pi/2
   double g[4];   // grid core: [0] 1/120 [1] 1/720 [2] 2^45 [3] spare
+  double ex[13];  // exp_neg: [0] log2(e) [1] -ln2_hi [2] -ln2_lo [3..12] 1/2! .. 1/11!
 };
 __host__ __device__ inline HotConsts make_hot_consts() {
   HotConsts h = {{-1.0 / 355687428096000.0, 1.0 / 1307674368000.0, -1.0 / 6227020800.0, 1.0 / 39916800.0,
@@ -51,7 +52,10 @@ __host__ __device__ inline HotConsts make_hot_consts() {
                  {1.0 / 6402373705728000.0, -1.0 / 20922789888000.0, 1.0 / 87178291200.0, -1.0 / 479001600.0,
                   1.0 / 3628800.0, -1.0 / 40320.0, 1.0 / 720.0, -1.0 / 24.0, 0.5},
                  {kPi, kTwoPi, kPi2, kPi4, kInvTwoPi, kMagic, kF1, 1.0 / 6.0, 1.0 / 24.0, 1.0 - kPi2},
-                 {1.0 / 120.0, 1.0 / 720.0, 35184372088832.0, 0.0}};
+                 {1.0 / 120.0, 1.0 / 720.0, 35184372088832.0, 0.0},
+                 {1.4426950408889634074, -6.93147180369123816490e-01, -1.90821492927058770002e-10, 1.0 / 2.0,
+                  1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0, 1.0 / 40320.0, 1.0 / 362880.0,
+                  1.0 / 3628800.0, 1.0 / 39916800.0}};
   return h;
 }
 
@@ -67,7 +71,9 @@ struct KepConst {
   double a1;      // A cos w
   double a2;      // -A sin w sqrt(1 - e^2)
   double a3;      // A e cos w
+  double b1;      // A cos w (1 - e^2): RV = (b1 cos E + a2 sin E) / (1 - e cos E)   (grid core)
   float ef, omef, c2f, ome3f;  // FP32 copies for the starter
+  float ef3, om23f, c2f3, efh; // e/3, 2(1-e)/3, 3 c2, e/2: constant factors folded for the grid core
   int slow_mod;                // |M| may exceed 1e12 somewhere in the data set: use the fmod path
   int robust;                  // e outside [0, kGridEccMax]: the grid-anchored core is not used
 };
@@ -138,6 +144,11 @@ __device__ inline void kep_constants(int model, const double* th, double t_absma
   k.a1 = A * cw;
   k.a2 = -A * sw * sqrt(ome * (1.0 + e));
   k.a3 = A * e * cw;
+  k.b1 = k.a1 * (ome * (1.0 + e));
+  k.ef3 = float(e / 3.0);
+  k.om23f = float(2.0 * ome / 3.0);
+  k.c2f3 = float(3.0 * k.c2);
+  k.efh = float(0.5 * e);
   k.ef = float(e);
   k.omef = float(ome);
   k.c2f = float(k.c2);
@@ -388,51 +399,56 @@ __device__ __noinline__ double kep_rv_robust(const KepConst& k, double t) {
 //   3. FP64: sin/cos(delta) by 3-term polynomials (|delta| < 4.4e-3), residual and slope at delta,
 //      one Newton correction dd (|dd| ~ 1e-9, so a 2^-46 reciprocal is exact enough) and a
 //      first-order rotation by dd give sin E, cos E of the root to ~1 ulp.
-//   4. RV term as in kep_rv: [a1 (cos E - e) + a2 sin E] / (1 - e cos E) + a3; the reciprocal of the
-//      denominator is one Newton step from the slope's reciprocal (they differ by ~1e-8 relative).
+//   4. RV term [b1 cos E + a2 sin E] / (1 - e cos E), b1 = A cos w (1 - e^2) (the template's
+//      A (cos(f+w) + e cos w) with the constant folded in); the reciprocal of the denominator is one
+//      Newton step from the slope's reciprocal (they differ by ~1e-8 relative).
 // CPU emulation vs an 80-bit solution, e in [0, 0.98]: max |dE| 1.1e-15, max |dRV/A| 6e-15
 // (the oracle's own figures: 7.5e-16 and 5.2e-15) — scripts/kepler_v6_emulation.py.
 __device__ __forceinline__ float markley_starter_f32(float M, const KepConst& k) {
+  // the starter of kepler.py with the constant factors 3 and 2 folded into per-walker constants
   const float M2 = M * M;
-  const float alpha = fmaf(k.c2f, 3.14159274f - M, 7.64804745f /* F1 */);
-  const float d = fmaf(alpha, k.ef, k.ome3f);
-  const float ad = alpha * d;
-  const float r = fmaf(3.0f * ad, d - k.omef, M2) * M;
-  const float q = fmaf(2.0f * ad, k.omef, -M2);
+  const float alpha3 = fmaf(k.c2f3, 3.14159274f - M, 22.9441414f /* 3 F1 */);  // 3 alpha
+  const float d = fmaf(alpha3, k.ef3, k.ome3f);                                 // 3 (1-e) + alpha e
+  const float ad3 = alpha3 * d;                                                 // 3 alpha d
+  const float r = fmaf(ad3, d - k.omef, M2) * M;
+  const float q = fmaf(ad3, k.om23f, -M2);                                      // 2 alpha d (1-e) - M^2
   const float q2 = q * q;
   const float x = fabsf(r) + f32_sqrt(fmaf(q2, q, r * r));
   const float w = f32_ex2(0.666666687f * f32_lg2(x));  // x^(2/3)
   const float den0 = fmaf(w, w + q, q2);
-  return fmaf(2.0f * r, w, M * den0) * f32_rcp(den0 * d);
+  return fmaf(r + r, w, M * den0) * f32_rcp(den0 * d);
 }
 
-__device__ __forceinline__ double kep_rv_grid(const KepConst& k, double t, const HotConsts& H,
-                                              const double2* __restrict__ tab, const float2* __restrict__ tabf,
-                                              bool& bad) {
+// One Keplerian's RV at time t ADDED to acc.  tabf holds (sin, cos, sin/2, cos/6)(Eh) in FP32.
+// No validity flag: for e in [0, kGridEccMax] and a finite mean anomaly the FP32 starter is finite
+// and inside [0, pi + 1e-3] (M = 0 gives E0 = 0), and the table index is masked.
+__device__ __forceinline__ double kep_rv_grid(const KepConst& k, double t, double acc, const HotConsts& H,
+                                              const double2* __restrict__ tab, const float4* __restrict__ tabf) {
   const double M = mean_anomaly(k, t);
-  int sign_hi;
-  const double Mr = fold_anomaly(M, H, sign_hi);
-  const float Mf = __double2float_rn(Mr);
-  const float E0f = markley_starter_f32(Mf, k);
-  bad = !(Mf > 1e-15f) || !(E0f >= 0.0f && E0f < 3.99f);
+  // centred remainder r = M - rint(M/2pi) 2pi (exact for ANY integer near M/2pi, so the FMA in the rint is free)
+  const double kd = fma(M, H.c[4], H.c[5]) - H.c[5];
+  const double rr = fma(-kd, H.c[1], M);
+  const int sign_hi = __double2hiint(rr) & 0x80000000;
+  const double Mr = fabs(rr);
+  const float E0f = markley_starter_f32(__double2float_rn(Mr), k);
   // grid point: the low mantissa bits of E0*128 + 1.5*2^23 are rint(128 E0)
   const float km = fmaf(E0f, 128.0f, 12582912.0f);
   const float El = fmaf(km - 12582912.0f, -0.0078125f, E0f);
   const int ki = __float_as_int(km) & (kGridN - 1);
-  const double2 sc = tab[ki];   // (sin Eh, cos Eh)
-  const float2 scf = tabf[ki];
+  const double2 sc = tab[ki];  // (sin Eh, cos Eh)
+  const float4 q = tabf[ki];
   const double Eh = __hiloint2double(0x42C00000, ki) - H.g[2];  // (2^45 + k 2^-7) - 2^45, exact
   const double c = fma(k.e, sc.x, Mr - Eh);
-  // FP32 Halley step in delta-space
+  // FP32 Halley step in delta-space:  g = d - e d [cos Eh - d (sin Eh/2 + d cos Eh/6)] - c
   const float cf = __double2float_rn(c);
-  const float af = k.ef * scf.y, bf = k.ef * scf.x;
-  const float f1f = 1.0f - af;
-  const float g0 = fmaf(El, fmaf(El, fmaf(El, af * 0.166666672f, 0.5f * bf), f1f), -cf);
-  const float g1 = fmaf(El, fmaf(El, 0.5f * af, bf), f1f);
-  const float g2 = fmaf(El, af, bf);
+  const float P = fmaf(-El, fmaf(El, q.w, q.z), q.y);
+  const float g0 = fmaf(-(k.ef * El), P, El - cf);
+  const float Q = fmaf(-El, fmaf(0.5f * El, q.y, q.x), q.y);
+  const float g1 = fmaf(-k.ef, Q, 1.0f);
+  const float g2h = k.efh * fmaf(El, q.y, q.x);  // g'' / 2
   const float r = f32_rcp(g1);
   const float dn = g0 * r;
-  const float d1 = fmaf(-0.5f * dn * dn, g2 * r, El - dn);
+  const float d1 = fmaf(-dn, dn * (g2h * r), El - dn);
   // FP64 correction
   const double df = double(d1);
   const double d2 = df * df;
@@ -448,8 +464,29 @@ __device__ __forceinline__ double kep_rv_grid(const KepConst& k, double t, const
   const double sE = fma(cEf, dd, sEf), cE = fma(-sEf, dd, cEf);
   const double den = fma(-k.e, cE, 1.0);
   const double y2 = fma(y1, fma(-den, y1, 1.0), y1);                      // 1/den: Newton from 1/gp
-  const double num = fma(k.a1, cE - k.e, k.a2 * flip_sign(sE, sign_hi));  // sin(2pi - E) = -sin E
-  return fma(num, y2, k.a3);
+  // A (cos(f+w) + e cos w) = [A cos w (1-e^2) cos E - A sin w sqrt(1-e^2) sin E] / (1 - e cos E)
+  const double num = fma(k.b1, cE, k.a2 * flip_sign(sE, sign_hi));        // sin(2pi - E) = -sin E
+  return fma(num, y2, acc);
+}
+
+// exp(x) for x <= 0 (decay factors of the MA block): n = rint(x log2 e), r = x - n ln2 (two-part),
+// degree-11 Taylor polynomial by Estrin (|r| <= 0.347: truncation 6e-15 relative), scaled by 2^n in the
+// exponent field.  Coefficients come from the kernel-parameter bank.  x < -708 saturates at ~1e-308.
+__device__ __forceinline__ double exp_neg(double x, const HotConsts& H) {
+  const double kd = fma(x, H.ex[0], H.c[5]);
+  const double n = kd - H.c[5];
+  const double r = fma(n, H.ex[2], fma(n, H.ex[1], x));
+  const double r2 = r * r, r4 = r2 * r2;
+  const double p01 = 1.0 + r;
+  const double p23 = fma(r, H.ex[4], H.ex[3]);
+  const double p45 = fma(r, H.ex[6], H.ex[5]);
+  const double p67 = fma(r, H.ex[8], H.ex[7]);
+  const double p89 = fma(r, H.ex[10], H.ex[9]);
+  const double pab = fma(r, H.ex[12], H.ex[11]);
+  const double lo = fma(r2, p23, p01), mid = fma(r2, p67, p45), hi = fma(r2, pab, p89);
+  const double p = fma(r4, fma(r4, hi, mid), lo);
+  const int ni = max(__double2loint(kd), -1021);
+  return __hiloint2double(__double2hiint(p) + (ni << 20), __double2loint(p));
 }
 
 // ---- A cos(freq t + phase): support/models/sinusoid00.model, magneticcycle00.model -------------

@@ -36,6 +36,7 @@ struct WalkerConst {
   double acc[EMP_MAX_ACC];
   double ma[2 * EMP_MAX_MA];
   double ma_itau[EMP_MAX_MA];              // 1 / tau_c
+  double ma_rh[EMP_MAX_MA], ma_thist[EMP_MAX_MA];  // MA(order >= 2) history, newest first (warp-uniform)
   PeriodicTerm per[2 * EMP_MAX_PERIODIC];  // A cos(freq t + phase) terms of Sinusoid / MagneticCycle blocks
   int n_per, _pad;
 };
@@ -53,7 +54,7 @@ struct LoglParams {
   double ll_const;            // -0.5*log(2*pi)*ndat  (00.like:1)
   double t_absmax;            // max |t|: bounds the mean anomaly per (walker, planet)
   const double2* grid_sc;     // [kGridN] (sin, cos)(k 2^-7), correctly rounded FP64
-  const float2* grid_scf;     // the same pairs rounded to FP32
+  const float4* grid_scf;     // (sin, cos, sin/2, cos/6) of the same points in FP32
   HotConsts H;                // FP64 literals of the hot loop, read as c[0x0][..] operands
 };
 
@@ -61,7 +62,7 @@ struct LoglParams {
 constexpr size_t kSmemBarOff = size_t(kStages) * kTileBytes;
 constexpr size_t kSmemTabOff = kSmemBarOff + 64;
 constexpr size_t kSmemTabfOff = kSmemTabOff + kGridN * sizeof(double2);
-constexpr size_t kSmemWalkerOff = kSmemTabfOff + kGridN * sizeof(float2);
+constexpr size_t kSmemWalkerOff = kSmemTabfOff + kGridN * sizeof(float4);
 constexpr size_t kLoglSmemBytes = kSmemWalkerOff + kWalkerWarps * sizeof(WalkerConst);
 static_assert(2 * kStages * sizeof(uint64_t) <= 64 && kSmemTabOff % 16 == 0, "shared-memory layout");
 
@@ -91,6 +92,7 @@ __device__ __forceinline__ void walker_constants(const EmpModelDesc* __restrict_
   if (lane < d->acc_order) wc.acc[lane] = wc.th[d->acc_off + lane];
   if (lane < 2 * d->ma_order) wc.ma[lane] = wc.th[d->ma_off + lane];
   if (lane < d->ma_order) wc.ma_itau[lane] = 1.0 / wc.th[d->ma_off + 2 * lane + 1];
+  if (lane < EMP_MAX_MA) { wc.ma_rh[lane] = 0.0; wc.ma_thist[lane] = 0.0; }
   if (lane == 0) {
     int n = 0;
     for (int b = 0; b < d->n_periodic; ++b) {
@@ -137,19 +139,31 @@ __device__ __forceinline__ double accel_term(const double* acc, int order, doubl
 }
 
 // ---- launch 2: likelihood -------------------------------------------------------------------
-// per-lane running sums and the warp-uniform MA state
+// per-lane running sums and the warp-uniform MA(1) state
 struct LaneAcc {
-  double chi, lsum, prod;
-  int nprod;
-  double r_carry, t_prev;                    // MA(1) carry: previous residual and timestamp
-  double rh[EMP_MAX_MA], thist[EMP_MAX_MA];  // MA(order >= 2) history, newest first
+  double chi;              // sum r^2 / err2
+  double prod;             // running product of err2, mantissa kept in [1, 2)
+  int esum;                // ... and the sum of the exponent fields taken out of it
+  double r_carry, t_prev;  // MA(1) carry: previous residual and timestamp
 };
+
+// one step of the inclusive warp scan over affine maps r -> A r + B, predicated instead of selected
+__device__ __forceinline__ void scan_step(double& A, double& B, double Ap, double Bp, int lane, int off) {
+  asm("{\n"
+      ".reg .pred p;\n"
+      "setp.ge.s32 p, %4, %5;\n"
+      "@p fma.rn.f64 %1, %0, %3, %1;\n"
+      "@p mul.rn.f64 %0, %0, %2;\n"
+      "}\n"
+      : "+d"(A), "+d"(B)
+      : "d"(Ap), "d"(Bp), "r"(lane), "r"(off));
+}
 
 // Everything after the Keplerian sum for one group of 64 points (lane owns points 2*lane, 2*lane+1 of
 // the group): acceleration, offsets, jitter, MA recurrence, periodic terms, chi^2 and log-det.
-__device__ __forceinline__ void tail64(const WalkerConst& wc, const LoglParams& P, LaneAcc& A, int lane, int it,
-                                       int cnt, int64_t base, const unsigned char* tb, double2 t2, double m0,
-                                       double m1, int acc_order, int ma_order, int n_per) {
+__device__ __forceinline__ void tail64(WalkerConst& wc, const LoglParams& P, LaneAcc& A, int lane, int it, int cnt,
+                                       int64_t base, const unsigned char* tb, double2 t2, double m0, double m1,
+                                       int acc_order, int ma_order, int n_per) {
   const double2* ys = reinterpret_cast<const double2*>(tb + kTilePoints * 8);
   const double2* es = reinterpret_cast<const double2*>(tb + kTilePoints * 16);
   const int2* is = reinterpret_cast<const int2*>(tb + kTilePoints * 24);
@@ -177,15 +191,16 @@ __device__ __forceinline__ void tail64(const WalkerConst& wc, const LoglParams& 
     const double tl = __shfl_up_sync(0xffffffffu, t2.y, 1);
     const double tp0 = (lane == 0) ? A.t_prev : tl;
     const bool first_pt = (base + p0) == 0;  // i == 0: no MA term (`if i > c`)
-    double a0 = (v0 && !first_pt) ? -phi * exp(-fabs(t2.x - tp0) * itau) : 0.0;
-    double a1 = v1 ? -phi * exp(-fabs(t2.y - t2.x) * itau) : 0.0;
+    const double x0 = -fabs(t2.x - tp0) * itau, x1 = -fabs(t2.y - t2.x) * itau;
+    double a0 = (v0 && !first_pt) ? -phi * exp_neg(x0, P.H) : 0.0;
+    double a1 = v1 ? -phi * exp_neg(x1, P.H) : 0.0;
     // compose the lane's two maps, then inclusive scan across lanes
     double Am = a1 * a0, Bm = fma(a1, d0, d1);
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
       const double Ap = __shfl_up_sync(0xffffffffu, Am, off);
       const double Bp = __shfl_up_sync(0xffffffffu, Bm, off);
-      if (lane >= off) { Bm = fma(Am, Bp, Bm); Am = Am * Ap; }
+      scan_step(Am, Bm, Ap, Bp, lane, off);
     }
     const double r_last = fma(Am, A.r_carry, Bm);  // residual at this lane's 2nd point
     double r_prev = __shfl_up_sync(0xffffffffu, r_last, 1);
@@ -198,8 +213,8 @@ __device__ __forceinline__ void tail64(const WalkerConst& wc, const LoglParams& 
     A.r_carry = __shfl_sync(0xffffffffu, last_is_second ? d1 : d0, last_lane);
     A.t_prev = __shfl_sync(0xffffffffu, last_is_second ? t2.y : t2.x, last_lane);
   } else if (ma_order >= 2) {
-    // general order: serial recurrence over the 64 points (rare configuration), every lane
-    // runs the same uniform loop on shuffled values so no shared scratch is needed.
+    // general order: serial recurrence over the 64 points (rare configuration), every lane runs the
+    // same uniform loop on shuffled values; the warp-uniform history lives in the walker's slot
     for (int j = 0; j < 64; ++j) {
       const int src = j >> 1;
       const double dj = __shfl_sync(0xffffffffu, (j & 1) ? d1 : d0, src);
@@ -208,17 +223,15 @@ __device__ __forceinline__ void tail64(const WalkerConst& wc, const LoglParams& 
       const int64_t gi = base + it * 64 + j;
       double r = dj;
       if (vj) {
-#pragma unroll
-        for (int c = 0; c < EMP_MAX_MA; ++c) {
-          if (c < ma_order && gi > c) {
-            const double ma = wc.ma[2 * c] * exp(-fabs(tj - A.thist[c]) / wc.ma[2 * c + 1]) * A.rh[c];
-            r -= ma;
-          }
+        for (int c = 0; c < ma_order; ++c)
+          if (gi > c) r -= wc.ma[2 * c] * exp(-fabs(tj - wc.ma_thist[c]) / wc.ma[2 * c + 1]) * wc.ma_rh[c];
+        __syncwarp();
+        if (lane == 0) {
+          for (int c = EMP_MAX_MA - 1; c > 0; --c) { wc.ma_rh[c] = wc.ma_rh[c - 1]; wc.ma_thist[c] = wc.ma_thist[c - 1]; }
+          wc.ma_rh[0] = r;
+          wc.ma_thist[0] = tj;
         }
-#pragma unroll
-        for (int c = EMP_MAX_MA - 1; c > 0; --c) { A.rh[c] = A.rh[c - 1]; A.thist[c] = A.thist[c - 1]; }
-        A.rh[0] = r;
-        A.thist[0] = tj;
+        __syncwarp();
         if (src == lane) { if (j & 1) d1 = r; else d0 = r; }
       }
     }
@@ -232,11 +245,15 @@ __device__ __forceinline__ void tail64(const WalkerConst& wc, const LoglParams& 
     if (v1) d1 -= periodic_value(pt, t2.y, P.H);
   }
 
-  // chi^2 and log-det: sum(r^2/err2 + log err2)  (00.like:5); logs taken on 4-point products
-  A.chi = fma(d0 * d0, rcp_nr<2>(w0), A.chi);
-  A.chi = fma(d1 * d1, rcp_nr<2>(w1), A.chi);
-  A.prod *= w0 * w1;
-  if (++A.nprod == 2) { A.lsum += log(A.prod); A.prod = 1.0; A.nprod = 0; }
+  // chi^2: r0^2/w0 + r1^2/w1 over the common denominator (one reciprocal per pair);
+  // log-det: sum(log err2) (00.like:5) as the log of a running product whose exponent is moved into
+  // an integer sum after every pair, so the only log() is the one after the last tile
+  const double w01 = w0 * w1;
+  A.chi = fma(fma(d0 * d0, w1, (d1 * d1) * w0), rcp_nr<2>(w01), A.chi);
+  const double pr = A.prod * w01;
+  const int hi = __double2hiint(pr);
+  A.esum += hi >> 20;
+  A.prod = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(pr));
 }
 
 // kGroups = groups of 64 points a warp works on at once: 2*kGroups independent Kepler chains per lane
@@ -247,7 +264,7 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kSmemBarOff);
   uint64_t* empty_bar = full_bar + kStages;
   double2* tab = reinterpret_cast<double2*>(smem + kSmemTabOff);
-  float2* tabf = reinterpret_cast<float2*>(smem + kSmemTabfOff);
+  float4* tabf = reinterpret_cast<float4*>(smem + kSmemTabfOff);
   WalkerConst* wcs = reinterpret_cast<WalkerConst*>(smem + kSmemWalkerOff);
 
   const int n_active = *P.n_active;
@@ -294,9 +311,8 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
   const int n_per = active ? wc.n_per : 0;
 
   LaneAcc A;
-  A.chi = 0.0; A.lsum = 0.0; A.prod = 1.0; A.nprod = 0; A.r_carry = 0.0; A.t_prev = 0.0;
-#pragma unroll
-  for (int c = 0; c < EMP_MAX_MA; ++c) { A.rh[c] = 0.0; A.thist[c] = 0.0; }
+  A.chi = 0.0; A.prod = 1.0; A.esum = 0; A.r_carry = 0.0; A.t_prev = 0.0;
+  int n_pairs = 0;  // pairs of points folded into the running product (warp-uniform)
 
   for (int i = 0; i < n_tiles; ++i) {
     const int s = i % kStages;
@@ -331,24 +347,11 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
         for (int k = 0; k < K; ++k) {
           const KepConst& kc = wc.kep[k];
           if ((kc.slow_mod | kc.robust) == 0) {  // warp-uniform
-            double r[2 * kGroups];
-            bool anybad = false;
 #pragma unroll
             for (int u = 0; u < kGroups; ++u) {  // straight-line code: the scheduler interleaves the chains
-              bool b0, b1;
-              r[2 * u] = kep_rv_grid(kc, t2[u].x, P.H, tab, tabf, b0);
-              r[2 * u + 1] = kep_rv_grid(kc, t2[u].y, P.H, tab, tabf, b1);
-              anybad = anybad || b0 || b1;
+              m[2 * u] = kep_rv_grid(kc, t2[u].x, m[2 * u], P.H, tab, tabf);
+              m[2 * u + 1] = kep_rv_grid(kc, t2[u].y, m[2 * u + 1], P.H, tab, tabf);
             }
-            if (__any_sync(0xffffffffu, anybad)) {  // rare (M ~ 0): redo the group on the checked path
-#pragma unroll
-              for (int u = 0; u < kGroups; ++u) {
-                r[2 * u] = kep_rv_robust(kc, t2[u].x);
-                r[2 * u + 1] = kep_rv_robust(kc, t2[u].y);
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 2 * kGroups; ++j) m[j] += r[j];
           } else {
 #pragma unroll
             for (int u = 0; u < kGroups; ++u) {
@@ -359,8 +362,10 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
         }
 #pragma unroll
         for (int u = 0; u < kGroups; ++u)
-          if (it + u < iters)
+          if (it + u < iters) {
             tail64(wc, P, A, lane, it + u, cnt, base, tb, t2[u], m[2 * u], m[2 * u + 1], acc_order, ma_order, n_per);
+            ++n_pairs;
+          }
       }
     }
     __syncwarp();
@@ -368,8 +373,8 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
   }
 
   if (active) {
-    A.lsum += log(A.prod);
-    const double tot = warp_sum(A.chi + A.lsum);
+    const double lsum = fma(double(A.esum - 1023 * n_pairs), 0.693147180559945309417, log(A.prod));
+    const double tot = warp_sum(A.chi + lsum);
     if (lane == 0) P.logl[slot] = fma(-0.5, tot, P.ll_const);
   }
 }
