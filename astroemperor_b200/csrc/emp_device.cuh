@@ -419,16 +419,28 @@ __device__ __forceinline__ float markley_starter_f32(float M, const KepConst& k)
   return fmaf(r + r, w, M * den0) * f32_rcp(den0 * d);
 }
 
-// One Keplerian's RV at time t ADDED to acc.  tabf holds (sin, cos, sin/2, cos/6)(Eh) in FP32.
-// No validity flag: for e in [0, kGridEccMax] and a finite mean anomaly the FP32 starter is finite
-// and inside [0, pi + 1e-3] (M = 0 gives E0 = 0), and the table index is masked.
-__device__ __forceinline__ double kep_rv_grid(const KepConst& k, double t, double acc, const HotConsts& H,
-                                              const double2* __restrict__ tab, const float4* __restrict__ tabf) {
+// The core is split in two stages so that the likelihood kernel can software-pipeline them across
+// planets (stage A of planet k+1 is issued next to stage C of planet k: A is FP32/MUFU/LDS heavy, C is
+// pure FP64, and a warp's in-order instruction stream then feeds both pipes all the time).
+struct GridStage {   // what stage A hands to stage C, per point
+  double df;         // FP32-accurate delta (E = Eh + delta), widened
+  double c;          // (M - Eh) + e sin Eh
+  double sh, ch;     // sin Eh, cos Eh
+  int sign_hi;       // sign bit of the centred remainder: the root is reflected to 2pi - E
+};
+
+// Stage A: mean anomaly, exact reduction, FP32 starter, grid lookup, FP32 Halley step in delta-space.
+// tabf holds (sin, cos, sin/2, cos/6)(Eh) in FP32.  No validity flag: for e in [0, kGridEccMax] and a
+// finite mean anomaly the FP32 starter is finite and inside [0, pi + 1e-3] (M = 0 gives E0 = 0), and
+// the table index is masked.
+__device__ __forceinline__ void kep_grid_a(const KepConst& k, double t, const HotConsts& H,
+                                           const double2* __restrict__ tab, const float4* __restrict__ tabf,
+                                           GridStage& S) {
   const double M = mean_anomaly(k, t);
   // centred remainder r = M - rint(M/2pi) 2pi (exact for ANY integer near M/2pi, so the FMA in the rint is free)
   const double kd = fma(M, H.c[4], H.c[5]) - H.c[5];
   const double rr = fma(-kd, H.c[1], M);
-  const int sign_hi = __double2hiint(rr) & 0x80000000;
+  S.sign_hi = __double2hiint(rr) & 0x80000000;
   const double Mr = fabs(rr);
   const float E0f = markley_starter_f32(__double2float_rn(Mr), k);
   // grid point: the low mantissa bits of E0*128 + 1.5*2^23 are rint(128 E0)
@@ -449,15 +461,22 @@ __device__ __forceinline__ double kep_rv_grid(const KepConst& k, double t, doubl
   const float r = f32_rcp(g1);
   const float dn = g0 * r;
   const float d1 = fmaf(-dn, dn * (g2h * r), El - dn);
-  // FP64 correction
-  const double df = double(d1);
+  S.df = double(d1);
+  S.c = c;
+  S.sh = sc.x;
+  S.ch = sc.y;
+}
+
+// Stage C: FP64 correction and the RV term, ADDED to acc.
+__device__ __forceinline__ double kep_grid_c(const KepConst& k, const GridStage& S, double acc, const HotConsts& H) {
+  const double df = S.df;
   const double d2 = df * df;
   const double sl = fma(df * d2, fma(d2, H.g[0], -H.c[7]), df);          // sin(delta)
-  const double cm = d2 * fma(d2, fma(d2, H.g[1], -H.c[8]), 0.5);          // 1 - cos(delta)
-  const double w1 = fma(sc.y, sl, -sc.x * cm);                            // sin E_f - sin Eh
-  const double w2 = fma(sc.x, sl, sc.y * cm);                             // cos Eh - cos E_f
-  const double sEf = sc.x + w1, cEf = sc.y - w2;
-  const double g = fma(-k.e, w1, df - c);                                 // E_f - e sin E_f - M
+  const double cm = d2 * fma(d2, -H.c[8], 0.5);                           // 1 - cos(delta): d^6/720 < 1.1e-17
+  const double w1 = fma(S.ch, sl, -S.sh * cm);                            // sin E_f - sin Eh
+  const double w2 = fma(S.sh, sl, S.ch * cm);                             // cos Eh - cos E_f
+  const double sEf = S.sh + w1, cEf = S.ch - w2;
+  const double g = fma(-k.e, w1, df - S.c);                               // E_f - e sin E_f - M
   const double gp = fma(-k.e, cEf, 1.0);                                  // 1 - e cos E_f
   const double y1 = rcp_nr<1>(gp);
   const double dd = -g * y1;
@@ -465,8 +484,15 @@ __device__ __forceinline__ double kep_rv_grid(const KepConst& k, double t, doubl
   const double den = fma(-k.e, cE, 1.0);
   const double y2 = fma(y1, fma(-den, y1, 1.0), y1);                      // 1/den: Newton from 1/gp
   // A (cos(f+w) + e cos w) = [A cos w (1-e^2) cos E - A sin w sqrt(1-e^2) sin E] / (1 - e cos E)
-  const double num = fma(k.b1, cE, k.a2 * flip_sign(sE, sign_hi));        // sin(2pi - E) = -sin E
+  const double num = fma(k.b1, cE, k.a2 * flip_sign(sE, S.sign_hi));      // sin(2pi - E) = -sin E
   return fma(num, y2, acc);
+}
+
+__device__ __forceinline__ double kep_rv_grid(const KepConst& k, double t, double acc, const HotConsts& H,
+                                              const double2* __restrict__ tab, const float4* __restrict__ tabf) {
+  GridStage S;
+  kep_grid_a(k, t, H, tab, tabf, S);
+  return kep_grid_c(k, S, acc, H);
 }
 
 // exp(x) for x <= 0 (decay factors of the MA block): n = rint(x log2 e), r = x - n ln2 (two-part),
