@@ -73,6 +73,8 @@ struct EmpHandle {
   size_t tev_used = 0;
 };
 
+static void make_grid_tables(std::vector<double2>& sc, std::vector<float4>& scf);
+
 extern "C" const char* emp_last_error(void) { return g_last_error.c_str(); }
 extern "C" int emp_abi_version(void) { return EMP_ABI_VERSION; }
 
@@ -201,14 +203,9 @@ extern "C" int emp_create(const EmpModelDesc* desc, const double* t, const doubl
   CUDA_TRY(cudaMemset(h->d_cnt, 0, 4 * sizeof(unsigned long long)));
 
   {
-    // (sin, cos)(k 2^-7) correctly rounded from long double; the FP32 copies are rounded from those
-    std::vector<double2> sc(kGridN);
-    std::vector<float4> scf(kGridN);
-    for (int k = 0; k < kGridN; ++k) {
-      const long double x = (long double)k / 128.0L;
-      sc[k] = make_double2(double(sinl(x)), double(cosl(x)));
-      scf[k] = make_float4(float(sc[k].x), float(sc[k].y), float(0.5 * sc[k].x), float(sc[k].y / 6.0));
-    }
+    std::vector<double2> sc;
+    std::vector<float4> scf;
+    make_grid_tables(sc, scf);
     CUDA_TRY(cudaMalloc(&h->d_grid_sc, kGridN * sizeof(double2)));
     CUDA_TRY(cudaMalloc(&h->d_grid_scf, kGridN * sizeof(float4)));
     CUDA_TRY(cudaMemcpy(h->d_grid_sc, sc.data(), kGridN * sizeof(double2), cudaMemcpyHostToDevice));
@@ -610,6 +607,85 @@ extern "C" int emp_kepler_solve_host(const double* M, const double* ecc, int64_t
   }
   if (e == cudaSuccess) e = cudaMemcpy(E, dE, n * sizeof(double), cudaMemcpyDeviceToHost);
   cudaFree(dM); cudaFree(de); cudaFree(dE);
+  if (e != cudaSuccess) return fail(EMP_ECUDA, cudaGetErrorString(e));
+  return EMP_OK;
+}
+
+// ---- the likelihood kernel's own solver, exposed for parity tests ------------------------------
+__global__ void kepler_grid_kernel(const double* __restrict__ M, const double* __restrict__ ecc, int64_t n,
+                                   int ecc_scalar, const double2* __restrict__ tab, const float4* __restrict__ tabf,
+                                   double* __restrict__ E, double* __restrict__ sinE, double* __restrict__ cosE,
+                                   const HotConsts H) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    KepConst k;
+    kep_constants_ecc(ecc[ecc_scalar ? 0 : i], k);
+    const double m = M[i];
+    double e_out, s_out, c_out;
+    if (k.robust || !(fabs(m) < 1.0e12)) {  // the kernel routes these to the kepler.py-style refinement
+      e_out = kepler_solve(m, k.e, H);
+      sincos(e_out, &s_out, &c_out);
+    } else {
+      GridStage S;
+      kep_grid_a(k, m, H, tab, tabf, S);  // freq = 1, tp = phase = 0: the mean anomaly is m itself
+      double sE, cE, dd, y1;
+      kep_grid_root(k, S, H, sE, cE, dd, y1);
+      const double Er = S.eh + (S.df + dd);
+      e_out = S.sign_hi ? H.c[1] - Er : Er;
+      s_out = flip_sign(sE, S.sign_hi);
+      c_out = cE;
+    }
+    E[i] = e_out;
+    if (sinE) sinE[i] = s_out;
+    if (cosE) cosE[i] = c_out;
+  }
+}
+
+static void make_grid_tables(std::vector<double2>& sc, std::vector<float4>& scf) {
+  // (sin, cos)(k 2^-7) correctly rounded from long double; the FP32 entries are rounded from those
+  sc.resize(kGridN);
+  scf.resize(kGridN);
+  for (int k = 0; k < kGridN; ++k) {
+    const long double x = (long double)k / 128.0L;
+    sc[k] = make_double2(double(sinl(x)), double(cosl(x)));
+    scf[k] = make_float4(float(sc[k].x), float(sc[k].y), float(0.5 * sc[k].x), float(sc[k].y / 6.0));
+  }
+}
+
+extern "C" int emp_kepler_grid_host(const double* M, const double* ecc, int64_t n, int ecc_is_scalar, double* E,
+                                    double* sinE, double* cosE, int device) {
+  if (!M || !ecc || !E || n < 0) return fail(EMP_EINVAL, "bad argument");
+  if (n == 0) return EMP_OK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(EMP_ENODEV, "no CUDA device (there is no CPU fallback)");
+  CUDA_TRY(cudaSetDevice(device));
+  std::vector<double2> sc;
+  std::vector<float4> scf;
+  make_grid_tables(sc, scf);
+  double *dM = nullptr, *de = nullptr, *dE = nullptr, *dS = nullptr, *dC = nullptr;
+  double2* dtab = nullptr;
+  float4* dtabf = nullptr;
+  const int64_t ne = ecc_is_scalar ? 1 : n;
+  cudaError_t e = cudaMalloc(&dM, n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&de, ne * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&dE, n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&dS, n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&dC, n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&dtab, kGridN * sizeof(double2));
+  if (e == cudaSuccess) e = cudaMalloc(&dtabf, kGridN * sizeof(float4));
+  if (e == cudaSuccess) e = cudaMemcpy(dM, M, n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(de, ecc, ne * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dtab, sc.data(), kGridN * sizeof(double2), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dtabf, scf.data(), kGridN * sizeof(float4), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    int blocks = int(std::min<int64_t>((n + 255) / 256, 148 * 8));
+    kepler_grid_kernel<<<blocks, 256>>>(dM, de, n, ecc_is_scalar, dtab, dtabf, dE, dS, dC, make_hot_consts());
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(E, dE, n * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && sinE) e = cudaMemcpy(sinE, dS, n * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && cosE) e = cudaMemcpy(cosE, dC, n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(dM); cudaFree(de); cudaFree(dE); cudaFree(dS); cudaFree(dC); cudaFree(dtab); cudaFree(dtabf);
   if (e != cudaSuccess) return fail(EMP_ECUDA, cudaGetErrorString(e));
   return EMP_OK;
 }

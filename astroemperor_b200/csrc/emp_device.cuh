@@ -309,6 +309,26 @@ __device__ __forceinline__ double kep_rv(const KepConst& k, double t, const HotC
   return fma(num, rcp_nr<2>(den), k.a3);
 }
 
+// the eccentricity-dependent constants alone (solver entry points: no amplitudes, no frequency)
+__device__ __forceinline__ void kep_constants_ecc(double ecc, KepConst& k) {
+  k.freq = 1.0; k.tpv = 0.0; k.phv = 0.0;
+  k.e = ecc;
+  k.ome = 1.0 - ecc;
+  k.c2 = kF2 / (1.0 + ecc);
+  k.ome3 = 3.0 * k.ome;
+  k.a1 = k.a2 = k.a3 = k.b1 = 0.0;
+  k.ef = float(ecc);
+  k.omef = float(k.ome);
+  k.c2f = float(k.c2);
+  k.ome3f = float(k.ome3);
+  k.ef3 = float(ecc / 3.0);
+  k.om23f = float(2.0 * k.ome / 3.0);
+  k.c2f3 = float(3.0 * k.c2);
+  k.efh = float(0.5 * ecc);
+  k.slow_mod = 0;
+  k.robust = (ecc >= 0.0 && ecc <= kGridEccMax) ? 0 : 1;
+}
+
 // kepler.solve(M, ecc) for one element (A13 of SURVEY.md §8a): E in [0, 2pi]
 __device__ __forceinline__ double kepler_solve(double M, double ecc, const HotConsts& H) {
   KepConst k;
@@ -426,6 +446,7 @@ struct GridStage {   // what stage A hands to stage C, per point
   double df;         // FP32-accurate delta (E = Eh + delta), widened
   double c;          // (M - Eh) + e sin Eh
   double sh, ch;     // sin Eh, cos Eh
+  double eh;         // the grid point itself (only the solver entry point reads it)
   int sign_hi;       // sign bit of the centred remainder: the root is reflected to 2pi - E
 };
 
@@ -465,10 +486,12 @@ __device__ __forceinline__ void kep_grid_a(const KepConst& k, double t, const Ho
   S.c = c;
   S.sh = sc.x;
   S.ch = sc.y;
+  S.eh = Eh;
 }
 
-// Stage C: FP64 correction and the RV term, ADDED to acc.
-__device__ __forceinline__ double kep_grid_c(const KepConst& k, const GridStage& S, double acc, const HotConsts& H) {
+// Stage C, first half: the root.  sin E, cos E of the refined E = Eh + (df + dd), and 1/(1 - e cos E_f).
+__device__ __forceinline__ void kep_grid_root(const KepConst& k, const GridStage& S, const HotConsts& H, double& sE,
+                                              double& cE, double& dd, double& y1) {
   const double df = S.df;
   const double d2 = df * df;
   const double sl = fma(df * d2, fma(d2, H.g[0], -H.c[7]), df);          // sin(delta)
@@ -478,9 +501,16 @@ __device__ __forceinline__ double kep_grid_c(const KepConst& k, const GridStage&
   const double sEf = S.sh + w1, cEf = S.ch - w2;
   const double g = fma(-k.e, w1, df - S.c);                               // E_f - e sin E_f - M
   const double gp = fma(-k.e, cEf, 1.0);                                  // 1 - e cos E_f
-  const double y1 = rcp_nr<1>(gp);
-  const double dd = -g * y1;
-  const double sE = fma(cEf, dd, sEf), cE = fma(-sEf, dd, cEf);
+  y1 = rcp_nr<1>(gp);
+  dd = -g * y1;
+  sE = fma(cEf, dd, sEf);
+  cE = fma(-sEf, dd, cEf);
+}
+
+// Stage C: FP64 correction and the RV term, ADDED to acc.
+__device__ __forceinline__ double kep_grid_c(const KepConst& k, const GridStage& S, double acc, const HotConsts& H) {
+  double sE, cE, dd, y1;
+  kep_grid_root(k, S, H, sE, cE, dd, y1);
   const double den = fma(-k.e, cE, 1.0);
   const double y2 = fma(y1, fma(-den, y1, 1.0), y1);                      // 1/den: Newton from 1/gp
   // A (cos(f+w) + e cos w) = [A cos w (1-e^2) cos E - A sin w sqrt(1-e^2) sin E] / (1 - e cos E)

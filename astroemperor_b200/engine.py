@@ -190,3 +190,17 @@ def kepler_solve(M, ecc, device: int = 0):
     _lib.check(_lib.lib().emp_kepler_solve_host(M.ctypes.data, ecc.ctypes.data, M.size, 1 if scalar else 0,
                                                 E.ctypes.data, int(device)))
     return E
+
+
+def kepler_solve_grid(M, ecc, device: int = 0):
+    """The likelihood kernel's own solver (grid-anchored core) for arrays: returns (E, sin E, cos E).
+    Same call shape as `kepler.solve(M, ecc)`; exists so that tests can pin the production core
+    element by element (the kernel never materialises E)."""
+    M = np.ascontiguousarray(M, dtype=np.float64)
+    ecc = np.asarray(ecc, dtype=np.float64)
+    scalar = ecc.ndim == 0 or ecc.size == 1
+    ecc = np.ascontiguousarray(ecc.reshape(-1) if scalar else np.broadcast_to(ecc, M.shape))
+    E, s, c = np.empty_like(M), np.empty_like(M), np.empty_like(M)
+    _lib.check(_lib.lib().emp_kepler_grid_host(M.ctypes.data, ecc.ctypes.data, M.size, 1 if scalar else 0,
+                                               E.ctypes.data, s.ctypes.data, c.ctypes.data, int(device)))
+    return E, s, c

@@ -192,6 +192,14 @@ int emp_model_host(EmpHandle *h, const double *theta_host, double *model_host, d
 int emp_kepler_solve_host(const double *M, const double *ecc, int64_t n, int ecc_is_scalar, double *E,
                           int device);
 
+/* The solver the likelihood kernel actually runs per (walker, planet, datapoint) — the grid-anchored
+ * core of emp_device.cuh (sin/cos table + FP32 Halley step + FP64 Newton correction), exposed so that
+ * parity tests can pin it element by element against the same kepler.solve call sites: E[i] in
+ * [0, 2pi] plus, if the pointers are not NULL, the sin E and cos E the RV term is built from.  Elements
+ * with ecc outside [0, 0.98] or |M| >= 1e12 take the kepler.py-style refinement, as in the kernel. */
+int emp_kepler_grid_host(const double *M, const double *ecc, int64_t n, int ecc_is_scalar, double *E,
+                         double *sinE, double *cosE, int device);
+
 /* ---- parallel-tempering step -------------------------------------------- */
 
 /* One emcee RedBlue stretch-move step of every temperature held by this handle
