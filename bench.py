@@ -304,8 +304,22 @@ def main():
     F = flops_per_point(w["kplan"], w["ma"])
     alg_flops = F * n_eval_active * N  # this rank, whole timed region
     achieved_tf = alg_flops / (kern_ms * 1e-3) * 1e-12 if kern_ms > 0 else None
+    traffic, traffic_src = None, None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
+        with open(os.path.join(REPO, "profiles", "kernel_traffic.json")) as fh:
+            tj = json.load(fh).get(args.workload)
+        if tj:
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {"bound": "fp64", "kernel": "emp::logl_rv_kernel", "achieved": achieved_tf, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": None,
+                "unit": "TFLOP/s", "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": traffic,
+                "traffic_unit": "bytes per launch (HBM); the path is compute-bound, see DESIGN.md §4.1",
+                "traffic_source": traffic_src,
+                "note": "achieved = ALGORITHMIC flops (the oracle's operation count, SURVEY.md §8d row D4: 230 per "
+                        "planet-point with libm calls at 20) / launch time; the kernel reaches the same root with "
+                        "~35 FP64 + ~40 FP32 instructions per planet-point, so frac can exceed 1 — the executed-"
+                        "instruction pipe utilisation (ncu) is in profiles/r01_notes.md",
                 "peak_source": "FP64 FMA microbenchmark measured in this run (emp_fp64_peak); "
                                "MEASURED_PEAKS.json has no FP64 entry",
                 "launches": kern_n, "avg_launch_ms": kern_ms / max(kern_n, 1),
