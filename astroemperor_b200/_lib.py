@@ -48,6 +48,7 @@ SYMBOLS = [
     ("emp_stream", ctypes.c_int, [_P, ctypes.POINTER(_P)]),
     ("emp_set_stream", ctypes.c_int, [_P, _P]),
     ("emp_synchronize", ctypes.c_int, [_P]),
+    ("emp_attach_sai", ctypes.c_int, [_P, _P, _I32]),
     ("emp_logl_batch", ctypes.c_int, [_P, _P, _I64, _P, _P]),
     ("emp_logl_batch_host", ctypes.c_int, [_P, _P, _I64, _P, _P]),
     ("emp_model_host", ctypes.c_int, [_P, _P, _P, _P]),
@@ -58,6 +59,7 @@ SYMBOLS = [
     ("emp_pt_gather_rows", ctypes.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P]),
     ("emp_nan_count", ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint32)]),
     ("emp_launch_count", ctypes.c_int, [_P, ctypes.POINTER(_I64)]),
+    ("emp_set_solver", ctypes.c_int, [_P, ctypes.c_int]),
     ("emp_set_timing", ctypes.c_int, [_P, ctypes.c_int]),
     ("emp_timing_collect", ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_I64)]),
     ("emp_counters", ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint64)]),

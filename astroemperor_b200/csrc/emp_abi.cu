@@ -46,6 +46,13 @@ struct EmpHandle {
   char* d_tiles = nullptr;
   double *d_t = nullptr, *d_y = nullptr, *d_e2 = nullptr;
   int32_t* d_ins = nullptr;
+  // host copies kept for re-packing the tiles when activity columns are attached
+  std::vector<double> h_t, h_y, h_e2;
+  std::vector<int32_t> h_ins;
+  double* d_sai = nullptr;   // [sai_cols][n] activity columns per point (of the point's own instrument)
+  int32_t sai_cols = 0;
+  bool sai_attached = false;
+  uint32_t tile_bytes = kTileBytes;
   double2* d_grid_sc = nullptr;  // sin/cos grid of the Kepler core (emp_device.cuh kep_rv_grid)
   float4* d_grid_scf = nullptr;
   double t0 = 0.0;
@@ -67,6 +74,7 @@ struct EmpHandle {
   int num_sms = 148;
   int64_t launches = 0;
   bool timing = false;
+  int solver = EMP_SOLVER_GRID;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // per-launch timing of the likelihood kernel (bench.py roofline): ring of event pairs
   std::vector<cudaEvent_t> tev;
@@ -104,6 +112,16 @@ static int validate_desc(const EmpModelDesc* d) {
     int np = (m == EMP_AKEP00) ? 7 : 5;
     if (d->kep_off[k] < 0 || d->kep_off[k] + np > d->ndim_full) return fail(EMP_EINVAL, "bad kep_off");
   }
+  if (d->n_sai < 0) return fail(EMP_EINVAL, "bad n_sai");
+  if (d->n_sai > 0) {
+    int tot = 0;
+    for (int i = 0; i < d->n_ins; ++i) {
+      if (d->sai_count[i] < 0 || d->sai_count[i] > EMP_MAX_SAI) return fail(EMP_EINVAL, "bad sai_count");
+      tot += d->sai_count[i];
+    }
+    if (tot != d->n_sai || d->sai_off < 0 || d->sai_off + d->n_sai > d->ndim_full)
+      return fail(EMP_EINVAL, "bad stellar-activity block");
+  }
   if (d->offset_off < 0 || d->offset_off + d->n_ins > d->ndim_full) return fail(EMP_EINVAL, "bad offset_off");
   if (d->has_jitter && (d->jitter_off < 0 || d->jitter_off + d->n_ins > d->ndim_full))
     return fail(EMP_EINVAL, "bad jitter_off");
@@ -119,6 +137,64 @@ static int validate_desc(const EmpModelDesc* d) {
         return fail(EMP_EINVAL, "bad prior index");
     }
   }
+  return EMP_OK;
+}
+
+// tiles: [t | y | yerr^2 | ins | activity columns...] per tile; padding replicates the last timestamp
+static int pack_tiles(EmpHandle* h, const double* sai_compact, int32_t sai_cols) {
+  const int64_t n = h->n;
+  const uint32_t tile_bytes = kTileBytes + uint32_t(sai_cols) * kTilePoints * 8;
+  std::vector<char> packed(size_t(h->n_tiles) * tile_bytes);
+  for (int32_t tix = 0; tix < h->n_tiles; ++tix) {
+    char* base = packed.data() + size_t(tix) * tile_bytes;
+    double* pt = reinterpret_cast<double*>(base);
+    double* py = pt + kTilePoints;
+    double* pe = py + kTilePoints;
+    int32_t* pi = reinterpret_cast<int32_t*>(pe + kTilePoints);
+    double* ps = reinterpret_cast<double*>(base + kTileBytes);
+    for (int j = 0; j < kTilePoints; ++j) {
+      int64_t i = int64_t(tix) * kTilePoints + j;
+      bool ok = i < n;
+      pt[j] = ok ? h->h_t[i] : h->h_t[n - 1];
+      py[j] = ok ? h->h_y[i] : 0.0;
+      pe[j] = ok ? h->h_e2[i] : 1.0;
+      pi[j] = ok ? h->h_ins[i] : 0;
+      for (int c = 0; c < sai_cols; ++c) ps[size_t(c) * kTilePoints + j] = ok ? sai_compact[size_t(c) * n + i] : 0.0;
+    }
+  }
+  cudaFree(h->d_tiles);
+  h->d_tiles = nullptr;
+  CUDA_TRY(cudaMalloc(&h->d_tiles, packed.size()));
+  CUDA_TRY(cudaMemcpy(h->d_tiles, packed.data(), packed.size(), cudaMemcpyHostToDevice));
+  h->tile_bytes = tile_bytes;
+  h->sai_cols = sai_cols;
+  return EMP_OK;
+}
+
+extern "C" int emp_attach_sai(EmpHandle* h, const double* sai_host, int32_t n_sai) {
+  if (!h || !sai_host) return fail(EMP_EINVAL, "NULL argument");
+  if (n_sai != h->desc.n_sai || n_sai < 1) return fail(EMP_EINVAL, "n_sai does not match the model descriptor");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  int cols = 0, base[EMP_MAX_INS];
+  for (int i = 0, acc = 0; i < h->desc.n_ins; ++i) {
+    base[i] = acc;
+    acc += h->desc.sai_count[i];
+    cols = std::max(cols, int(h->desc.sai_count[i]));
+  }
+  const int64_t n = h->n;
+  std::vector<double> compact(size_t(cols) * n, 0.0);
+  for (int64_t i = 0; i < n; ++i) {
+    const int in = h->h_ins[i];
+    for (int c = 0; c < h->desc.sai_count[in]; ++c) compact[size_t(c) * n + i] = sai_host[size_t(base[in] + c) * n + i];
+  }
+  int rc = pack_tiles(h, compact.data(), cols);
+  if (rc) return rc;
+  cudaFree(h->d_sai);
+  h->d_sai = nullptr;
+  CUDA_TRY(cudaMalloc(&h->d_sai, compact.size() * sizeof(double)));
+  CUDA_TRY(cudaMemcpy(h->d_sai, compact.data(), compact.size() * sizeof(double), cudaMemcpyHostToDevice));
+  h->sai_attached = true;
   return EMP_OK;
 }
 
@@ -162,31 +238,18 @@ extern "C" int emp_create(const EmpModelDesc* desc, const double* t, const doubl
   CUDA_TRY(cudaEventCreate(&h->ev0));
   CUDA_TRY(cudaEventCreate(&h->ev1));
 
-  // pack tiles: [t | y | yerr^2 | ins] per tile; padding replicates the last timestamp
-  std::vector<char> packed(size_t(h->n_tiles) * kTileBytes);
-  std::vector<double> e2(n);
-  std::vector<int32_t> ins(n);
+  h->h_t.assign(t, t + n);
+  h->h_y.assign(y, y + n);
+  h->h_e2.resize(n);
+  h->h_ins.resize(n);
   for (int64_t i = 0; i < n; ++i) {
-    e2[i] = yerr[i] * yerr[i];  // err20 = YERR_ ** 2 (emp_model.py:714)
-    ins[i] = flag[i] - 1;
+    h->h_e2[i] = yerr[i] * yerr[i];  // err20 = YERR_ ** 2 (emp_model.py:714)
+    h->h_ins[i] = flag[i] - 1;
   }
-  for (int32_t tix = 0; tix < h->n_tiles; ++tix) {
-    char* base = packed.data() + size_t(tix) * kTileBytes;
-    double* pt = reinterpret_cast<double*>(base);
-    double* py = pt + kTilePoints;
-    double* pe = py + kTilePoints;
-    int32_t* pi = reinterpret_cast<int32_t*>(pe + kTilePoints);
-    for (int j = 0; j < kTilePoints; ++j) {
-      int64_t i = int64_t(tix) * kTilePoints + j;
-      bool ok = i < n;
-      pt[j] = ok ? t[i] : t[n - 1];
-      py[j] = ok ? y[i] : 0.0;
-      pe[j] = ok ? e2[i] : 1.0;
-      pi[j] = ok ? ins[i] : 0;
-    }
-  }
-  CUDA_TRY(cudaMalloc(&h->d_tiles, packed.size()));
-  CUDA_TRY(cudaMemcpy(h->d_tiles, packed.data(), packed.size(), cudaMemcpyHostToDevice));
+  const std::vector<double>& e2 = h->h_e2;
+  const std::vector<int32_t>& ins = h->h_ins;
+  rc = pack_tiles(h, nullptr, 0);
+  if (rc) { std::string msg = g_last_error; emp_destroy(h); return fail(rc, msg); }
   CUDA_TRY(cudaMalloc(&h->d_t, n * sizeof(double)));
   CUDA_TRY(cudaMalloc(&h->d_y, n * sizeof(double)));
   CUDA_TRY(cudaMalloc(&h->d_e2, n * sizeof(double)));
@@ -212,7 +275,7 @@ extern "C" int emp_create(const EmpModelDesc* desc, const double* t, const doubl
     CUDA_TRY(cudaMemcpy(h->d_grid_scf, scf.data(), kGridN * sizeof(float4), cudaMemcpyHostToDevice));
   }
   CUDA_TRY(cudaFuncSetAttribute(logl_rv_kernel<EMP_LOGL_GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                int(kLoglSmemBytes)));
+                                int(logl_smem_bytes(kTileBytesMax))));
   if (desc->am_enabled) {
     rc = am_upload(am, &h->am);
     if (rc) {
@@ -230,7 +293,7 @@ extern "C" int emp_destroy(EmpHandle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_tiles); cudaFree(h->d_t); cudaFree(h->d_y); cudaFree(h->d_e2); cudaFree(h->d_ins);
-  cudaFree(h->d_grid_sc); cudaFree(h->d_grid_scf); cudaFree(h->d_index); cudaFree(h->d_nact); cudaFree(h->d_cnt);
+  cudaFree(h->d_sai); cudaFree(h->d_grid_sc); cudaFree(h->d_grid_scf); cudaFree(h->d_index); cudaFree(h->d_nact); cudaFree(h->d_cnt);
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
   cudaFree(h->d_desc); cudaFree(h->d_theta); cudaFree(h->d_ll); cudaFree(h->d_lp);
   cudaFree(h->d_q); cudaFree(h->d_llq); cudaFree(h->d_lpq); cudaFree(h->d_llwork); cudaFree(h->d_nan);
@@ -268,6 +331,8 @@ extern "C" int emp_synchronize(EmpHandle* h) {
 static int launch_logl(EmpHandle* h, const double* theta_dev, int64_t n_eval, double* logl_dev,
                        double* logp_dev) {
   if (n_eval == 0) return EMP_OK;
+  if (h->desc.n_sai > 0 && !h->sai_attached)
+    return fail(EMP_EINVAL, "the model has a StellarActivityBlock: call emp_attach_sai first");
   if (n_eval > 2147483647LL - kWalkerWarps) return fail(EMP_EINVAL, "n_eval too large for one launch");
   if (n_eval > h->cap_index) {
     cudaFree(h->d_index);
@@ -296,6 +361,9 @@ static int launch_logl(EmpHandle* h, const double* theta_dev, int64_t n_eval, do
   P.t_absmax = h->t_absmax;
   P.grid_sc = h->d_grid_sc;
   P.grid_scf = h->d_grid_scf;
+  P.tile_bytes = h->tile_bytes;
+  P.sai_cols = h->sai_cols;
+  P.solver = h->solver;
   P.H = make_hot_consts();
   const unsigned grid = unsigned((n_eval + kWalkerWarps - 1) / kWalkerWarps);
   cudaEvent_t e0 = h->ev0, e1 = h->ev1;
@@ -312,7 +380,7 @@ static int launch_logl(EmpHandle* h, const double* theta_dev, int64_t n_eval, do
     h->tev_used += 2;
     CUDA_TRY(cudaEventRecord(e0, h->stream));
   }
-  logl_rv_kernel<EMP_LOGL_GROUPS><<<grid, kLoglThreads, kLoglSmemBytes, h->stream>>>(P);
+  logl_rv_kernel<EMP_LOGL_GROUPS><<<grid, kLoglThreads, logl_smem_bytes(h->tile_bytes), h->stream>>>(P);
   if (h->timing) CUDA_TRY(cudaEventRecord(e1, h->stream));
   h->launches += 1;
   CUDA_TRY(cudaGetLastError());
@@ -362,6 +430,8 @@ extern "C" int emp_logl_batch_host(EmpHandle* h, const double* theta_host, int64
 
 extern "C" int emp_model_host(EmpHandle* h, const double* theta_host, double* model_host, double* err2_host) {
   if (!h || !theta_host || !model_host || !err2_host) return fail(EMP_EINVAL, "bad argument");
+  if (h->desc.n_sai > 0 && !h->sai_attached)
+    return fail(EMP_EINVAL, "the model has a StellarActivityBlock: call emp_attach_sai first");
   CUDA_TRY(cudaSetDevice(h->device));
   int rc = ensure_eval_scratch(h, 1);
   if (rc) return rc;
@@ -373,14 +443,15 @@ extern "C" int emp_model_host(EmpHandle* h, const double* theta_host, double* mo
   int blocks = int((h->n + 255) / 256);
   if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms;
   model_rv_kernel<<<blocks, 256, 0, h->stream>>>(h->d_desc, h->d_theta, h->d_t, h->d_y, h->d_e2, h->d_ins, h->n,
-                                                 h->t0, h->t_absmax, d_model, d_err2, make_hot_consts());
+                                                 h->t0, h->t_absmax, d_model, d_err2, h->d_sai, h->sai_cols,
+                                                 make_hot_consts());
   h->launches += 1;
   if (h->desc.ma_mode == EMP_MA_GLOBAL && h->desc.ma_order > 0) {
     model_ma_kernel<<<1, 32, 0, h->stream>>>(h->d_desc, h->d_theta, h->d_t, h->d_y, h->n, d_model);
     h->launches += 1;
-    if (h->desc.n_periodic > 0) {
-      model_periodic_kernel<<<blocks, 256, 0, h->stream>>>(h->d_desc, h->d_theta, h->d_t, h->n, h->t_absmax, d_model,
-                                                           make_hot_consts());
+    if (h->desc.n_periodic > 0 || h->sai_cols > 0) {
+      model_periodic_kernel<<<blocks, 256, 0, h->stream>>>(h->d_desc, h->d_theta, h->d_t, h->d_ins, h->n, h->t_absmax,
+                                                           d_model, h->d_sai, h->sai_cols, make_hot_consts());
       h->launches += 1;
     }
   }
@@ -498,6 +569,13 @@ extern "C" int emp_nan_count(EmpHandle* h, uint32_t* count) {
 extern "C" int emp_launch_count(EmpHandle* h, int64_t* count) {
   if (!h || !count) return fail(EMP_EINVAL, "NULL argument");
   *count = h->launches;
+  return EMP_OK;
+}
+
+extern "C" int emp_set_solver(EmpHandle* h, int solver) {
+  if (!h) return fail(EMP_EINVAL, "NULL handle");
+  if (solver != EMP_SOLVER_GRID && solver != EMP_SOLVER_KEPLERPY) return fail(EMP_EINVAL, "unknown solver");
+  h->solver = solver;
   return EMP_OK;
 }
 

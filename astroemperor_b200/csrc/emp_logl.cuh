@@ -37,6 +37,7 @@ struct WalkerConst {
   double ma[2 * EMP_MAX_MA];
   double ma_itau[EMP_MAX_MA];              // 1 / tau_c
   double ma_rh[EMP_MAX_MA], ma_thist[EMP_MAX_MA];  // MA(order >= 2) history, newest first (warp-uniform)
+  double sai[EMP_MAX_INS * EMP_MAX_SAI];    // activity coefficient of (instrument, column), 0 where absent
   PeriodicTerm per[2 * EMP_MAX_PERIODIC];  // A cos(freq t + phase) terms of Sinusoid / MagneticCycle blocks
   int n_per, _pad;
 };
@@ -55,16 +56,28 @@ struct LoglParams {
   double t_absmax;            // max |t|: bounds the mean anomaly per (walker, planet)
   const double2* grid_sc;     // [kGridN] (sin, cos)(k 2^-7), correctly rounded FP64
   const float4* grid_scf;     // (sin, cos, sin/2, cos/6) of the same points in FP32
+  uint32_t tile_bytes;        // kTileBytes + sai_cols * kTilePoints * 8 (activity columns follow the instrument ids)
+  int32_t sai_cols;           // activity columns per point (max over the instruments), 0 = none
+  int32_t solver;             // EMP_SOLVER_GRID (default) | EMP_SOLVER_KEPLERPY: every planet takes kep_rv_robust
   HotConsts H;                // FP64 literals of the hot loop, read as c[0x0][..] operands
 };
 
 // dynamic shared memory: tile ring | mbarriers | sin/cos grid (FP64 pairs, FP32 pairs) | walker constants
-constexpr size_t kSmemBarOff = size_t(kStages) * kTileBytes;
-constexpr size_t kSmemTabOff = kSmemBarOff + 64;
-constexpr size_t kSmemTabfOff = kSmemTabOff + kGridN * sizeof(double2);
-constexpr size_t kSmemWalkerOff = kSmemTabfOff + kGridN * sizeof(float4);
-constexpr size_t kLoglSmemBytes = kSmemWalkerOff + kWalkerWarps * sizeof(WalkerConst);
-static_assert(2 * kStages * sizeof(uint64_t) <= 64 && kSmemTabOff % 16 == 0, "shared-memory layout");
+// (the ring's size depends on the number of activity columns, so the offsets are functions of tile_bytes)
+__host__ __device__ constexpr size_t smem_bar_off(uint32_t tile_bytes) { return size_t(kStages) * tile_bytes; }
+__host__ __device__ constexpr size_t smem_tab_off(uint32_t tile_bytes) { return smem_bar_off(tile_bytes) + 64; }
+__host__ __device__ constexpr size_t smem_tabf_off(uint32_t tile_bytes) {
+  return smem_tab_off(tile_bytes) + kGridN * sizeof(double2);
+}
+__host__ __device__ constexpr size_t smem_walker_off(uint32_t tile_bytes) {
+  return smem_tabf_off(tile_bytes) + kGridN * sizeof(float4);
+}
+__host__ __device__ constexpr size_t logl_smem_bytes(uint32_t tile_bytes) {
+  return smem_walker_off(tile_bytes) + kWalkerWarps * sizeof(WalkerConst);
+}
+constexpr uint32_t kTileBytesMax = kTileBytes + EMP_MAX_SAI * kTilePoints * 8;
+static_assert(2 * kStages * sizeof(uint64_t) <= 64 && kTileBytes % 16 == 0 && (kTilePoints * 8) % 16 == 0,
+              "shared-memory layout");
 
 // theta[ndim_free] -> full theta in shared memory (emp_model.py:709-711)
 __device__ __forceinline__ void load_full_theta(const EmpModelDesc* __restrict__ d,
@@ -93,6 +106,15 @@ __device__ __forceinline__ void walker_constants(const EmpModelDesc* __restrict_
   if (lane < 2 * d->ma_order) wc.ma[lane] = wc.th[d->ma_off + lane];
   if (lane < d->ma_order) wc.ma_itau[lane] = 1.0 / wc.th[d->ma_off + 2 * lane + 1];
   if (lane < EMP_MAX_MA) { wc.ma_rh[lane] = 0.0; wc.ma_thist[lane] = 0.0; }
+  if (d->n_sai > 0) {
+    // theta_sa[j] of sai00.model, regrouped per instrument: column c of instrument i is j = sum(count[:i]) + c
+    for (int idx = lane; idx < d->n_ins * EMP_MAX_SAI; idx += 32) {
+      const int i = idx / EMP_MAX_SAI, c = idx % EMP_MAX_SAI;
+      int base = 0;
+      for (int q = 0; q < i; ++q) base += d->sai_count[q];
+      wc.sai[idx] = (c < d->sai_count[i]) ? wc.th[d->sai_off + base + c] : 0.0;
+    }
+  }
   if (lane == 0) {
     int n = 0;
     for (int b = 0; b < d->n_periodic; ++b) {
@@ -237,8 +259,14 @@ __device__ __forceinline__ void tail64(WalkerConst& wc, const LoglParams& P, Lan
     }
   }
 
-  // Sinusoid / MagneticCycle blocks come after the MA block in the reference's model
-  // (emp.py:2646-2650): they are not part of the MA residuals, only of the final one
+  // StellarActivity, Sinusoid and MagneticCycle blocks come after the MA block in the reference's model
+  // (emp.py:2636-2650): they are not part of the MA residuals, only of the final one.
+  // sai00.model: model0 += theta_sa[j] * SAI{j}_ — the tile carries, per point, the columns of ITS instrument
+  for (int c = 0; c < P.sai_cols; ++c) {
+    const double2 s2 = reinterpret_cast<const double2*>(tb + kTileBytes + size_t(c) * kTilePoints * 8)[li];
+    d0 = fma(-wc.sai[in2.x * EMP_MAX_SAI + c], s2.x, d0);  // padding rows carry 0
+    d1 = fma(-wc.sai[in2.y * EMP_MAX_SAI + c], s2.y, d1);
+  }
   for (int q = 0; q < n_per; ++q) {
     const PeriodicTerm& pt = wc.per[q];
     if (v0) d0 -= periodic_value(pt, t2.x, P.H);
@@ -261,11 +289,12 @@ template <int kGroups>
 __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* tiles_s = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kSmemBarOff);
+  const uint32_t tile_bytes = P.tile_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + smem_bar_off(tile_bytes));
   uint64_t* empty_bar = full_bar + kStages;
-  double2* tab = reinterpret_cast<double2*>(smem + kSmemTabOff);
-  float4* tabf = reinterpret_cast<float4*>(smem + kSmemTabfOff);
-  WalkerConst* wcs = reinterpret_cast<WalkerConst*>(smem + kSmemWalkerOff);
+  double2* tab = reinterpret_cast<double2*>(smem + smem_tab_off(tile_bytes));
+  float4* tabf = reinterpret_cast<float4*>(smem + smem_tabf_off(tile_bytes));
+  WalkerConst* wcs = reinterpret_cast<WalkerConst*>(smem + smem_walker_off(tile_bytes));
 
   const int n_active = *P.n_active;
   const int first = blockIdx.x * kWalkerWarps;
@@ -284,8 +313,8 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
     // prime the ring
     const int pre = n_tiles < kStages ? n_tiles : kStages;
     for (int i = 0; i < pre; ++i) {
-      mbar_arrive_expect_tx(&full_bar[i], kTileBytes);
-      tma_bulk_g2s(tiles_s + size_t(i) * kTileBytes, P.tiles + size_t(i) * kTileBytes, kTileBytes, &full_bar[i]);
+      mbar_arrive_expect_tx(&full_bar[i], tile_bytes);
+      tma_bulk_g2s(tiles_s + size_t(i) * tile_bytes, P.tiles + size_t(i) * tile_bytes, tile_bytes, &full_bar[i]);
     }
   }
   // sin/cos grid of the Kepler core (12 KB, L2-resident)
@@ -302,6 +331,7 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
     slot = P.eval_index[first + warp];
     load_full_theta(d, P.theta + slot * d->ndim_free, wc.th, lane);
     walker_constants(d, wc, lane, P.t_absmax);
+    if (P.solver == EMP_SOLVER_KEPLERPY && lane < d->n_kep) wc.kep[lane].robust = 1;
   }
   __syncthreads();  // publishes the barrier inits and the grid to all warps
 
@@ -321,14 +351,14 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
     if (threadIdx.x == 0 && i >= 2 && (i - 2 + kStages) < n_tiles) {
       const int sp = (i - 2) % kStages;
       mbar_wait(&empty_bar[sp], ((i - 2) / kStages) & 1);
-      mbar_arrive_expect_tx(&full_bar[sp], kTileBytes);
-      tma_bulk_g2s(tiles_s + size_t(sp) * kTileBytes, P.tiles + size_t(i - 2 + kStages) * kTileBytes, kTileBytes,
+      mbar_arrive_expect_tx(&full_bar[sp], tile_bytes);
+      tma_bulk_g2s(tiles_s + size_t(sp) * tile_bytes, P.tiles + size_t(i - 2 + kStages) * tile_bytes, tile_bytes,
                    &full_bar[sp]);
     }
     __syncwarp();
     mbar_wait(&full_bar[s], (i / kStages) & 1);
     if (active) {
-      const unsigned char* tb = tiles_s + size_t(s) * kTileBytes;
+      const unsigned char* tb = tiles_s + size_t(s) * tile_bytes;
       const double2* ts = reinterpret_cast<const double2*>(tb);
       const int64_t base = int64_t(i) * kTilePoints;
       const int64_t rem = P.n_points - base;
@@ -385,7 +415,7 @@ __global__ void model_rv_kernel(const EmpModelDesc* __restrict__ d, const double
                                 const double* __restrict__ t, const double* __restrict__ y,
                                 const double* __restrict__ e2, const int32_t* __restrict__ ins, int64_t n,
                                 double t0, double t_absmax, double* __restrict__ model, double* __restrict__ err2,
-                                const HotConsts H) {
+                                const double* __restrict__ sai, int sai_cols, const HotConsts H) {
   __shared__ WalkerConst wc;
   if (threadIdx.x < 32) {
     load_full_theta(d, theta, wc.th, threadIdx.x);
@@ -397,25 +427,30 @@ __global__ void model_rv_kernel(const EmpModelDesc* __restrict__ d, const double
     for (int k = 0; k < d->n_kep; ++k) m += kep_rv_checked(wc.kep[k], t[i], H);
     if (d->acc_order > 0) m += accel_term(wc.acc, d->acc_order, __dsub_rn(t[i], t0));
     m += wc.gamma[ins[i]];
-    if (d->ma_mode != EMP_MA_GLOBAL || d->ma_order == 0)  // else added after the MA pass (model_periodic_kernel)
+    if (d->ma_mode != EMP_MA_GLOBAL || d->ma_order == 0) {  // else added after the MA pass (model_periodic_kernel)
+      for (int c = 0; c < sai_cols; ++c) m += wc.sai[ins[i] * EMP_MAX_SAI + c] * sai[size_t(c) * n + i];
       for (int q = 0; q < wc.n_per; ++q) m += periodic_value(wc.per[q], t[i], H);
+    }
     model[i] = m;
     err2[i] = e2[i] + wc.jit2[ins[i]];
   }
 }
 
-// periodic terms of a model with a global MA block: added after model_ma_kernel
+// activity / periodic terms of a model with a global MA block: added after model_ma_kernel
 __global__ void model_periodic_kernel(const EmpModelDesc* __restrict__ d, const double* __restrict__ theta,
-                                      const double* __restrict__ t, int64_t n, double t_absmax,
-                                      double* __restrict__ model, const HotConsts H) {
+                                      const double* __restrict__ t, const int32_t* __restrict__ ins, int64_t n,
+                                      double t_absmax, double* __restrict__ model, const double* __restrict__ sai,
+                                      int sai_cols, const HotConsts H) {
   __shared__ WalkerConst wc;
   if (threadIdx.x < 32) {
     load_full_theta(d, theta, wc.th, threadIdx.x);
     walker_constants(d, wc, threadIdx.x, t_absmax);
   }
   __syncthreads();
-  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    for (int c = 0; c < sai_cols; ++c) model[i] += wc.sai[ins[i] * EMP_MAX_SAI + c] * sai[size_t(c) * n + i];
     for (int q = 0; q < wc.n_per; ++q) model[i] += periodic_value(wc.per[q], t[i], H);
+  }
 }
 
 __global__ void model_ma_kernel(const EmpModelDesc* __restrict__ d, const double* __restrict__ theta,

@@ -22,7 +22,7 @@ def _np64(a):
 
 
 class LikelihoodEngine:
-    def __init__(self, model, t, y, yerr, flag, am=None, device: int = 0):
+    def __init__(self, model, t, y, yerr, flag, am=None, device: int = 0, sai=None):
         import torch  # device memory / streams only
 
         self.cm: CompiledModel = model.compile() if isinstance(model, ModelSpec) else model
@@ -52,6 +52,16 @@ class LikelihoodEngine:
                                 self.flag.ctypes.data, self.ndat, am_ptr, self.device, ctypes.byref(h)))
         self._h = h
         self._L = L
+        n_sai = int(sum(getattr(self.cm, "sai_count", [])))
+        if n_sai:
+            # the SAI{j}_ columns of the generated script (emp_model.py:425-433), [ndat, n_sai]
+            if sai is None:
+                raise ValueError("model has a StellarActivityBlock but no `sai` columns were given")
+            sai = _np64(sai).reshape(self.ndat, -1)
+            if sai.shape[1] != n_sai:
+                raise ValueError(f"sai has {sai.shape[1]} columns, the model expects {n_sai}")
+            cols = np.ascontiguousarray(sai.T)  # column-major for the C-ABI: [n_sai][ndat]
+            _lib.check(L.emp_attach_sai(self._h, cols.ctypes.data, n_sai))
         self.use_torch_stream()
 
     # ---- lifetime -------------------------------------------------------------
@@ -80,6 +90,13 @@ class LikelihoodEngine:
         c = ctypes.c_int64()
         _lib.check(self._L.emp_launch_count(self._h, ctypes.byref(c)))
         return int(c.value)
+
+    SOLVERS = {"grid": 0, "kepler.py": 1}
+
+    def set_solver(self, name: str):
+        """'grid' (default): the grid-anchored refinement; 'kepler.py': the single high-order refinement of
+        kepler.py 0.0.7 for every planet (include/emperor_b200.h emp_set_solver)."""
+        _lib.check(self._L.emp_set_solver(self._h, self.SOLVERS[name]))
 
     def set_timing(self, on: bool):
         _lib.check(self._L.emp_set_timing(self._h, 1 if on else 0))

@@ -159,6 +159,18 @@ def instrument_blocks(data: RVData, acceleration=0, jitter=True, moav=None,
     return blocks
 
 
+def activity_block(data: RVData) -> List[BlockSpec]:
+    """SAIBlock + SmartSetter.set_StellarActivity (block_repo.py:243-272, 742-749): one coefficient per
+    activity column, named `Staract <instrument> <column>`, Uniform on [-1, 1]."""
+    cornums = list(data.cornums or [])
+    if not sum(cornums):
+        return []
+    ps = [_param(f"Staract {i + 1} {c + 1}", "Uniform", [-1., 1.], None)
+          for i, n in enumerate(cornums) for c in range(n)]
+    # number_: the model writer reuses it as the running column index (emp_model.py:740-745) and leaves the last
+    return [BlockSpec(type_="StellarActivity", params=ps, number=sum(cornums), sai_counts=cornums)]
+
+
 def astrometry_blocks() -> List[BlockSpec]:
     """add_offset_am / add_jitter_am (emp.py:1300-1311) + SmartSetter.set_Astrometry* (block_repo.py:835-850)."""
     off = [_param(n, "Uniform", [-1e1, 1e1], [])
@@ -199,7 +211,8 @@ def default_spec(data: RVData, kplan: int, parameterisation: int = 0, accelerati
     blocks = [keplerian_block(data, k + 1, parameterisation, list(eccentricity_limits),
                               list(eccentricity_prargs), astrometry=astrometry) for k in range(kplan)]
     blocks += instrument_blocks(data, acceleration, jitter, moav, jitter_prargs)
-    blocks += periodic_blocks(data, sinusoid, magnetic_cycle)  # after MOAV (emp.py:2646-2650)
+    blocks += activity_block(data)                              # after MOAV, before the periodic blocks
+    blocks += periodic_blocks(data, sinusoid, magnetic_cycle)  # (emp.py:2636-2650)
     if astrometry:
         blocks += astrometry_blocks()
     spec = ModelSpec(blocks=blocks, nins=data.nins)
@@ -218,6 +231,7 @@ class Simulation:
         self.keplerian_parameterisation = 0
         self.acceleration = 0
         self.switch_jitter = True
+        self.switch_SA = False  # read before load_data, like the reference (emp.py:2307)
         self.moav = {"order": 0, "global": False}
         self.sinusoid = 0
         self.magnetic_cycle = 0
@@ -243,7 +257,7 @@ class Simulation:
         """`datafiles/<star>/RV/*.vels` under read_loc (qol_utils.py:16-100)."""
         self.starname = folder_name
         base = os.path.join(f"{self.read_loc}datafiles", folder_name)
-        self.data = load_rv_folder(os.path.join(base, "RV") + os.sep)
+        self.data = load_rv_folder(os.path.join(base, "RV") + os.sep, switch_SA=self.switch_SA)
         am_dir = os.path.join(base, "AM")
         if os.path.isdir(am_dir) and os.listdir(am_dir):
             from .amdata import load_am_folder
@@ -283,7 +297,8 @@ class Simulation:
             assert len(self.engine_config["betas"]) == ntemps, f"betas should have {ntemps} items"
         self.model = self.build_model(kplan)
         d = self.data
-        eng = LikelihoodEngine(self.model, d.t, d.y, d.yerr, d.flag, am=self.am_data, device=self.device)
+        eng = LikelihoodEngine(self.model, d.t, d.y, d.yerr, d.flag, am=self.am_data, device=self.device,
+                               sai=d.sai)
         cfg = self.engine_config
         self.sampler = PTSampler(nwalkers, self.model.ndim, eng, ntemps=ntemps, betas=cfg["betas"],
                                  tsw_history=cfg["tsw_history"], smd_history=cfg["smd_history"],

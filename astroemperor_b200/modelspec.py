@@ -21,13 +21,14 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 # ---- limits of the C descriptor (include/emperor_b200.h) --------------------
-EMP_ABI_VERSION = 4
+EMP_ABI_VERSION = 5
 EMP_MAX_KEP = 10
 EMP_MAX_INS = 16
 EMP_MAX_DIM = 128
 EMP_MAX_ACC = 4
 EMP_MAX_MA = 4
 EMP_MAX_PERIODIC = 4
+EMP_MAX_SAI = 4
 EMP_MAX_PRIOR_OPS = 2 * EMP_MAX_DIM + 2 * EMP_MAX_KEP + 8
 
 PRIOR_KINDS = {"Uniform": 0, "Normal": 1, "Jeffreys": 2, "Isotropic": 3, "Fixed": 4}
@@ -77,6 +78,7 @@ class BlockSpec:
     number: int = 0  # nins for Offset/Jitter/MOAV, order for Acceleration
     moav_order: int = 0
     moav_global: bool = False
+    sai_counts: List[int] = field(default_factory=list)  # StellarActivity only: columns per instrument (cornums)
     additional: List[AdditionalPrior] = field(default_factory=list)
 
 
@@ -194,6 +196,7 @@ class EmpModelDescC(ctypes.Structure):
         ("am_jitter_off", ctypes.c_int32), ("n_prior_ops", ctypes.c_int32),
         ("n_periodic", ctypes.c_int32), ("periodic_kind", ctypes.c_int32 * EMP_MAX_PERIODIC),
         ("periodic_off", ctypes.c_int32 * EMP_MAX_PERIODIC),
+        ("n_sai", ctypes.c_int32), ("sai_off", ctypes.c_int32), ("sai_count", ctypes.c_int32 * EMP_MAX_INS),
         ("free_to_full", ctypes.c_int32 * EMP_MAX_DIM),
         ("full_init", ctypes.c_double * EMP_MAX_DIM),
         ("prior_ops", _PriorOpC * EMP_MAX_PRIOR_OPS),
@@ -228,6 +231,7 @@ class CompiledModel:
         self.ma_mode, self.ma_order, self.ma_off = MA_NONE, 0, 0
         self.am_enabled, self.am_offset_off, self.am_jitter_off = 0, 0, 0
         self.periodic: List[tuple] = []  # (kind, offset): 0 sinusoid00.model, 1 magneticcycle00.model
+        self.sai_off, self.sai_count = 0, [0] * self.n_ins  # StellarActivityBlock: columns per instrument
         self.prior_ops: List[tuple] = []
 
         off = 0
@@ -276,6 +280,14 @@ class CompiledModel:
                 self.periodic.append((kind, off))
                 if len(self.periodic) > EMP_MAX_PERIODIC:
                     raise UnsupportedModelError(f"more than {EMP_MAX_PERIODIC} Sinusoid/MagneticCycle blocks")
+            elif b.type_ == "StellarActivity":
+                seen_tail = True
+                counts = [int(c) for c in b.sai_counts]
+                if len(counts) != self.n_ins or sum(counts) != n or n == 0:
+                    raise UnsupportedModelError("StellarActivityBlock: columns per instrument do not match")
+                if max(counts) > EMP_MAX_SAI:
+                    raise UnsupportedModelError(f"more than {EMP_MAX_SAI} activity columns for one instrument")
+                self.sai_off, self.sai_count = off, counts
             elif b.type_ == "AstrometryOffset":
                 seen_tail = True
                 self.am_enabled, self.am_offset_off = 1, off
@@ -283,7 +295,7 @@ class CompiledModel:
                 seen_tail = True
                 self.am_jitter_off = off
             else:
-                # StellarActivity, Celerite2: SURVEY.md §2 rows 19, 23
+                # StellarActivityPRO, Celerite2: SURVEY.md §2 rows 19, 23
                 raise UnsupportedModelError(f"block type '{b.type_}' is outside the device hot path")
 
             # --- prior program, in the order emp.py:200-246 writes it
@@ -325,10 +337,10 @@ class CompiledModel:
         residual must see every mean-model term, so MOAV has to come last of the
         RV blocks."""
         rv = [t for t in types if t in ("Acceleration", "Offset", "Jitter", "MOAV")]
-        seq = [t for t in types if t in ("MOAV", "Sinusoid", "MagneticCycle")]
+        seq = [t for t in types if t in ("MOAV", "StellarActivity", "Sinusoid", "MagneticCycle")]
         if "MOAV" in seq and seq.index("MOAV") != 0:
-            # the reference computes the MA residuals before the periodic terms are added
-            raise UnsupportedModelError("Sinusoid/MagneticCycle blocks before MOAV are not supported")
+            # the reference computes the MA residuals before the activity / periodic terms are added
+            raise UnsupportedModelError("StellarActivity/Sinusoid/MagneticCycle blocks before MOAV are not supported")
         if "MOAV" in rv and rv.index("MOAV") < max(
                 (i for i, t in enumerate(rv) if t in ("Acceleration", "Offset")), default=-1):
             raise UnsupportedModelError("MOAV block before Offset/Acceleration is not supported")
@@ -353,6 +365,9 @@ class CompiledModel:
         d.n_periodic = len(self.periodic)
         for j, (kind, o) in enumerate(self.periodic):
             d.periodic_kind[j], d.periodic_off[j] = kind, o
+        d.n_sai, d.sai_off = int(sum(self.sai_count)), self.sai_off
+        for i, c in enumerate(self.sai_count):
+            d.sai_count[i] = c
         for j, f in enumerate(self.free_to_full):
             d.free_to_full[j] = int(f)
         for j, v in enumerate(self.full_init):
@@ -418,7 +433,8 @@ def spec_from_reddmodel(model) -> ModelSpec:
                        astrometry=bool(getattr(b, "astrometry_bool", False)),
                        number=int(getattr(b, "number_", 0) or 0),
                        moav_order=int(getattr(b, "moav", 0) or 0),
-                       moav_global=bool(getattr(b, "is_global", False)))
+                       moav_global=bool(getattr(b, "is_global", False)),
+                       sai_counts=[int(c) for c in getattr(b, "cornums", [])] if str(b.type_) == "StellarActivity" else [])
         if bs.type_ == "Offset":
             nins = len(params)
         blocks.append(bs)

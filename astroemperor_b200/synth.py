@@ -54,3 +54,15 @@ def make_synthetic_rv(seed, n, nins, kplan, ma=False, span=4000.0):
     rv += eps
     t = t + 2450000.0  # BJD-like absolute epochs; the loader subtracts common_t
     return [(t[ins == j], rv[ins == j], yerr[ins == j]) for j in range(nins)]
+
+
+def add_activity_columns(files, counts, seed):
+    """Synthetic stellar-activity indices: `counts[i]` extra columns for instrument i, weakly correlated with
+    its RVs (the shape of a `.vels` file with columns after eRV, qol_utils.py:74-79).  Returns
+    (t, rv, erv, activity[n_i, counts[i]]) per instrument."""
+    rng = np.random.default_rng(seed + 1000)
+    out = []
+    for i, (t, rv, erv) in enumerate(files):
+        cols = [rng.normal(size=len(t)) * 3.0 + 0.1 * rv for _ in range(counts[i])]
+        out.append((t, rv, erv, np.column_stack(cols) if cols else np.zeros((len(t), 0))))
+    return out

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define EMP_ABI_VERSION 4
+#define EMP_ABI_VERSION 5
 
 #define EMP_MAX_KEP 10   /* Keplerian blocks                                  */
 #define EMP_MAX_INS 16   /* instruments (offset / jitter entries)             */
@@ -36,6 +36,7 @@ extern "C" {
 #define EMP_MAX_ACC 4    /* polynomial acceleration order                     */
 #define EMP_MAX_MA 4     /* moving-average order                              */
 #define EMP_MAX_PERIODIC 4 /* Sinusoid / MagneticCycle blocks                  */
+#define EMP_MAX_SAI 4    /* stellar-activity index columns per instrument     */
 #define EMP_MAX_PRIOR_OPS (2 * EMP_MAX_DIM + 2 * EMP_MAX_KEP + 8)
 
 /* error codes */
@@ -121,6 +122,14 @@ typedef struct EmpModelDesc {
   int32_t n_periodic;
   int32_t periodic_kind[EMP_MAX_PERIODIC]; /* 0 = sinusoid, 1 = magnetic cycle */
   int32_t periodic_off[EMP_MAX_PERIODIC];
+  /* StellarActivityBlock (support/models/sai00.model, emitted once per activity column,
+   * emp_model.py:736-745): model0 += theta_sa[j] * SAI{j+1}_, also AFTER the MA block.  Column j
+   * belongs to one instrument (its entries are 0 elsewhere, qol_utils.py:74-95, 198), columns are
+   * numbered instrument by instrument: instrument i owns sai_count[i] columns starting at
+   * sum(sai_count[:i]); theta_sa = theta_full[sai_off : sai_off + n_sai]. */
+  int32_t n_sai;
+  int32_t sai_off;
+  int32_t sai_count[EMP_MAX_INS];
   int32_t free_to_full[EMP_MAX_DIM]; /* full index of free parameter j         */
   double full_init[EMP_MAX_DIM];     /* fixed values at their full index, 0 elsewhere */
   EmpPriorOp prior_ops[EMP_MAX_PRIOR_OPS];
@@ -170,6 +179,11 @@ int emp_stream(EmpHandle *h, void **stream);
  * stream, so that torch copies and these kernels are ordered without extra syncs). */
 int emp_set_stream(EmpHandle *h, void *stream);
 int emp_synchronize(EmpHandle *h);
+
+/* Stellar-activity columns of a model with desc->n_sai > 0 (the SAI{j}_ arrays of the generated
+ * script, emp_model.py:425-433): sai_host[j*n + i] = column j at point i, j < n_sai, same point
+ * order as emp_create's arrays.  Must be called once before the first evaluation. */
+int emp_attach_sai(EmpHandle *h, const double *sai_host, int32_t n_sai);
 
 /* ---- likelihood / prior -------------------------------------------------- */
 
@@ -248,6 +262,15 @@ int emp_nan_count(EmpHandle *h, uint32_t *count);
 /* ---- introspection -------------------------------------------------------- */
 /* Number of kernels this handle has launched since creation (bench.py gpu_launches). */
 int emp_launch_count(EmpHandle *h, int64_t *count);
+/* Kepler solver of the likelihood kernel.  EMP_SOLVER_GRID (default): Markley starter, then the
+ * grid-anchored refinement of emp_device.cuh (same root as kepler.solve to ~1 ulp, about half the FP64
+ * instructions).  EMP_SOLVER_KEPLERPY: Markley starter + the single high-order refinement of kepler.py
+ * 0.0.7 (the iteration the reference's kepler.solve call sites run) for every planet; the grid solver
+ * already hands eccentricities above 0.98 to it.  Both agree to ~1e-14 relative on logL (tests). */
+#define EMP_SOLVER_GRID 0
+#define EMP_SOLVER_KEPLERPY 1
+int emp_set_solver(EmpHandle *h, int solver);
+
 /* Per-launch device timing of the likelihood kernel: while enabled every launch is bracketed
  * by CUDA events on the handle's stream; emp_timing_collect synchronises, returns the summed
  * kernel time and the number of launches since the last collect, and resets. */

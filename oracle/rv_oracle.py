@@ -35,8 +35,10 @@ class RVOracle:
     """One generated script's worth of functions, for a compiled model
     (astroemperor_b200.modelspec.CompiledModel is only read as plain data)."""
 
-    def __init__(self, cm, t, y, yerr, flag):
+    def __init__(self, cm, t, y, yerr, flag, sai=None):
         self.cm = cm
+        # emp_model.py:425-433: SAI{j}_ = my_data.iloc[:, 3 + j].values, one array per activity column
+        self.SAI_ = None if sai is None else np.ascontiguousarray(sai, dtype=np.float64).reshape(len(t), -1)
         self.X_ = np.ascontiguousarray(t, dtype=np.float64)
         self.Y_ = np.ascontiguousarray(y, dtype=np.float64)
         self.YERR_ = np.ascontiguousarray(yerr, dtype=np.float64)
@@ -146,6 +148,12 @@ class RVOracle:
                         MA = macoef * np.exp(-dt / matime) * res_[i - 1 - c]
                         model0[i] += MA
                         residuals[i] -= MA
+        n_sai = int(sum(getattr(cm, "sai_count", [])))
+        if n_sai:
+            # emp_model.py:736-745 + support/models/sai00.model:3, once per activity column
+            theta_sa = theta[cm.sai_off:cm.sai_off + n_sai]
+            for j in range(n_sai):
+                model0 += theta_sa[j] * self.SAI_[:, j]
         for kind, off in getattr(cm, "periodic", []):
             if kind == 0:  # support/models/sinusoid00.model
                 per, A, phase = theta[off:off + 3]

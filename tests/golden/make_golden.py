@@ -98,7 +98,7 @@ def _write_vels(path, t, rv, erv):
     np.savetxt(path, np.column_stack([t, rv, erv]), fmt="%.17g")
 
 
-def _run_generator(workdir, starname, configure):
+def _run_generator(workdir, starname, configure, pre=None):
     """Returns (sim, namespace of the executed model/likelihood/prior section)."""
     import astroemperor as emp  # the real reference
 
@@ -109,6 +109,8 @@ def _run_generator(workdir, starname, configure):
             sim = emp.Simulation()
             sim.read_loc = workdir + "/"
             sim.save_loc = workdir + "/"
+            if pre is not None:
+                pre(sim)  # switches that load_data itself reads (switch_SA)
             sim.load_data(starname)
             sim.set_engine("reddemcee")
             k = configure(sim)
@@ -148,14 +150,16 @@ def _stage_star(workdir, star):
     return dst
 
 
-def _synthetic_star(workdir, star, seed, n, nins, kplan, ma=False):
-    """SURVEY.md §8d row D2 generator (same code as astroemperor_b200.synth)."""
-    from astroemperor_b200.synth import make_synthetic_rv
+def _synthetic_star(workdir, star, seed, n, nins, kplan, ma=False, sai=None):
+    """SURVEY.md §8d row D2 generator (same code as astroemperor_b200.synth).  `sai` = activity-index
+    columns per instrument: extra columns after eRV (qol_utils.py:74-79), correlated with the RVs."""
+    from astroemperor_b200.synth import add_activity_columns, make_synthetic_rv
     files = make_synthetic_rv(seed=seed, n=n, nins=nins, kplan=kplan, ma=ma)
+    files = add_activity_columns(files, sai if sai else [0] * nins, seed)
     d = os.path.join(workdir, "datafiles", star, "RV")
     os.makedirs(d)
-    for i, (t, rv, erv) in enumerate(files):
-        _write_vels(os.path.join(d, f"{star}_ins{i + 1}.vels"), t, rv, erv)
+    for i, (t, rv, erv, act) in enumerate(files):
+        np.savetxt(os.path.join(d, f"{star}_ins{i + 1}.vels"), np.column_stack([t, rv, erv, act]), fmt="%.17g")
 
 
 # ------------------------------------------------------------------ cases ----
@@ -212,6 +216,14 @@ CASES = {
     "synth_k1_p1_magcycle_ma1_global": dict(star="synth", cfg=_cfg(
         1, 1, moav={"order": 1, "global": True},
         extra=lambda sim: (setattr(sim, "magnetic_cycle", 1), setattr(sim, "sinusoid", 2))), n_theta=48),
+    # stellar-activity indices (sai00.model): 2 + 1 columns on 2 instruments; second case with a global MA
+    # block and a sinusoid, which fixes the reference's order MOAV -> activity -> periodic
+    "synth_k1_p0_sai21": dict(synth=dict(seed=9, n=120, nins=2, kplan=1, sai=[2, 1]), cfg=_cfg(1, 0),
+                              pre=lambda sim: setattr(sim, "switch_SA", True), n_theta=48),
+    "synth_k2_p1_sai03_ma1_global_sin": dict(
+        synth=dict(seed=10, n=150, nins=2, kplan=2, ma=True, sai=[0, 3]),
+        cfg=_cfg(2, 1, moav={"order": 1, "global": True}, extra=lambda sim: setattr(sim, "sinusoid", 1)),
+        pre=lambda sim: setattr(sim, "switch_SA", True), n_theta=48),
     # no jitter block
     "synth_k1_p0_nojit": dict(star="synth", cfg=_cfg(1, 0, jitter=False), n_theta=32),
     # GJ876: 8 instruments, 770 points
@@ -241,7 +253,7 @@ def make_case(name, case):
         else:
             star = name
             _synthetic_star(workdir, star, **case["synth"])
-        sim, ns = _run_generator(workdir, star, case["cfg"])
+        sim, ns = _run_generator(workdir, star, case["cfg"], pre=case.get("pre"))
         spec = spec_from_reddmodel(sim.model)
         assert spec.ndim == ns_ndim(sim), (spec.ndim, ns_ndim(sim))
         thetas = _draw_thetas(spec, rng, case["n_theta"])
@@ -260,6 +272,9 @@ def make_case(name, case):
                    D_=np.diff(np.array(sim.model.get_attr_param("limits", flat=True), dtype=float)[
                        sim.model.C_]).flatten(),
                    common_t=np.float64(sim.my_data_common_t))
+        n_sai = int(np.sum(getattr(sim, "cornums", [0])))
+        if n_sai:
+            out["sai"] = np.column_stack([ns[f"SAI{j + 1}_"] for j in range(n_sai)]).astype(np.float64)
         if case.get("am"):
             from astroemperor_b200.amdata import am_arrays_from_namespace
             am = am_arrays_from_namespace(ns)

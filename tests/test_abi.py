@@ -29,7 +29,7 @@ def test_python_binding_covers_header(built_lib):
     bound = {s[0] for s in _lib.SYMBOLS}
     assert bound == set(_declared_functions())
     from astroemperor_b200.modelspec import EMP_ABI_VERSION
-    assert _lib.lib().emp_abi_version() == EMP_ABI_VERSION == 4
+    assert _lib.lib().emp_abi_version() == EMP_ABI_VERSION == 5
 
 
 def test_descriptor_layout_matches_c(built_lib, tmp_path):

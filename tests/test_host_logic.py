@@ -75,6 +75,9 @@ MIRROR_CASES = {
     "synth_k1_p0_sinusoid": dict(kplan=1, sinusoid=1),
     "synth_k1_p1_magcycle_ma1_global": dict(kplan=1, parameterisation=1, moav={"order": 1, "global": True},
                                             magnetic_cycle=1, sinusoid=2),
+    "synth_k1_p0_sai21": dict(kplan=1),
+    "synth_k2_p1_sai03_ma1_global_sin": dict(kplan=2, parameterisation=1, moav={"order": 1, "global": True},
+                                             sinusoid=1),
 }
 
 
@@ -98,6 +101,9 @@ def test_default_spec_matches_reference_model(name):
     from astroemperor_b200.frontend import default_spec
     g, ref = load_golden(name)
     data = RVData(g["t"], g["y"], g["yerr"], g["flag"], float(g["common_t"]), [f"i{i}" for i in range(ref.nins)])
+    if "sai" in g.files:  # activity columns per instrument, as the loader reports them
+        data.sai = g["sai"]
+        data.cornums = [int(np.any(g["sai"][g["flag"] == i + 1] != 0, axis=0).sum()) for i in range(ref.nins)]
     mine = default_spec(data, **MIRROR_CASES[name])
     a, b = json.loads(ref.to_json()), json.loads(mine.to_json())
     assert len(a["blocks"]) == len(b["blocks"]) and a["nins"] == b["nins"]
@@ -129,6 +135,27 @@ def test_load_rv_folder_matches_datawrapper(tmp_path):
     assert np.allclose(data.t, g["t"], rtol=0, atol=1e-9) and np.allclose(data.y, g["y"], rtol=1e-14, atol=1e-13)
     # the reference's temp_data.csv round trip (emp_model.py:337) can move values by 1 ulp
     assert np.allclose(data.yerr, g["yerr"], rtol=1e-15, atol=0) and data.common_t == float(g["common_t"])
+
+
+def test_load_rv_folder_activity_columns_match_datawrapper(tmp_path):
+    """switch_SA: the activity columns after eRV get the reference's per-file normalisation
+    (qol_utils.py:88-93) and are zero outside their instrument; compared with the SAI{j}_ arrays the
+    real generator's script loaded for the same files."""
+    from astroemperor_b200.data import load_rv_folder
+    from astroemperor_b200.synth import add_activity_columns, make_synthetic_rv
+    g, spec = load_golden("synth_k1_p0_sai21")
+    d = tmp_path / "datafiles" / "star" / "RV"
+    d.mkdir(parents=True)
+    files = add_activity_columns(make_synthetic_rv(seed=9, n=120, nins=2, kplan=1), [2, 1], 9)
+    for i, (t, rv, erv, act) in enumerate(files):
+        np.savetxt(d / f"star_ins{i + 1}.vels", np.column_stack([t, rv, erv, act]), fmt="%.17g")
+    data = load_rv_folder(str(d) + os.sep, switch_SA=True)
+    assert data.cornums == [2, 1] and data.sai.shape == g["sai"].shape
+    assert np.array_equal(data.sai == 0, g["sai"] == 0)
+    assert np.allclose(data.sai, g["sai"], rtol=1e-13, atol=1e-12)
+    assert load_rv_folder(str(d) + os.sep).sai is None  # the default drops them (emp.py:2310-2312)
+    cm = spec.compile()
+    assert cm.sai_count == [2, 1] and cm.to_c().n_sai == 3
 
 
 def test_unsupported_blocks_raise():

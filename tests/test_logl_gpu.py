@@ -15,6 +15,8 @@ RTOL = 1e-12  # required by north_star: 1e-10
 
 def _engine(spec, g, **kw):
     from astroemperor_b200.engine import LikelihoodEngine
+    if hasattr(g, "files") and "sai" in g.files:
+        kw.setdefault("sai", g["sai"])
     return LikelihoodEngine(spec, g["t"], g["y"], g["yerr"], g["flag"], **kw)
 
 
@@ -39,7 +41,8 @@ def test_logl_logp_match_golden(name):
 
 @pytest.mark.parametrize("name", ["c1_51peg_k1_p0", "synth_k1_p0_acc2_fixed", "synth_k1_p1_ma2_global",
                                   "c4_synth5p_4ins_ma_global_n600", "synth_k1_p0_sinusoid",
-                                  "synth_k1_p1_magcycle_ma1_global"])
+                                  "synth_k1_p1_magcycle_ma1_global", "synth_k1_p0_sai21",
+                                  "synth_k2_p1_sai03_ma1_global_sin"])
 def test_my_model_matches_golden(name):
     g, spec = load_golden(name)
     eng = _engine(spec, g)
@@ -140,3 +143,46 @@ def test_absurd_frequency_takes_fmod_path():
     ref, _ = orc.logl_logp_batch(th)
     assert np.all(np.isfinite(ll))
     assert np.max(np.abs(ll - ref) / np.abs(ref)) < 1e-10
+
+
+def test_both_solvers_agree():
+    """EMP_SOLVER_GRID (default) and EMP_SOLVER_KEPLERPY (kepler.py's own refinement for every planet)
+    reach the same root: logL agrees to 1e-13 relative and both meet the bar against the golden values."""
+    for name in ("c4_synth5p_4ins_ma_global_n600", "c2_synth3p_2ins_n400", "c1_51peg_k1_p0"):
+        g, spec = load_golden(name)
+        eng = _engine(spec, g)
+        ll_g, _ = eng.logl_batch(g["thetas"])
+        eng.set_solver("kepler.py")
+        ll_k, _ = eng.logl_batch(g["thetas"])
+        eng.set_solver("grid")
+        ll_g2, _ = eng.logl_batch(g["thetas"])
+        fin = np.isfinite(g["logp"])
+        assert np.array_equal(ll_g, ll_g2, equal_nan=True)
+        assert np.max(np.abs(ll_g[fin] - ll_k[fin]) / np.abs(ll_k[fin])) < 1e-13, name
+        for ll in (ll_g, ll_k):
+            assert np.max(np.abs(ll[fin] - g["logl"][fin]) / np.abs(g["logl"][fin])) < RTOL, name
+
+
+def test_activity_columns_required_and_ragged():
+    """A model with a StellarActivityBlock refuses to run without its columns; with them, sizes that
+    are not multiples of the tile / warp step still match the oracle (the tile carries the columns)."""
+    from oracle.rv_oracle import RVOracle
+    from astroemperor_b200.engine import LikelihoodEngine
+    g, spec = load_golden("synth_k2_p1_sai03_ma1_global_sin")
+    with pytest.raises(ValueError):
+        LikelihoodEngine(spec, g["t"], g["y"], g["yerr"], g["flag"])
+    cm = spec.compile()
+    fin = np.isfinite(g["logp"])
+    th = g["thetas"][fin][:8]
+    rng = np.random.default_rng(3)
+    # a long, ragged data set built by tiling the fixture in time (keeps every instrument's columns consistent)
+    reps = 9
+    t = np.concatenate([g["t"] + k * (g["t"].max() + 1.0) for k in range(reps)])
+    y = np.tile(g["y"], reps) + rng.normal(size=len(t))
+    e, f, sai = np.tile(g["yerr"], reps), np.tile(g["flag"], reps), np.tile(g["sai"], (reps, 1))
+    for n in (65, 513, 1100, len(t)):
+        eng = LikelihoodEngine(spec, t[:n], y[:n], e[:n], f[:n], sai=sai[:n])
+        ll, _ = eng.logl_batch(th)
+        orc = RVOracle(cm, t[:n], y[:n], e[:n], f[:n], sai=sai[:n])
+        ref = np.array([orc.my_likelihood(x) for x in th])
+        assert np.max(np.abs(ll - ref) / np.abs(ref)) < RTOL, n

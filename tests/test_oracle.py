@@ -12,7 +12,7 @@ from oracle.rv_oracle import RVOracle
 @pytest.mark.parametrize("name", golden_cases())
 def test_oracle_matches_reference_generated_script(name):
     g, spec = load_golden(name)
-    orc = RVOracle(spec.compile(), g["t"], g["y"], g["yerr"], g["flag"])
+    orc = RVOracle(spec.compile(), g["t"], g["y"], g["yerr"], g["flag"], sai=g["sai"] if "sai" in g.files else None)
     ll, lp = orc.logl_logp_batch(g["thetas"])
     # same NumPy, same operation order -> bit identical to the generated script
     assert np.array_equal(lp, g["logp"])
