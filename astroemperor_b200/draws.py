@@ -15,8 +15,11 @@ the packages are not vendored):
         zz   = ((a-1)*rand(Ns) + 1)**2 / a
         rint = randint(Nc, size=Ns)
         u    = rand() for each walker of the split, in index order
-  swap stream, for i in range(ntemps-1, 0, -1):        # hot -> cold
+  swap draws, one RandomState per adjacent pair (i, i-1), consumed hot -> cold:
     iperm = permutation(W) ; i1perm = permutation(W) ; raccept = log(uniform(size=W))
+  (one stream per pair, not one for the sweep: a rank of a sharded ladder draws only the pairs of
+  its own temperatures and the ranks all-gather them over NCCL — with one sequential stream every
+  rank had to generate the 2(T-1) permutations of the WHOLE ladder, 10 ms per sweep at T = 256)
 
 Logs (`(ndim-1)*log(zz)`, `log(u)`) are taken here with NumPy so the device and
 the oracle compare against bit-identical thresholds.
@@ -35,8 +38,8 @@ class SweepDraws:
     rint: np.ndarray      # [nsteps, T_loc, 2, H] int32
     factors: np.ndarray   # [nsteps, T_loc, 2, H]  (ndim-1)*log(zz)
     lnu: np.ndarray       # [nsteps, T_loc, 2, H]  log(u)
-    perm: np.ndarray      # [T-1, 2, W] int32: perm[j] couples temperature j+1 (row 0) with j (row 1)
-    lnu_swap: np.ndarray  # [T-1, W]
+    perm: np.ndarray      # [R, 2, W] int32: the row of pair j couples temperature j+1 (row 0) with j (row 1)
+    lnu_swap: np.ndarray  # [R, W]   (R = T-1 pairs, or this rank's rows of a sharded ladder)
 
     FIELDS = ("half_idx", "zz", "rint", "factors", "lnu", "perm", "lnu_swap")
 
@@ -48,15 +51,15 @@ class DrawStreams:
     """One `RandomState` per temperature (reddemcee keeps one emcee sampler, hence one random
     state, per temperature) plus one for the swap sweep and one for the initial ensemble, all
     derived from a single seed.  A rank of a sharded ladder only advances the streams of its
-    own temperatures; the swap stream is advanced identically on every rank."""
+    own temperatures and of the swap pairs it was assigned."""
 
     def __init__(self, seed, ntemps: int):
         ss = np.random.SeedSequence(seed)
-        kids = ss.spawn(ntemps + 2)
+        kids = ss.spawn(2 * ntemps + 1)
         mk = lambda k: np.random.RandomState(np.random.MT19937(k))
         self.temp = [mk(k) for k in kids[:ntemps]]
-        self.swap = mk(kids[ntemps])
         self.init = mk(kids[ntemps + 1])
+        self.swap_pair = [mk(k) for k in kids[ntemps + 2:]]  # pair j: temperatures (j+1, j), j < ntemps-1
         self.ntemps = ntemps
 
 
@@ -81,9 +84,10 @@ def draw_stretch(rng: np.random.RandomState, W: int, nsteps: int, a: float = 2.0
 
 
 def draw_sweep(streams: DrawStreams, W: int, ndim: int, nsteps: int, a: float = 2.0,
-               temps: slice = None, swap: bool = True) -> SweepDraws:
+               temps: slice = None, swap: bool = True, swap_rows=None) -> SweepDraws:
     """Draws of one sweep: stretch draws for the temperatures in `temps` (default: all), swap
-    draws for the whole ladder."""
+    draws for the pairs in `swap_rows` (default: all T-1; a row index >= T-1 yields a zero row, the
+    padding of a sharded ladder whose ranks hold T/G rows each)."""
     if W % 2:
         raise ValueError("nwalkers must be even (two equal halves, emcee RedBlueMove nsplits=2)")
     T = streams.ntemps
@@ -98,15 +102,18 @@ def draw_sweep(streams: DrawStreams, W: int, ndim: int, nsteps: int, a: float = 
     factors = (ndim - 1.0) * np.log(zz)
     with np.errstate(divide="ignore"):
         lnu = np.log(u)
-    perm = np.empty((max(T - 1, 0), 2, W), dtype=np.int32)
-    lnu_swap = np.empty((max(T - 1, 0), W))
+    rows = list(range(max(T - 1, 0))) if swap_rows is None else list(swap_rows)
+    perm = np.zeros((len(rows), 2, W), dtype=np.int32)
+    lnu_swap = np.zeros((len(rows), W))
     if swap:
-        rng = streams.swap
-        for i in range(T - 1, 0, -1):
-            perm[i - 1, 0] = rng.permutation(W)
-            perm[i - 1, 1] = rng.permutation(W)
+        for k, j in enumerate(rows):
+            if j >= T - 1:
+                continue
+            rng = streams.swap_pair[j]
+            perm[k, 0] = rng.permutation(W)
+            perm[k, 1] = rng.permutation(W)
             with np.errstate(divide="ignore"):
-                lnu_swap[i - 1] = np.log(rng.uniform(size=W))
+                lnu_swap[k] = np.log(rng.uniform(size=W))
     return SweepDraws(half_idx, zz, rint, factors, lnu, perm, lnu_swap)
 
 

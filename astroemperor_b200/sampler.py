@@ -196,7 +196,14 @@ class PTSampler:
                                 draws["rint"][s], draws["factors"][s], draws["lnu"][s], self.accepted)
             self._n_accepted += self.accepted
             self._n_steps += 1
-        self._swap_draws = (draws["perm"], draws["lnu_swap"]) if self.ntemps > 1 else None
+        self._swap_draws = None
+        if self.ntemps > 1:
+            perm, lnu_swap = draws["perm"], draws["lnu_swap"]
+            if self.shard.world > 1 and perm.shape[0] == self.shard.n_local:
+                # every rank replays the whole plan: gather the pair rows (NCCL, behind the stretch kernels)
+                perm = self.shard.all_gather_rows(perm)[: self.ntemps - 1]
+                lnu_swap = self.shard.all_gather_rows(lnu_swap)[: self.ntemps - 1]
+            self._swap_draws = (perm, lnu_swap)
         self._mark("stretch")
 
     def _mark(self, name):
@@ -291,8 +298,11 @@ class PTSampler:
 
     def draw(self, nsteps: int) -> SweepDraws:
         """Host draws of one sweep for this rank (draws.py)."""
+        # sharded ladder: this rank draws the swap pairs whose row index is one of its temperatures
+        # (row T-1 is padding); sweep_begin all-gathers them into ladder order
+        rows = None if self.shard.world == 1 else range(self.ntemps)[self.shard.local_slice]
         return draw_sweep(self.streams, self.nwalkers, self.ndim, nsteps, self.a,
-                          temps=self.shard.local_slice, swap=self.ntemps > 1)
+                          temps=self.shard.local_slice, swap=self.ntemps > 1, swap_rows=rows)
 
     def run_mcmc(self, p0, nsweeps: int, nsteps: int = 1, progress: bool = False, on_sweep=None):
         """sampler.run_mcmc(p1, nsweeps=, nsteps=, progress=) (support/endit_reddemcee.scr:3).
@@ -318,11 +328,14 @@ class PTSampler:
             self.timings["draws"] += _time.perf_counter() - t0
             return d
 
-        draws = draw() if nsweeps > 0 else None
+        staged = self.stage_draws(draw(), pinned=True) if nsweeps > 0 else None
         for k in it:
-            self.sweep_begin(self.stage_draws(draws, pinned=True))
-            if k + 1 < nsweeps:  # the host draws the next sweep while the device runs this one
-                draws = draw()
+            self.sweep_begin(staged)
+            if k + 1 < nsweeps:
+                # while the device runs this sweep the host draws the next one, packs it into the other
+                # pinned buffer and enqueues its H2D copy behind the stretch kernels (double-buffered on
+                # both sides), so nothing but the 4(T-1)-byte swap-count read sits between two sweeps
+                staged = self.stage_draws(draw(), pinned=True)
             self.sweep_end()
             if self._chain is not None and (k % self.thin_by == 0):
                 j = self._stored

@@ -13,12 +13,12 @@ acc = {}
 def tk(name, t0):
     acc[name] = acc.get(name, 0.0) + time.perf_counter() - t0
 ll_host = torch.empty((w["T"], w["W"]), dtype=torch.float64).pin_memory()
-d = samp.draw(1)
+st = samp.stage_draws(samp.draw(1), pinned=True)
 for it in range(9):
     if it == 3: acc.clear(); torch.cuda.synchronize(); T0 = time.perf_counter()
-    t0 = time.perf_counter(); st = samp.stage_draws(d, pinned=True); tk("stage", t0)
     t0 = time.perf_counter(); samp.sweep_begin(st); tk("enqueue", t0)
     t0 = time.perf_counter(); d = samp.draw(1); tk("draw", t0)
+    t0 = time.perf_counter(); st = samp.stage_draws(d, pinned=True); tk("stage", t0)
     t0 = time.perf_counter(); samp.sweep_end(); tk("wait_end", t0)
     t0 = time.perf_counter(); ll_host.copy_(samp.logl, non_blocking=True); torch.cuda.current_stream().synchronize(); tk("readback", t0)
 tot = time.perf_counter() - T0

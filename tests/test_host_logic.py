@@ -39,6 +39,11 @@ def test_draw_sweep_protocol():
     d3 = draw_sweep(DrawStreams(1, T), W, nd, ns, temps=slice(1, 3))
     assert np.array_equal(d3.zz, d.zz[:, 1:3]) and np.array_equal(d3.perm, d.perm)
     assert np.array_equal(d3.lnu_swap, d.lnu_swap)
+    # a rank of a sharded ladder draws only the pair rows of its temperatures (per-pair streams); row T-1 pads
+    d4 = draw_sweep(DrawStreams(1, T), W, nd, ns, temps=slice(1, T, 2), swap_rows=range(T)[1:T:2])
+    d5 = draw_sweep(DrawStreams(1, T), W, nd, ns, temps=slice(0, T, 2), swap_rows=range(T)[0:T:2])
+    assert np.array_equal(d4.perm[0], d.perm[1]) and np.array_equal(d5.perm[0], d.perm[0])
+    assert np.array_equal(d5.lnu_swap[0], d.lnu_swap[0]) and not d5.perm[1].any() and not d5.lnu_swap[1].any()
     with pytest.raises(ValueError):
         draw_sweep(DrawStreams(1, 2), 7, 3, 1)
 
