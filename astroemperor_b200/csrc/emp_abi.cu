@@ -82,6 +82,8 @@ struct EmpHandle {
 };
 
 static void make_grid_tables(std::vector<double2>& sc, std::vector<float4>& scf);
+static int create_fill(EmpHandle* h, const EmpModelDesc* desc, const double* t, const double* y, const double* yerr,
+                       const int32_t* flag, int64_t n, const EmpAmData* am, int device, int num_sms);
 
 extern "C" const char* emp_last_error(void) { return g_last_error.c_str(); }
 extern "C" int emp_abi_version(void) { return EMP_ABI_VERSION; }
@@ -224,8 +226,21 @@ extern "C" int emp_create(const EmpModelDesc* desc, const double* t, const doubl
 
   EmpHandle* h = new (std::nothrow) EmpHandle();
   if (!h) return fail(EMP_ENOMEM, "host allocation failed");
+  rc = create_fill(h, desc, t, y, yerr, flag, n, am, device, prop.multiProcessorCount);
+  if (rc) {  // every failure after this point releases what was allocated so far
+    const std::string msg = g_last_error;
+    emp_destroy(h);
+    return fail(rc, msg);
+  }
+  *out = h;
+  return EMP_OK;
+}
+
+static int create_fill(EmpHandle* h, const EmpModelDesc* desc, const double* t, const double* y, const double* yerr,
+                       const int32_t* flag, int64_t n, const EmpAmData* am, int device, int num_sms) {
+  int rc = EMP_OK;
   h->device = device;
-  h->num_sms = prop.multiProcessorCount;
+  h->num_sms = num_sms;
   h->desc = *desc;
   h->n = n;
   h->n_tiles = int32_t((n + kTilePoints - 1) / kTilePoints);
@@ -249,7 +264,7 @@ extern "C" int emp_create(const EmpModelDesc* desc, const double* t, const doubl
   const std::vector<double>& e2 = h->h_e2;
   const std::vector<int32_t>& ins = h->h_ins;
   rc = pack_tiles(h, nullptr, 0);
-  if (rc) { std::string msg = g_last_error; emp_destroy(h); return fail(rc, msg); }
+  if (rc) return rc;
   CUDA_TRY(cudaMalloc(&h->d_t, n * sizeof(double)));
   CUDA_TRY(cudaMalloc(&h->d_y, n * sizeof(double)));
   CUDA_TRY(cudaMalloc(&h->d_e2, n * sizeof(double)));
@@ -278,13 +293,8 @@ extern "C" int emp_create(const EmpModelDesc* desc, const double* t, const doubl
                                 int(logl_smem_bytes(kTileBytesMax))));
   if (desc->am_enabled) {
     rc = am_upload(am, &h->am);
-    if (rc) {
-      std::string msg = g_last_error;
-      emp_destroy(h);
-      return fail(rc, msg);
-    }
+    if (rc) return rc;
   }
-  *out = h;
   return EMP_OK;
 }
 
