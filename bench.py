@@ -348,7 +348,7 @@ def main():
 
     if not args.no_cpu_baseline:
         cores = os.cpu_count()
-        n_cpu = args.cpu_evals or max(cores * 48, 64)
+        n_cpu = args.cpu_evals or max(cores * 600, 640)  # ~10 s of work on all host cores at C4
         cb = cpu_baseline(args.workload, n_cpu, cores)
         out["cpu_baseline"] = {"value": cb["value"], "unit": "walker*temp*datapoint/s", "cores": cores, "kind": "port",
                                "sample": f"{n_cpu} walkers x {N} points of the same workload through "
@@ -364,7 +364,7 @@ def run_reference(args, rank):
         return
     w = WORKLOADS[args.workload]
     cores = os.cpu_count()
-    n_cpu = args.cpu_evals or max(cores * 16, 32)
+    n_cpu = args.cpu_evals or max(cores * 128, 256)  # ~2 s per step on all host cores at C4
     vals = []
     t_all0 = time.perf_counter()
     for _ in range(max(args.warmup, 0)):

@@ -18,6 +18,8 @@ ncu --set full --import-source on --clock-control none -k regex:logl_rv -s 66 -c
     python bench.py --steps 1 --warmup 3 --burn 30 --no-cpu-baseline > $o/${tag}_ncu_full.log 2>&1
 ncu -i $o/${tag}_logl.ncu-rep --page raw --csv > $o/${tag}_logl_raw.csv 2>/dev/null
 compute-sanitizer --tool memcheck python -c "import __graft_entry__ as g; g.smoke()" > $o/${tag}_sanitizer.log 2>&1
+compute-sanitizer --tool racecheck python -c "import __graft_entry__ as g; g.smoke()" >> $o/${tag}_sanitizer.log 2>&1
+grep "ERROR SUMMARY" $o/${tag}_sanitizer.log
 tail -3 $o/${tag}_sanitizer.log
 for f in reference c4 c5 c2; do python - <<EOF
 import json

@@ -74,19 +74,19 @@ def v6(Mr, e, w=None):
     c = e * sh + (Mr - Eh)
     cf = c.astype(f32)
     ef = e.astype(f32)
-    af = ef * chf
-    bf = ef * shf
-    f1f = f32(1.0) - af
-    g0 = El * (El * (El * (af * f32(1.0 / 6.0)) + f32(0.5) * bf) + f1f) - cf
-    g1 = El * (El * (f32(0.5) * af) + bf) + f1f
-    g2 = El * af + bf
+    c6, s2 = (ch / 6.0).astype(f32), (0.5 * sh).astype(f32)  # table entries (sin/2, cos/6)
+    P = -El * (El * c6 + s2) + chf
+    g0 = -(ef * El) * P + (El - cf)
+    Q = -El * ((f32(0.5) * El) * chf + shf) + chf
+    g1 = -ef * Q + f32(1.0)
+    g2h = (f32(0.5) * ef) * (El * chf + shf)
     r = mufu(f32(1.0) / g1)
     dn = g0 * r
-    d1 = (f32(-0.5) * dn * dn) * (g2 * r) + (El - dn)
+    d1 = -dn * (dn * (g2h * r)) + (El - dn)
     df = d1.astype(np.float64)
     d2 = df * df
     sl = (df * d2) * (d2 * (1.0 / 120.0) - 1.0 / 6.0) + df
-    cm = d2 * (d2 * (d2 * (1.0 / 720.0) - 1.0 / 24.0) + 0.5)
+    cm = d2 * (d2 * (-1.0 / 24.0) + 0.5)  # d^6/720 < 1.1e-17 is dropped on the device too
     w1 = ch * sl - sh * cm
     w2 = sh * sl + ch * cm
     sEf = sh + w1
@@ -102,10 +102,9 @@ def v6(Mr, e, w=None):
     E = Eh + (df + dd)
     out = None
     if w is not None:
-        a1 = np.cos(w)
+        b1 = np.cos(w) * ((1.0 - e) * (1.0 + e))  # A cos w (1 - e^2): the additive constant folded in
         a2 = -np.sin(w) * np.sqrt((1.0 - e) * (1.0 + e))
-        a3 = e * np.cos(w)
-        out = (a1 * (cE - e) + a2 * sE) * y2 + a3
+        out = (b1 * cE + a2 * sE) * y2
     return E, sE, cE, out, np.abs(dd), np.abs(df)
 
 
