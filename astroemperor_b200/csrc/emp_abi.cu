@@ -75,6 +75,8 @@ struct EmpHandle {
   int64_t launches = 0;
   bool timing = false;
   int solver = EMP_SOLVER_GRID;
+  LoglKernel logl_kernels[kNumFeat] = {};  // one instantiation per model-feature mask (emp_logl.cuh)
+  LoglKernel logl_kernel = nullptr;         // the one this handle's descriptor selects
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // per-launch timing of the likelihood kernel (bench.py roofline): ring of event pairs
   std::vector<cudaEvent_t> tev;
@@ -289,7 +291,10 @@ static int create_fill(EmpHandle* h, const EmpModelDesc* desc, const double* t, 
     CUDA_TRY(cudaMemcpy(h->d_grid_sc, sc.data(), kGridN * sizeof(double2), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(h->d_grid_scf, scf.data(), kGridN * sizeof(float4), cudaMemcpyHostToDevice));
   }
-  CUDA_TRY(cudaFuncSetAttribute(logl_rv_kernel<EMP_LOGL_GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  LoglKernelTable<EMP_LOGL_GROUPS, 0>::fill(h->logl_kernels);
+  h->logl_kernel = h->logl_kernels[logl_features(*desc)];
+  if (!h->logl_kernel) return fail(EMP_EINVAL, "no likelihood kernel for this feature combination");
+  CUDA_TRY(cudaFuncSetAttribute((const void*)h->logl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 int(logl_smem_bytes(kTileBytesMax))));
   if (desc->am_enabled) {
     rc = am_upload(am, &h->am);
@@ -390,7 +395,7 @@ static int launch_logl(EmpHandle* h, const double* theta_dev, int64_t n_eval, do
     h->tev_used += 2;
     CUDA_TRY(cudaEventRecord(e0, h->stream));
   }
-  logl_rv_kernel<EMP_LOGL_GROUPS><<<grid, kLoglThreads, logl_smem_bytes(h->tile_bytes), h->stream>>>(P);
+  h->logl_kernel<<<grid, kLoglThreads, logl_smem_bytes(h->tile_bytes), h->stream>>>(P);
   if (h->timing) CUDA_TRY(cudaEventRecord(e1, h->stream));
   h->launches += 1;
   CUDA_TRY(cudaGetLastError());

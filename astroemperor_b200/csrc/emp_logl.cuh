@@ -181,8 +181,19 @@ __device__ __forceinline__ void scan_step(double& A, double& B, double Ap, doubl
       : "d"(Ap), "d"(Bp), "r"(lane), "r"(off));
 }
 
+// Model features the kernel is specialised on (one instantiation per combination the descriptor can ask
+// for): the tail runs once per point, and its warp-uniform `if (acc_order)`, `if (ma_order == 1)` ... tests
+// and loops cost a fifth of its instructions when they are decided at run time.
+constexpr int kFeatAcc = 1;    // AccelerationBlock
+constexpr int kFeatMa1 = 2;    // global MA(1) (moav01.model, order 1): warp scan
+constexpr int kFeatMaN = 4;    // global MA of order >= 2: serial recurrence
+constexpr int kFeatPost = 8;   // StellarActivity / Sinusoid / MagneticCycle terms after the MA block
+constexpr int kNumFeat = 16;
+
 // Everything after the Keplerian sum for one group of 64 points (lane owns points 2*lane, 2*lane+1 of
 // the group): acceleration, offsets, jitter, MA recurrence, periodic terms, chi^2 and log-det.
+// kFull: every point of the tile is a data point (all tiles but the last one): no validity selects.
+template <int kFeat, bool kFull>
 __device__ __forceinline__ void tail64(WalkerConst& wc, const LoglParams& P, LaneAcc& A, int lane, int it, int cnt,
                                        int64_t base, const unsigned char* tb, double2 t2, double m0, double m1,
                                        int acc_order, int ma_order, int n_per) {
@@ -191,8 +202,8 @@ __device__ __forceinline__ void tail64(WalkerConst& wc, const LoglParams& P, Lan
   const int2* is = reinterpret_cast<const int2*>(tb + kTilePoints * 24);
   const int li = it * 32 + lane;
   const int p0 = it * 64 + 2 * lane;
-  const bool v0 = p0 < cnt, v1 = (p0 + 1) < cnt;
-  if (acc_order > 0) {
+  const bool v0 = kFull || p0 < cnt, v1 = kFull || (p0 + 1) < cnt;
+  if (kFeat & kFeatAcc) {
     m0 += accel_term(wc.acc, acc_order, __dsub_rn(t2.x, P.t0));
     m1 += accel_term(wc.acc, acc_order, __dsub_rn(t2.y, P.t0));
   }
@@ -206,15 +217,16 @@ __device__ __forceinline__ void tail64(WalkerConst& wc, const LoglParams& P, Lan
   const double w0 = v0 ? e2.x + wc.jit2[in2.x] : 1.0;
   const double w1 = v1 ? e2.y + wc.jit2[in2.y] : 1.0;
 
-  if (ma_order == 1) {
+  if (kFeat & kFeatMa1) {
     // moav01.model: r_i = d_i - phi*exp(-|t_i - t_{i-1}|/tau) * r_{i-1}, sequential in i.
-    // Evaluated as a warp scan over the affine maps r -> a*r + b (exact algebra).
+    // Evaluated as a warp scan over the affine maps r -> a*r + b (exact algebra).  The very first point
+    // has no MA term (`if i > c`): its predecessor residual is the initial carry 0, so the term vanishes
+    // by itself (a0 is finite: t_prev starts at 0).
     const double phi = wc.ma[0], itau = wc.ma_itau[0];
     const double tl = __shfl_up_sync(0xffffffffu, t2.y, 1);
     const double tp0 = (lane == 0) ? A.t_prev : tl;
-    const bool first_pt = (base + p0) == 0;  // i == 0: no MA term (`if i > c`)
     const double x0 = -fabs(t2.x - tp0) * itau, x1 = -fabs(t2.y - t2.x) * itau;
-    double a0 = (v0 && !first_pt) ? -phi * exp_neg(x0, P.H) : 0.0;
+    double a0 = v0 ? -phi * exp_neg(x0, P.H) : 0.0;
     double a1 = v1 ? -phi * exp_neg(x1, P.H) : 0.0;
     // compose the lane's two maps, then inclusive scan across lanes
     double Am = a1 * a0, Bm = fma(a1, d0, d1);
@@ -230,11 +242,16 @@ __device__ __forceinline__ void tail64(WalkerConst& wc, const LoglParams& P, Lan
     d0 = fma(a0, r_prev, d0);
     d1 = fma(a1, d0, d1);
     // carry to the next 64 points: last VALID point of this group
-    const int last_lane = min(31, (cnt - it * 64 - 1) >> 1);
-    const bool last_is_second = ((cnt - it * 64) >= 2 * (last_lane + 1));
-    A.r_carry = __shfl_sync(0xffffffffu, last_is_second ? d1 : d0, last_lane);
-    A.t_prev = __shfl_sync(0xffffffffu, last_is_second ? t2.y : t2.x, last_lane);
-  } else if (ma_order >= 2) {
+    if (kFull) {
+      A.r_carry = __shfl_sync(0xffffffffu, d1, 31);
+      A.t_prev = __shfl_sync(0xffffffffu, t2.y, 31);
+    } else {
+      const int last_lane = min(31, (cnt - it * 64 - 1) >> 1);
+      const bool last_is_second = ((cnt - it * 64) >= 2 * (last_lane + 1));
+      A.r_carry = __shfl_sync(0xffffffffu, last_is_second ? d1 : d0, last_lane);
+      A.t_prev = __shfl_sync(0xffffffffu, last_is_second ? t2.y : t2.x, last_lane);
+    }
+  } else if (kFeat & kFeatMaN) {
     // general order: serial recurrence over the 64 points (rare configuration), every lane runs the
     // same uniform loop on shuffled values; the warp-uniform history lives in the walker's slot
     for (int j = 0; j < 64; ++j) {
@@ -262,15 +279,17 @@ __device__ __forceinline__ void tail64(WalkerConst& wc, const LoglParams& P, Lan
   // StellarActivity, Sinusoid and MagneticCycle blocks come after the MA block in the reference's model
   // (emp.py:2636-2650): they are not part of the MA residuals, only of the final one.
   // sai00.model: model0 += theta_sa[j] * SAI{j}_ — the tile carries, per point, the columns of ITS instrument
-  for (int c = 0; c < P.sai_cols; ++c) {
-    const double2 s2 = reinterpret_cast<const double2*>(tb + kTileBytes + size_t(c) * kTilePoints * 8)[li];
-    d0 = fma(-wc.sai[in2.x * EMP_MAX_SAI + c], s2.x, d0);  // padding rows carry 0
-    d1 = fma(-wc.sai[in2.y * EMP_MAX_SAI + c], s2.y, d1);
-  }
-  for (int q = 0; q < n_per; ++q) {
-    const PeriodicTerm& pt = wc.per[q];
-    if (v0) d0 -= periodic_value(pt, t2.x, P.H);
-    if (v1) d1 -= periodic_value(pt, t2.y, P.H);
+  if (kFeat & kFeatPost) {
+    for (int c = 0; c < P.sai_cols; ++c) {
+      const double2 s2 = reinterpret_cast<const double2*>(tb + kTileBytes + size_t(c) * kTilePoints * 8)[li];
+      d0 = fma(-wc.sai[in2.x * EMP_MAX_SAI + c], s2.x, d0);  // padding rows carry 0
+      d1 = fma(-wc.sai[in2.y * EMP_MAX_SAI + c], s2.y, d1);
+    }
+    for (int q = 0; q < n_per; ++q) {
+      const PeriodicTerm& pt = wc.per[q];
+      if (v0) d0 -= periodic_value(pt, t2.x, P.H);
+      if (v1) d1 -= periodic_value(pt, t2.y, P.H);
+    }
   }
 
   // chi^2: r0^2/w0 + r1^2/w1 over the common denominator (one reciprocal per pair);
@@ -285,7 +304,7 @@ __device__ __forceinline__ void tail64(WalkerConst& wc, const LoglParams& P, Lan
 }
 
 // kGroups = groups of 64 points a warp works on at once: 2*kGroups independent Kepler chains per lane
-template <int kGroups>
+template <int kGroups, int kFeat>
 __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* tiles_s = smem;
@@ -390,12 +409,21 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
             }
           }
         }
+        if (cnt == kTilePoints) {  // warp-uniform: every tile but the last
 #pragma unroll
-        for (int u = 0; u < kGroups; ++u)
-          if (it + u < iters) {
-            tail64(wc, P, A, lane, it + u, cnt, base, tb, t2[u], m[2 * u], m[2 * u + 1], acc_order, ma_order, n_per);
-            ++n_pairs;
-          }
+          for (int u = 0; u < kGroups; ++u)
+            tail64<kFeat, true>(wc, P, A, lane, it + u, cnt, base, tb, t2[u], m[2 * u], m[2 * u + 1], acc_order,
+                                ma_order, n_per);
+          n_pairs += kGroups;
+        } else {
+#pragma unroll
+          for (int u = 0; u < kGroups; ++u)
+            if (it + u < iters) {
+              tail64<kFeat, false>(wc, P, A, lane, it + u, cnt, base, tb, t2[u], m[2 * u], m[2 * u + 1], acc_order,
+                                   ma_order, n_per);
+              ++n_pairs;
+            }
+        }
       }
     }
     __syncwarp();
@@ -408,6 +436,30 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
     if (lane == 0) P.logl[slot] = fma(-0.5, tot, P.ll_const);
   }
 }
+
+// host side: the feature mask of a descriptor and the instantiation that serves it
+inline int logl_features(const EmpModelDesc& d) {
+  int f = 0;
+  if (d.acc_order > 0) f |= kFeatAcc;
+  if (d.ma_mode == EMP_MA_GLOBAL && d.ma_order == 1) f |= kFeatMa1;
+  if (d.ma_mode == EMP_MA_GLOBAL && d.ma_order >= 2) f |= kFeatMaN;
+  if (d.n_periodic > 0 || d.n_sai > 0) f |= kFeatPost;
+  return f;
+}
+using LoglKernel = void (*)(const LoglParams);
+template <int kGroups, int kFeat>
+struct LoglKernelTable {
+  static void fill(LoglKernel* tab) {
+    // MA(1) and MA(order >= 2) exclude each other: those slots stay null
+    if constexpr ((kFeat & kFeatMa1) && (kFeat & kFeatMaN)) tab[kFeat] = nullptr;
+    else tab[kFeat] = logl_rv_kernel<kGroups, kFeat>;
+    LoglKernelTable<kGroups, kFeat + 1>::fill(tab);
+  }
+};
+template <int kGroups>
+struct LoglKernelTable<kGroups, kNumFeat> {
+  static void fill(LoglKernel*) {}
+};
 
 // my_model(theta) for one theta: model0[n], err20[n]  (emp_model.py:706-781); thread per point
 // for the first pass, MA recurrence (if any) applied serially by one thread afterwards.
