@@ -69,7 +69,7 @@ def kernel_metrics():
         if h in KEEP or (h.startswith(STALLS) and h.endswith("_per_issue_active.ratio")):
             out.append((h, units[i], vals[i]))
     with open(os.path.join(P, f"{dst_tag}_logl_kernel_ncu.csv"), "w") as fh:
-        fh.write("# ncu --set full --import-source on --clock-control none, emp::logl_rv_kernel<2>, first launch of the timed\n"
+        fh.write("# ncu --set full --import-source on --clock-control none, emp::logl_rv_kernel<2, 2> (groups, feature mask), first launch of the timed\n"
                  "# region of `bench.py --steps 1 --warmup 3 --burn 30` (C4: N=10k, K=5, 4 ins, global MA(1); 32768 proposals\n"
                  f"# per launch, ~78% inside the prior = evaluated).  source: gpurun_out/{src_tag}_logl.ncu-rep (not committed)\n"
                  "metric,unit,value\n")
