@@ -532,13 +532,14 @@ extern "C" int emp_pt_swap_plan(EmpHandle* h, int32_t T, int32_t W, const double
   if (T > 1 && (!perm || !lnu)) return fail(EMP_EINVAL, "NULL draws");
   CUDA_TRY(cudaSetDevice(h->device));
   const size_t plan_smem = size_t(W) * 24;
-  if (plan_smem <= 200 * 1024) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      CUDA_TRY(cudaFuncSetAttribute(pt_swap_plan_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_set = true;
-    }
-    pt_swap_plan_smem_kernel<<<1, 1024, plan_smem, h->stream>>>(T, W, logl_all, betas, perm, lnu, src, n_acc);
+  if (plan_smem <= 200 * 1024 && W <= 8192) {
+    using PlanKernel = void (*)(int32_t, int32_t, const double*, const double*, const int32_t*, const double*, int32_t*,
+                                int32_t*);
+    const PlanKernel k = W <= 1024 ? pt_swap_plan_smem_kernel<1>
+                       : W <= 2048 ? pt_swap_plan_smem_kernel<2>
+                       : W <= 4096 ? pt_swap_plan_smem_kernel<4> : pt_swap_plan_smem_kernel<8>;
+    CUDA_TRY(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    k<<<1, 1024, plan_smem, h->stream>>>(T, W, logl_all, betas, perm, lnu, src, n_acc);
     h->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return EMP_OK;

@@ -131,61 +131,89 @@ __global__ void pt_swap_plan_kernel(int32_t T, int32_t W, const double* __restri
 }
 
 // Same plan with the two active logL rows and their source-index rows resident in shared memory
-// (24*W bytes, W <= 8192): per pair one coalesced read of the colder row + draws, decisions out of
-// shared memory, one coalesced write-back of the finished hot row of `src`.  The sweep is
-// sequential over pairs and every rank of a sharded ladder replays all of them, so this kernel's
-// latency is the serial (Amdahl) part of a sweep: ~2 us per pair instead of ~7.
+// (24*W bytes, W <= 8192).  The sweep is sequential over pairs and every rank of a sharded ladder replays
+// all of them, so this kernel's latency is the serial (Amdahl) part of a sweep.  Per pair: the colder
+// logL row, the two permutation rows and the uniforms of the NEXT pair are prefetched into registers while
+// the current pair is decided out of shared memory (software pipeline: the global-load latency, ~1.5 us of
+// the former 2.9 us per pair, is hidden), two block barriers, one coalesced write-back of the finished row
+// of `src` by the threads that own the same elements in the next pair (no barrier needed for it).
+// kR = elements per thread = ceil(W / 1024).
+template <int kR>
 __global__ void __launch_bounds__(1024) pt_swap_plan_smem_kernel(int32_t T, int32_t W, const double* __restrict__ logl,
                                                                 const double* __restrict__ betas,
                                                                 const int32_t* __restrict__ perm,
                                                                 const double* __restrict__ lnu,
                                                                 int32_t* __restrict__ src, int32_t* __restrict__ n_acc) {
   extern __shared__ __align__(16) unsigned char plan_smem[];
-  double* ll_a = reinterpret_cast<double*>(plan_smem);
-  double* ll_b = ll_a + W;
-  int32_t* sr_a = reinterpret_cast<int32_t*>(ll_b + W);
-  int32_t* sr_b = sr_a + W;
+  double* ll_hot = reinterpret_cast<double*>(plan_smem);
+  double* ll_cold = ll_hot + W;
+  int32_t* sr_hot = reinterpret_cast<int32_t*>(ll_cold + W);
+  int32_t* sr_cold = sr_hot + W;
   __shared__ int32_t s_count;
   const int tid = threadIdx.x, nt = blockDim.x;
-  double* ll_hot = ll_a; double* ll_cold = ll_b;
-  int32_t* sr_hot = sr_a; int32_t* sr_cold = sr_b;
+  int32_t pa[kR], pb[kR];
+  double pu[kR], pl[kR];
+  // prefetch of pair j (temperatures j+1 and j): perm rows, uniforms, the colder logL row
+  auto prefetch = [&](int j) {
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      const int k = tid + r * nt;
+      if (k < W) {
+        pa[r] = perm[(int64_t(j) * 2 + 0) * W + k];
+        pb[r] = perm[(int64_t(j) * 2 + 1) * W + k];
+        pu[r] = lnu[int64_t(j) * W + k];
+        pl[r] = logl[int64_t(j) * W + k];
+      }
+    }
+  };
   for (int w = tid; w < W; w += nt) {
     ll_hot[w] = logl[int64_t(T - 1) * W + w];
     sr_hot[w] = (T - 1) * W + w;
   }
   if (tid == 0) s_count = 0;
+  if (T > 1) prefetch(T - 2);
   for (int i = T - 1; i >= 1; --i) {
-    for (int w = tid; w < W; w += nt) {
-      ll_cold[w] = logl[int64_t(i - 1) * W + w];
-      sr_cold[w] = (i - 1) * W + w;
+    int32_t ca[kR], cb[kR];
+    double cu[kR];
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      const int k = tid + r * nt;
+      ca[r] = pa[r]; cb[r] = pb[r]; cu[r] = pu[r];
+      if (k < W) {
+        ll_cold[k] = pl[r];
+        sr_cold[k] = (i - 1) * W + k;
+      }
     }
-    __syncthreads();
     const double dbeta = __dsub_rn(betas[i - 1], betas[i]);
-    const int32_t* pi = perm + (int64_t(i - 1) * 2 + 0) * W;
-    const int32_t* pi1 = perm + (int64_t(i - 1) * 2 + 1) * W;
-    const double* u = lnu + int64_t(i - 1) * W;
+    __syncthreads();
+    if (i >= 2) prefetch(i - 2);  // in flight while this pair is decided
     int local = 0;
-    for (int k = tid; k < W; k += nt) {
-      const int a = pi[k], b = pi1[k];
-      const double la = ll_hot[a], lb = ll_cold[b];
-      if (__dmul_rn(dbeta, __dsub_rn(la, lb)) > u[k]) {
-        const int32_t sa = sr_hot[a];
-        sr_hot[a] = sr_cold[b];
-        sr_cold[b] = sa;
-        ll_hot[a] = lb;
-        ll_cold[b] = la;
-        ++local;
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      const int k = tid + r * nt;
+      if (k < W) {
+        const int a = ca[r], b = cb[r];  // slot a of temp i  <->  slot b of temp i-1; perm rows are permutations
+        const double la = ll_hot[a], lb = ll_cold[b];
+        if (__dmul_rn(dbeta, __dsub_rn(la, lb)) > cu[r]) {
+          const int32_t sa = sr_hot[a];
+          sr_hot[a] = sr_cold[b];
+          sr_cold[b] = sa;
+          ll_hot[a] = lb;
+          ll_cold[b] = la;
+          ++local;
+        }
       }
     }
     if (local) atomicAdd(&s_count, local);
     __syncthreads();
-    // row i of the plan is final: write it back; row i-1 becomes the hot side
+    // row i of the plan is final: write it back (each thread the elements it overwrites next iteration);
+    // row i-1 becomes the hot side
     for (int w = tid; w < W; w += nt) src[int64_t(i) * W + w] = sr_hot[w];
     if (tid == 0) { n_acc[i - 1] = s_count; s_count = 0; }
     double* tl = ll_hot; ll_hot = ll_cold; ll_cold = tl;
     int32_t* ts = sr_hot; sr_hot = sr_cold; sr_cold = ts;
-    __syncthreads();
   }
+  __syncthreads();
   for (int w = tid; w < W; w += nt) src[w] = sr_hot[w];
 }
 
