@@ -306,7 +306,21 @@ class Simulation:
                                  adapt_mode=cfg["adapt_mode"], seed=self.seed)
         self.sampler.D_ = self.model.prior_widths()  # emp.py:595-602
         p1 = self.sampler.initial_positions(self.model)
-        self.sampler.run_mcmc(p1, nsweeps=nsweeps, nsteps=nsteps, progress=bool(cfg.get("progress")))
+        progress = bool(cfg.get("progress"))
+        rc = self.run_config
+        if rc.get("adaptation_batches") and rc.get("adaptation_nsweeps"):
+            # two-phase run of support/endit_freeze1.scr: `reddemcee_discard` adaptation sweeps
+            # (_prepare_run_reddemcee, emp.py:2512-2520; _set_run overrides adaptation_nsweeps with it,
+            # emp.py:699-701), then the ladder is frozen for the rest
+            niter = nsteps * nsweeps
+            burn = rc.get("burnin")
+            discard = int(burn * niter) if isinstance(burn, float) else (int(burn) if isinstance(burn, int) else 0)
+            discard = min(discard, nsweeps)
+            self.sampler.run_mcmc(p1, nsweeps=discard, nsteps=nsteps, progress=progress)
+            self.sampler.select_adjustment("00")
+            self.sampler.run_mcmc(None if discard else p1, nsweeps=nsweeps - discard, nsteps=nsteps, progress=progress)
+        else:
+            self.sampler.run_mcmc(p1, nsweeps=nsweeps, nsteps=nsteps, progress=progress)
         return self.sampler
 
     def autorun(self, k_start=0, k_end=10):

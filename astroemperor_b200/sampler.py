@@ -348,6 +348,14 @@ class PTSampler:
         self.torch.cuda.synchronize(self.dev)
         return self.p
 
+    def select_adjustment(self, mode):
+        """reddemcee's ladder-adjustment selector as EMPEROR drives it: `support/endit_freeze1.scr:10` calls
+        `sampler.select_adjustment('00')` after the adaptation burn-in to FREEZE the ladder for the production
+        sweeps.  Other selectors are reddemcee internals that are not recoverable offline."""
+        if str(mode) != "00":
+            raise NotImplementedError(f"select_adjustment('{mode}'): only '00' (freeze the ladder) is implemented")
+        self.adapt = False
+
     # ---- read-back API the reference's parent process uses (SURVEY.md §8b row B2) --------
     def _get(self, buf, discard, thin, flat):
         if buf is None:
@@ -448,10 +456,67 @@ class PTSampler:
         ch = self.get_chain(discard=discard, thin=thin)  # [T, n, W, ndim]
         return np.array([thin * integrated_time(ch[t], c=c, tol=tol, quiet=quiet) for t in range(ch.shape[0])])
 
+    @property
+    def backend(self):
+        """What EMPEROR's generated save section reads after the run (emp.py:727-761): `sampler.backend.iteration`,
+        `.tsw_history[_bool]`, `.smd_history[_bool]` and, per temperature, `sampler.backend[t].iteration`,
+        `.get_chain()`, `.get_log_like()`, `.get_log_prob()`, `.get_betas()`, `.accepted`.  A read-only view: the
+        arrays are pulled from the device (and gathered over the ranks) once per view."""
+        return _BackendView(self)
+
     def save_backend(self, name, discard=0):
         """Chain sink in the layout EMPEROR writes after a run (emp.py:722-762)."""
         from .postproc import save_backend
         return save_backend(self, name, discard=discard)
+
+
+class _TemperatureBackend:
+    """`sampler.backend[t]` of reddemcee as EMPEROR reads it (emp.py:749-761)."""
+
+    def __init__(self, view, t):
+        self._v, self._t = view, t
+
+    @property
+    def iteration(self):
+        return self._v.iteration
+
+    def get_chain(self):
+        return self._v._chain[self._t]          # [iteration, W, ndim]
+
+    def get_log_like(self):
+        return self._v._ll[self._t]             # [iteration, W]
+
+    def get_log_prob(self):
+        return self._v._lpost[self._t]          # tempered posterior beta*logL + logP, [iteration, W]
+
+    def get_betas(self):
+        return self._v._betas[:, self._t]       # [iteration]
+
+    @property
+    def accepted(self):
+        return self._v._accepted[self._t]       # accepted moves per walker, [W]
+
+
+class _BackendView:
+    def __init__(self, s: "PTSampler"):
+        self._chain = s.get_chain()
+        self._ll = s.get_log_like()
+        self._lpost = s.get_log_prob()
+        self._betas = s.get_betas()[:: s.thin_by]
+        self._accepted = np.rint(s.acceptance_fraction * max(s._n_steps, 1)).astype(np.int64)
+        self.iteration = self._chain.shape[1]
+        self.ntemps = s.ntemps
+        self.tsw_history_bool, self.smd_history_bool = s.tsw_history_bool, s.smd_history_bool
+        self.tsw_history = s.get_tsw()
+        self.smd_history = s.get_smd() if s.smd_history_bool else np.zeros((0, max(s.ntemps - 1, 0)))
+
+    def __getitem__(self, t):
+        if not -self.ntemps <= t < self.ntemps:
+            raise IndexError(t)
+        return _TemperatureBackend(self, t % self.ntemps)
+
+    def __len__(self):
+        return self.ntemps
 
 
 def _adapt_ladder(betas, ratios, time, adapt_tau, adapt_nu):

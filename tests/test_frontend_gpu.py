@@ -43,6 +43,39 @@ def test_simulation_autorun_finds_the_planet(tmp_path):
     assert np.isclose(eng.my_likelihood(best), np.max(ll), rtol=1e-12)
 
 
+def test_freeze_variant_stops_the_ladder_adaptation(tmp_path):
+    """run_config adaptation_batches / adaptation_nsweeps select support/endit_freeze1.scr in the reference:
+    `burnin` adaptation sweeps, sampler.select_adjustment('00'), then production sweeps on a frozen ladder."""
+    from astroemperor_b200.frontend import Simulation
+    sim = Simulation()
+    sim.read_loc = _write_star(tmp_path)
+    sim.load_data("synthstar")
+    sim.set_engine("reddemcee")
+    sim.engine_config["setup"] = [5, 64, 40, 1]
+    sim.engine_config["progress"] = False
+    sim.engine_config["adapt_tau"] = 20
+    sim.run_config.update(burnin=15, adaptation_batches=1, adaptation_nsweeps=15)
+    sim.seed = 3
+    s = sim.run(1)
+    b = s.get_betas()
+    assert b.shape == (40, 5)
+    assert np.any(b[14] != b[0])                      # the ladder moved during the adaptation phase
+    assert np.all(b[15:] == b[14])                    # and is frozen afterwards
+    assert s.get_chain().shape[1] == 40
+    # the view EMPEROR's generated save section reads (emp.py:727-761)
+    be = s.backend
+    assert be.iteration == be[0].iteration == 40 and len(be) == 5
+    assert be.tsw_history_bool and be.tsw_history.shape == (40, 4) and be.smd_history.shape == (40, 4)
+    for t in (0, 4):
+        assert np.array_equal(be[t].get_chain(), s.get_chain()[t]) and be[t].get_chain().shape == (40, 64, s.ndim)
+        assert np.array_equal(be[t].get_log_like(), s.get_log_like()[t])
+        assert np.array_equal(be[t].get_log_prob(), s.get_log_prob()[t])
+        assert np.array_equal(be[t].get_betas(), b[:, t]) and be[t].accepted.shape == (64,)
+    assert be[0].accepted.sum() == round(s.acceptance_fraction[0].sum() * 40)
+    with pytest.raises(NotImplementedError):
+        s.select_adjustment("11")
+
+
 def test_unsupported_engine_and_missing_data():
     from astroemperor_b200.frontend import Simulation
     from astroemperor_b200.modelspec import UnsupportedModelError
