@@ -291,6 +291,18 @@ def main():
         e2e_ms = float(tms.item())
     e2e_value = T * W * N * args.steps / (e2e_ms * 1e-3)
 
+    # ---------------- the likelihood callable alone, host buffers (emp_logl_batch_host) -----------------
+    # what an unmodified CPU sampler would call instead of Pool.map(my_likelihood): theta[n, ndim] in pageable
+    # host memory -> H2D -> prior + likelihood kernels -> D2H of logL, logP; n = this rank's walkers
+    th_host = samp.p.reshape(-1, ndim).cpu().numpy().copy()
+    eng.logl_batch(th_host[:64])
+    barrier()
+    tc0 = time.perf_counter()
+    for _ in range(max(args.steps // 2, 2)):
+        eng.logl_batch(th_host)
+    call_s = (time.perf_counter() - tc0) / max(args.steps // 2, 2)
+    callable_value = len(th_host) * N / call_s * world  # every rank does the same amount concurrently
+
     if rank == 0:
         clocks.stop()
     if world > 1:
@@ -339,6 +351,10 @@ def main():
            "e2e": {"value": e2e_value, "unit": "walker*temp*datapoint/s", "h2d_bytes_per_step": h2d // args.steps,
                    "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_ms / args.steps,
                    "includes": "host RNG draws, pinned staging, H2D, step, D2H of logL[T,W]"},
+           "callable_host": {"value": callable_value, "unit": "walker*temp*datapoint/s", "ms_per_call": call_s * 1e3,
+                             "n_eval_per_call": int(len(th_host)),
+                             "what": "emp_logl_batch_host on the current ensemble (all inside the prior): pageable "
+                                     "host theta -> H2D -> prior + likelihood kernels -> D2H of logL, logP"},
            "gpu_launches": launches, "burn_in_sweeps": args.burn, "roofline": roofline,
            "clocks": clocks.summary(tw0, tw1),
            "phase_ms_per_step_rank0": {k: v / args.steps for k, v in phases.items()},
