@@ -423,7 +423,7 @@ __device__ __noinline__ double kep_rv_robust(const KepConst& k, double t) {
 //      A (cos(f+w) + e cos w) with the constant folded in); the reciprocal of the denominator is one
 //      Newton step from the slope's reciprocal (they differ by ~1e-8 relative).
 // CPU emulation vs an 80-bit solution, e in [0, 0.98]: max |dE| 1.1e-15, max |dRV/A| 6e-15
-// (the oracle's own figures: 7.5e-16 and 5.2e-15) — scripts/kepler_v6_emulation.py.
+// (the oracle's own figures: 7.5e-16 and 5.2e-15) — tests/tools/kepler_grid_emulation.py.
 __device__ __forceinline__ float markley_starter_f32(float M, const KepConst& k) {
   // the starter of kepler.py with the constant factors 3 and 2 folded into per-walker constants
   const float M2 = M * M;

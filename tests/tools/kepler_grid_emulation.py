@@ -8,7 +8,7 @@ of astroemperor_b200/csrc/emp_device.cuh `kepler_grid`:
          Halley) correction, first-order rotation to sin E / 1 - cos E of the root.
 and compares E, sin E, 1-cos E and the RV term with an 80-bit Newton solution.
 
-Development aid (not a test): python scripts/kepler_v6_emulation.py
+Development aid (not a test): python tests/tools/kepler_grid_emulation.py
 """
 import numpy as np
 
@@ -110,7 +110,7 @@ def v6(Mr, e, w=None):
 
 def oracle(Mr, e):
     import os, sys
-    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
     from oracle import kepler_shim
     return kepler_shim.solve(Mr, e)
 
