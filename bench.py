@@ -80,7 +80,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -102,9 +102,10 @@ class ClockSampler:
     def summary(self, t0, t1):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, line in self.lines:
-            if not (t0 <= ts <= t1 + 0.25):
-                continue
+        inside = [(ts, line) for ts, line in self.lines if t0 <= ts <= t1 + 0.25]
+        if not inside and self.lines:  # timed region shorter than the sampling period: the nearest sample
+            inside = [min(self.lines, key=lambda tl: abs(tl[0] - 0.5 * (t0 + t1)))]
+        for ts, line in inside:
             f = [x.strip() for x in line.split(",")]
             try:
                 sm.append(float(f[0])); mx.append(float(f[1]))
