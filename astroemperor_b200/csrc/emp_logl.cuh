@@ -190,76 +190,90 @@ constexpr int kFeatMaN = 4;    // global MA of order >= 2: serial recurrence
 constexpr int kFeatPost = 8;   // StellarActivity / Sinusoid / MagneticCycle terms after the MA block
 constexpr int kNumFeat = 16;
 
-// Everything after the Keplerian sum for one group of 64 points (lane owns points 2*lane, 2*lane+1 of
-// the group): acceleration, offsets, jitter, MA recurrence, periodic terms, chi^2 and log-det.
+// Everything after the Keplerian sum for one segment of 128 points (lane owns the 4 CONSECUTIVE points
+// 4*lane .. 4*lane+3 of the segment, so that the MA recurrence needs one warp scan per 128 points):
+// acceleration, offsets, jitter, MA recurrence, activity / periodic terms, chi^2 and log-det.
 // kFull: every point of the tile is a data point (all tiles but the last one): no validity selects.
 template <int kFeat, bool kFull>
-__device__ __forceinline__ void tail64(WalkerConst& wc, const LoglParams& P, LaneAcc& A, int lane, int it, int cnt,
-                                       int64_t base, const unsigned char* tb, double2 t2, double m0, double m1,
-                                       int acc_order, int ma_order, int n_per) {
+__device__ __forceinline__ void tail128(WalkerConst& wc, const LoglParams& P, LaneAcc& A, int lane, int seg, int cnt,
+                                        int64_t base, const unsigned char* tb, const double (&t)[4], double (&m)[4],
+                                        int acc_order, int ma_order, int n_per) {
   const double2* ys = reinterpret_cast<const double2*>(tb + kTilePoints * 8);
   const double2* es = reinterpret_cast<const double2*>(tb + kTilePoints * 16);
-  const int2* is = reinterpret_cast<const int2*>(tb + kTilePoints * 24);
-  const int li = it * 32 + lane;
-  const int p0 = it * 64 + 2 * lane;
-  const bool v0 = kFull || p0 < cnt, v1 = kFull || (p0 + 1) < cnt;
+  const int4* is = reinterpret_cast<const int4*>(tb + kTilePoints * 24);
+  const int li = seg * 64 + 2 * lane;  // double2 index of the lane's first pair
+  const int p0 = seg * 128 + 4 * lane;
+  bool v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = kFull || (p0 + j) < cnt;
   if (kFeat & kFeatAcc) {
-    m0 += accel_term(wc.acc, acc_order, __dsub_rn(t2.x, P.t0));
-    m1 += accel_term(wc.acc, acc_order, __dsub_rn(t2.y, P.t0));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m[j] += accel_term(wc.acc, acc_order, __dsub_rn(t[j], P.t0));
   }
-  const int2 in2 = is[li];
-  const double2 y2 = ys[li];
-  const double2 e2 = es[li];
-  m0 += wc.gamma[in2.x];
-  m1 += wc.gamma[in2.y];
-  double d0 = v0 ? y2.x - m0 : 0.0;
-  double d1 = v1 ? y2.y - m1 : 0.0;
-  const double w0 = v0 ? e2.x + wc.jit2[in2.x] : 1.0;
-  const double w1 = v1 ? e2.y + wc.jit2[in2.y] : 1.0;
+  const int4 in4 = is[seg * 32 + lane];
+  const int in[4] = {in4.x, in4.y, in4.z, in4.w};
+  const double2 ya = ys[li], yb = ys[li + 1], ea = es[li], eb = es[li + 1];
+  const double y[4] = {ya.x, ya.y, yb.x, yb.y};
+  const double e2[4] = {ea.x, ea.y, eb.x, eb.y};
+  double d[4], w[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    m[j] += wc.gamma[in[j]];
+    d[j] = v[j] ? y[j] - m[j] : 0.0;
+    w[j] = v[j] ? e2[j] + wc.jit2[in[j]] : 1.0;
+  }
 
   if (kFeat & kFeatMa1) {
     // moav01.model: r_i = d_i - phi*exp(-|t_i - t_{i-1}|/tau) * r_{i-1}, sequential in i.
     // Evaluated as a warp scan over the affine maps r -> a*r + b (exact algebra).  The very first point
     // has no MA term (`if i > c`): its predecessor residual is the initial carry 0, so the term vanishes
-    // by itself (a0 is finite: t_prev starts at 0).
+    // by itself (a is finite: t_prev starts at 0).
     const double phi = wc.ma[0], itau = wc.ma_itau[0];
-    const double tl = __shfl_up_sync(0xffffffffu, t2.y, 1);
-    const double tp0 = (lane == 0) ? A.t_prev : tl;
-    const double x0 = -fabs(t2.x - tp0) * itau, x1 = -fabs(t2.y - t2.x) * itau;
-    double a0 = v0 ? -phi * exp_neg(x0, P.H) : 0.0;
-    double a1 = v1 ? -phi * exp_neg(x1, P.H) : 0.0;
-    // compose the lane's two maps, then inclusive scan across lanes
-    double Am = a1 * a0, Bm = fma(a1, d0, d1);
+    const double tl = __shfl_up_sync(0xffffffffu, t[3], 1);
+    double tp = (lane == 0) ? A.t_prev : tl;
+    double a[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double ex = exp_neg(-fabs(t[j] - tp) * itau, P.H);
+      a[j] = v[j] ? -phi * ex : 0.0;
+      tp = t[j];
+    }
+    // compose the lane's four maps, then inclusive scan across lanes
+    double Am = a[0], Bm = d[0];
+#pragma unroll
+    for (int j = 1; j < 4; ++j) { Bm = fma(a[j], Bm, d[j]); Am = a[j] * Am; }
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
       const double Ap = __shfl_up_sync(0xffffffffu, Am, off);
       const double Bp = __shfl_up_sync(0xffffffffu, Bm, off);
       scan_step(Am, Bm, Ap, Bp, lane, off);
     }
-    const double r_last = fma(Am, A.r_carry, Bm);  // residual at this lane's 2nd point
+    const double r_last = fma(Am, A.r_carry, Bm);  // residual at this lane's last point
     double r_prev = __shfl_up_sync(0xffffffffu, r_last, 1);
     if (lane == 0) r_prev = A.r_carry;
-    d0 = fma(a0, r_prev, d0);
-    d1 = fma(a1, d0, d1);
-    // carry to the next 64 points: last VALID point of this group
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { d[j] = fma(a[j], r_prev, d[j]); r_prev = d[j]; }
+    // carry to the next segment: last VALID point of this one
     if (kFull) {
-      A.r_carry = __shfl_sync(0xffffffffu, d1, 31);
-      A.t_prev = __shfl_sync(0xffffffffu, t2.y, 31);
+      A.r_carry = __shfl_sync(0xffffffffu, d[3], 31);
+      A.t_prev = __shfl_sync(0xffffffffu, t[3], 31);
     } else {
-      const int last_lane = min(31, (cnt - it * 64 - 1) >> 1);
-      const bool last_is_second = ((cnt - it * 64) >= 2 * (last_lane + 1));
-      A.r_carry = __shfl_sync(0xffffffffu, last_is_second ? d1 : d0, last_lane);
-      A.t_prev = __shfl_sync(0xffffffffu, last_is_second ? t2.y : t2.x, last_lane);
+      const int last = min(127, cnt - seg * 128 - 1);  // >= 0: the caller skips empty segments
+      const int lj = last & 3;
+      const double dv = lj == 0 ? d[0] : lj == 1 ? d[1] : lj == 2 ? d[2] : d[3];
+      const double tv = lj == 0 ? t[0] : lj == 1 ? t[1] : lj == 2 ? t[2] : t[3];
+      A.r_carry = __shfl_sync(0xffffffffu, dv, last >> 2);
+      A.t_prev = __shfl_sync(0xffffffffu, tv, last >> 2);
     }
   } else if (kFeat & kFeatMaN) {
-    // general order: serial recurrence over the 64 points (rare configuration), every lane runs the
+    // general order: serial recurrence over the 128 points (rare configuration), every lane runs the
     // same uniform loop on shuffled values; the warp-uniform history lives in the walker's slot
-    for (int j = 0; j < 64; ++j) {
-      const int src = j >> 1;
-      const double dj = __shfl_sync(0xffffffffu, (j & 1) ? d1 : d0, src);
-      const double tj = __shfl_sync(0xffffffffu, (j & 1) ? t2.y : t2.x, src);
-      const bool vj = (it * 64 + j) < cnt;
-      const int64_t gi = base + it * 64 + j;
+    for (int j = 0; j < 128; ++j) {
+      const int src = j >> 2, cj = j & 3;
+      const double dj = __shfl_sync(0xffffffffu, cj == 0 ? d[0] : cj == 1 ? d[1] : cj == 2 ? d[2] : d[3], src);
+      const double tj = __shfl_sync(0xffffffffu, cj == 0 ? t[0] : cj == 1 ? t[1] : cj == 2 ? t[2] : t[3], src);
+      const bool vj = (seg * 128 + j) < cnt;
+      const int64_t gi = base + seg * 128 + j;
       double r = dj;
       if (vj) {
         for (int c = 0; c < ma_order; ++c)
@@ -271,7 +285,9 @@ __device__ __forceinline__ void tail64(WalkerConst& wc, const LoglParams& P, Lan
           wc.ma_thist[0] = tj;
         }
         __syncwarp();
-        if (src == lane) { if (j & 1) d1 = r; else d0 = r; }
+        if (src == lane) {
+          if (cj == 0) d[0] = r; else if (cj == 1) d[1] = r; else if (cj == 2) d[2] = r; else d[3] = r;
+        }
       }
     }
   }
@@ -281,31 +297,38 @@ __device__ __forceinline__ void tail64(WalkerConst& wc, const LoglParams& P, Lan
   // sai00.model: model0 += theta_sa[j] * SAI{j}_ — the tile carries, per point, the columns of ITS instrument
   if (kFeat & kFeatPost) {
     for (int c = 0; c < P.sai_cols; ++c) {
-      const double2 s2 = reinterpret_cast<const double2*>(tb + kTileBytes + size_t(c) * kTilePoints * 8)[li];
-      d0 = fma(-wc.sai[in2.x * EMP_MAX_SAI + c], s2.x, d0);  // padding rows carry 0
-      d1 = fma(-wc.sai[in2.y * EMP_MAX_SAI + c], s2.y, d1);
+      const double2* sc = reinterpret_cast<const double2*>(tb + kTileBytes + size_t(c) * kTilePoints * 8);
+      const double2 sa = sc[li], sb = sc[li + 1];
+      d[0] = fma(-wc.sai[in[0] * EMP_MAX_SAI + c], sa.x, d[0]);  // padding rows carry 0
+      d[1] = fma(-wc.sai[in[1] * EMP_MAX_SAI + c], sa.y, d[1]);
+      d[2] = fma(-wc.sai[in[2] * EMP_MAX_SAI + c], sb.x, d[2]);
+      d[3] = fma(-wc.sai[in[3] * EMP_MAX_SAI + c], sb.y, d[3]);
     }
     for (int q = 0; q < n_per; ++q) {
       const PeriodicTerm& pt = wc.per[q];
-      if (v0) d0 -= periodic_value(pt, t2.x, P.H);
-      if (v1) d1 -= periodic_value(pt, t2.y, P.H);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (v[j]) d[j] -= periodic_value(pt, t[j], P.H);
     }
   }
 
   // chi^2: r0^2/w0 + r1^2/w1 over the common denominator (one reciprocal per pair);
   // log-det: sum(log err2) (00.like:5) as the log of a running product whose exponent is moved into
-  // an integer sum after every pair, so the only log() is the one after the last tile
-  const double w01 = w0 * w1;
-  A.chi = fma(fma(d0 * d0, w1, (d1 * d1) * w0), rcp_nr<2>(w01), A.chi);
-  const double pr = A.prod * w01;
+  // an integer sum after every segment, so the only log() is the one after the last tile
+  const double w01 = w[0] * w[1], w23 = w[2] * w[3];
+  A.chi = fma(fma(d[0] * d[0], w[1], (d[1] * d[1]) * w[0]), rcp_nr<2>(w01), A.chi);
+  A.chi = fma(fma(d[2] * d[2], w[3], (d[3] * d[3]) * w[2]), rcp_nr<2>(w23), A.chi);
+  const double pr = A.prod * (w01 * w23);
   const int hi = __double2hiint(pr);
   A.esum += hi >> 20;
   A.prod = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(pr));
 }
 
-// kGroups = groups of 64 points a warp works on at once: 2*kGroups independent Kepler chains per lane
+// kGroups = groups of 64 points a warp works on at once: 2*kGroups independent Kepler chains per lane (A/B
+// builds showed 2 is the sweet spot; the tail is written for exactly that: 128-point segments)
 template <int kGroups, int kFeat>
 __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglParams P) {
+  static_assert(kGroups == 2, "the tail works on 128-point segments");
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* tiles_s = smem;
   const uint32_t tile_bytes = P.tile_bytes;
@@ -361,7 +384,7 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
 
   LaneAcc A;
   A.chi = 0.0; A.prod = 1.0; A.esum = 0; A.r_carry = 0.0; A.t_prev = 0.0;
-  int n_pairs = 0;  // pairs of points folded into the running product (warp-uniform)
+  int n_pairs = 0;  // segments folded into the running product (warp-uniform)
 
   for (int i = 0; i < n_tiles; ++i) {
     const int s = i % kStages;
@@ -382,48 +405,29 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
       const int64_t base = int64_t(i) * kTilePoints;
       const int64_t rem = P.n_points - base;
       const int cnt = rem < kTilePoints ? int(rem) : kTilePoints;
-      const int iters = (cnt + 63) >> 6;
-      for (int it = 0; it < iters; it += kGroups) {
-        // (a tile always holds kTilePoints/64 full groups: padding replicates the last timestamp)
-        double2 t2[kGroups];
-        double m[2 * kGroups];
-#pragma unroll
-        for (int u = 0; u < kGroups; ++u) {
-          t2[u] = ts[(it + u) * 32 + lane];
-          m[2 * u] = 0.0;
-          m[2 * u + 1] = 0.0;
-        }
+      const int segs = (cnt + 127) >> 7;
+      for (int seg = 0; seg < segs; ++seg) {
+        // lane owns points 4*lane .. 4*lane+3 of the segment: two 128-bit reads 32 bytes apart (a 2-way bank
+        // conflict on 4 reads per segment; the tile's padding replicates the last timestamp)
+        const double2 ta = ts[seg * 64 + 2 * lane], tc = ts[seg * 64 + 2 * lane + 1];
+        const double t[4] = {ta.x, ta.y, tc.x, tc.y};
+        double m[4] = {0.0, 0.0, 0.0, 0.0};
         for (int k = 0; k < K; ++k) {
           const KepConst& kc = wc.kep[k];
           if ((kc.slow_mod | kc.robust) == 0) {  // warp-uniform
 #pragma unroll
-            for (int u = 0; u < kGroups; ++u) {  // straight-line code: the scheduler interleaves the chains
-              m[2 * u] = kep_rv_grid(kc, t2[u].x, m[2 * u], P.H, tab, tabf);
-              m[2 * u + 1] = kep_rv_grid(kc, t2[u].y, m[2 * u + 1], P.H, tab, tabf);
-            }
+            for (int j = 0; j < 4; ++j)  // straight-line code: the scheduler interleaves the four chains
+              m[j] = kep_rv_grid(kc, t[j], m[j], P.H, tab, tabf);
           } else {
 #pragma unroll
-            for (int u = 0; u < kGroups; ++u) {
-              m[2 * u] += kep_rv_robust(kc, t2[u].x);
-              m[2 * u + 1] += kep_rv_robust(kc, t2[u].y);
-            }
+            for (int j = 0; j < 4; ++j) m[j] += kep_rv_robust(kc, t[j]);
           }
         }
-        if (cnt == kTilePoints) {  // warp-uniform: every tile but the last
-#pragma unroll
-          for (int u = 0; u < kGroups; ++u)
-            tail64<kFeat, true>(wc, P, A, lane, it + u, cnt, base, tb, t2[u], m[2 * u], m[2 * u + 1], acc_order,
-                                ma_order, n_per);
-          n_pairs += kGroups;
-        } else {
-#pragma unroll
-          for (int u = 0; u < kGroups; ++u)
-            if (it + u < iters) {
-              tail64<kFeat, false>(wc, P, A, lane, it + u, cnt, base, tb, t2[u], m[2 * u], m[2 * u + 1], acc_order,
-                                   ma_order, n_per);
-              ++n_pairs;
-            }
-        }
+        if (cnt == kTilePoints)  // warp-uniform: every tile but the last
+          tail128<kFeat, true>(wc, P, A, lane, seg, cnt, base, tb, t, m, acc_order, ma_order, n_per);
+        else
+          tail128<kFeat, false>(wc, P, A, lane, seg, cnt, base, tb, t, m, acc_order, ma_order, n_per);
+        ++n_pairs;
       }
     }
     __syncwarp();
