@@ -328,14 +328,19 @@ class PTSampler:
             self.timings["draws"] += _time.perf_counter() - t0
             return d
 
-        staged = self.stage_draws(draw(), pinned=True) if nsweeps > 0 else None
+        # the draws of the first sweep may already be staged: every call ends by drawing and staging one sweep
+        # ahead (below), so that back-to-back calls — adaptation then production (support/endit_freeze1.scr),
+        # warm-up then measurement — do not pay the 5 ms pipeline fill again
+        staged, pre = None, getattr(self, "_prefetched", None)
+        self._prefetched = None
+        if nsweeps > 0:
+            staged = pre[1] if (pre is not None and pre[0] == nsteps) else self.stage_draws(draw(), pinned=True)
         for k in it:
             self.sweep_begin(staged)
-            if k + 1 < nsweeps:
-                # while the device runs this sweep the host draws the next one, packs it into the other
-                # pinned buffer and enqueues its H2D copy behind the stretch kernels (double-buffered on
-                # both sides), so nothing but the 4(T-1)-byte swap-count read sits between two sweeps
-                staged = self.stage_draws(draw(), pinned=True)
+            # while the device runs this sweep the host draws the next one, packs it into the other pinned
+            # buffer and enqueues its H2D copy behind the stretch kernels (double-buffered on both sides), so
+            # nothing but the 4(T-1)-byte swap-count read sits between two sweeps
+            staged = self.stage_draws(draw(), pinned=True)
             self.sweep_end()
             if self._chain is not None and (k % self.thin_by == 0):
                 j = self._stored
@@ -345,6 +350,8 @@ class PTSampler:
                 self._stored += 1
             if on_sweep is not None:
                 on_sweep(self, k)
+        if nsweeps > 0:
+            self._prefetched = (nsteps, staged)
         self.torch.cuda.synchronize(self.dev)
         return self.p
 
