@@ -11,9 +11,9 @@ ladder adaptation needs only the T-1 swap counts and runs on the host exactly li
 the oracle (bit-identical beta history).
 
 With `torch.distributed` initialised (one process per GPU) the temperature ladder
-is sharded in contiguous blocks of T/G temperatures (dist.py): the stretch steps
-need no communication, the swap sweep all-gathers logL over NCCL and every rank
-replays the same plan.
+is sharded over the ranks, T/G temperatures each, interleaved by default (dist.py): the
+stretch steps need no communication, the swap sweep all-gathers logL (and the swap draws
+each rank generated for its own pairs) over NCCL and every rank replays the same plan.
 """
 from __future__ import annotations
 

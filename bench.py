@@ -7,7 +7,7 @@
 Metric (BASELINE.json): logL evals/sec x datapoints = walkers x temps x datapoints / s.
 Workload (config.workload): BASELINE configs[3] — synthetic 5-planet RV, 4 instruments +
 global MA(1) noise, 10 000 points, 32 temperatures x 2048 walkers per GPU (weak scaling: N
-GPUs hold 32*N temperatures, sharded in contiguous blocks, swap sweep every step).
+GPUs hold 32*N temperatures, interleaved over the ranks, swap sweep every step).
 
 A "step" is one parallel-tempering sweep with nsteps=1: red/blue stretch move of every walker
 of every temperature (propose -> batched likelihood+prior -> accept, per half), the hot->cold
