@@ -202,7 +202,8 @@ int emp_model_host(EmpHandle *h, const double *theta_host, double *model_host, d
 
 /* kepler.solve(M, ecc) (kepler.py 0.0.7; call sites support/models/kep00.model:6 ... akep00.model:5,
  * emp_model.py:1325): eccentric anomaly E[i] of M[i], ecc[i] (or ecc[0] if ecc_is_scalar), host
- * buffers, same solver the likelihood kernel inlines. */
+ * buffers.  Runs kepler.py's own scheme (Markley starter + its single high-order refinement): the solver
+ * the likelihood kernel uses under EMP_SOLVER_KEPLERPY and for eccentricities above 0.98. */
 int emp_kepler_solve_host(const double *M, const double *ecc, int64_t n, int ecc_is_scalar, double *E,
                           int device);
 
