@@ -73,19 +73,28 @@ def _sorted_by_beta(betas, *arrs):
     return (np.asarray(betas)[order],) + tuple(np.asarray(a)[order] for a in arrs)
 
 
-def evidence_ti(logl, betas):
-    """Thermodynamic integration: logZ = int_0^1 <logL>_beta dbeta, trapezoid over the ladder
-    (logl [T, n_samples]).  Error = |full - every-other-rung| (ptemcee convention)."""
+def evidence_ti(logl, betas, pchip=False):
+    """Thermodynamic integration: logZ = int_0^1 <logL>_beta dbeta over the ladder (logl [T, n_samples]):
+    trapezoid rule, or with `pchip=True` (the option emp.py:1434-1446 passes on) the integral of the
+    monotone piecewise-cubic Hermite interpolant of <logL>(beta).  Error = |full ladder - every other
+    rung| (ptemcee convention)."""
     mean_ll = np.mean(np.reshape(logl, (len(betas), -1)), axis=1)
     b, m = _sorted_by_beta(betas, mean_ll)
     if b[0] > 0:
         b, m = np.concatenate([[0.0], b]), np.concatenate([[m[0]], m])
     trap = np.trapezoid if hasattr(np, "trapezoid") else np.trapz
-    logz = float(trap(m, b))
+
+    def integral(bb, mm):
+        if pchip and len(bb) >= 3:
+            from scipy.interpolate import PchipInterpolator
+            return float(PchipInterpolator(bb, mm).integrate(bb[0], bb[-1]))
+        return float(trap(mm, bb))
+
+    logz = integral(b, m)
     b2, m2 = b[::2], m[::2]
     if b2[-1] != b[-1]:
         b2, m2 = np.append(b2, b[-1]), np.append(m2, m[-1])
-    return logz, abs(logz - float(trap(m2, b2)))
+    return logz, abs(logz - integral(b2, m2))
 
 
 def evidence_ss(logl, betas, n_batches=8):

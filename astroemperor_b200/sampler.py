@@ -438,10 +438,10 @@ class PTSampler:
 
     # ---- post-run reductions (emp.py:1375-1385, 1432-1447; host NumPy, postproc.py) ----------
     def get_evidence_ti(self, discard=0, pchip=False):
-        """Thermodynamic-integration log-evidence: trapezoid of <logL>_beta over beta (the
-        estimator emp.py:1432-1447 falls back to; `pchip` is accepted and ignored)."""
+        """Thermodynamic-integration log-evidence: integral of <logL>_beta over beta (the estimator
+        emp.py:1432-1447 falls back to), trapezoid or, with `pchip=True`, monotone cubic interpolation."""
         from .postproc import evidence_ti
-        return evidence_ti(self.get_log_like(discard=discard), self.betas)
+        return evidence_ti(self.get_log_like(discard=discard), self.betas, pchip=pchip)
 
     def get_evidence_ss(self, discard=0):
         """Stepping-stone log-evidence with a batch-means error."""

@@ -225,3 +225,22 @@ def test_sharded_swap_exchange_two_ranks_gloo(T, W, layout):
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
     assert sum(n for _, _, n in res) > 0  # some rows really crossed the shard edge
+
+
+# ------------------------------------------------------------ post-run reductions ----
+def test_evidence_estimators_on_an_analytic_ladder():
+    """logL ~ N(mu(beta), .) with <logL>_beta = -1/(beta + 0.1): int_0^1 = -ln(11).  Trapezoid and
+    PCHIP thermodynamic integration bracket the analytic value; PCHIP is the closer one on a coarse
+    geometric ladder, and both report an error of the size of their miss."""
+    from astroemperor_b200.postproc import evidence_ti
+    rng = np.random.default_rng(0)
+    betas = 2.0 ** (-np.arange(12.0))
+    logl = np.stack([-1.0 / (b + 0.1) + 1e-3 * rng.normal(size=4000) for b in betas])
+    exact = -np.log(11.0)
+    z_tr, e_tr = evidence_ti(logl, betas)
+    z_pc, e_pc = evidence_ti(logl, betas, pchip=True)
+    assert abs(z_pc - exact) < abs(z_tr - exact) < 0.1
+    assert abs(z_pc - exact) < 0.02 and e_tr > 0 and e_pc > 0
+    # the ladder order does not matter
+    p = rng.permutation(len(betas))
+    assert np.isclose(evidence_ti(logl[p], betas[p], pchip=True)[0], z_pc)
