@@ -244,3 +244,34 @@ def test_evidence_estimators_on_an_analytic_ladder():
     # the ladder order does not matter
     p = rng.permutation(len(betas))
     assert np.isclose(evidence_ti(logl[p], betas[p], pchip=True)[0], z_pc)
+
+
+def test_integrated_autocorrelation_time_of_an_ar1_chain():
+    """emcee's estimator (what sampler.get_autocorr_time mirrors, emp.py:1375-1385) on AR(1) walkers:
+    tau = (1 + rho) / (1 - rho)."""
+    from astroemperor_b200.postproc import integrated_time
+    rng = np.random.default_rng(2)
+    n, W, rho = 20000, 16, np.array([0.5, 0.9])
+    x = np.zeros((n, W, 2))
+    eps = rng.normal(size=(n, W, 2))
+    for i in range(1, n):
+        x[i] = rho * x[i - 1] + eps[i]
+    tau = integrated_time(x, c=5, tol=50, quiet=True)
+    assert np.allclose(tau, (1 + rho) / (1 - rho), rtol=0.15), tau
+    with pytest.raises(RuntimeError):  # a chain much shorter than tol * tau is refused unless quiet
+        integrated_time(x[:200], c=5, tol=50, quiet=False)
+
+
+def test_stepping_stone_matches_thermodynamic_integration_on_gaussian_rungs():
+    """For logL | beta ~ N(m, s^2) independent of beta both estimators have closed forms:
+    TI = m, SS = sum_i [db_i m + db_i^2 s^2 / 2]."""
+    from astroemperor_b200.postproc import evidence_ss, evidence_ti
+    rng = np.random.default_rng(3)
+    betas = np.linspace(0.0, 1.0, 21)
+    m, sd = -12.0, 0.8
+    logl = m + sd * rng.normal(size=(len(betas), 20000))
+    z_ti, _ = evidence_ti(logl, betas)
+    z_ss, e_ss = evidence_ss(logl, betas)
+    db = np.diff(betas)
+    assert abs(z_ti - m) < 0.02
+    assert abs(z_ss - (m + 0.5 * sd ** 2 * np.sum(db ** 2))) < 0.02 and e_ss < 0.02
