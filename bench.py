@@ -172,6 +172,8 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-evals", type=int, default=0, help="walkers in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--solver", default="grid", choices=["grid", "kepler.py"],
+                    help="Kepler solver of the likelihood kernel (A/B; the default is the product path)")
     ap.add_argument("--burn", type=int, default=40,
                     help="untimed sweeps before the warm-up so that the ensemble has left its uniform "
                          "initial state (a young chain proposes ~40%% of its moves outside the prior box, "
@@ -200,6 +202,7 @@ def main():
     w, data, spec = build_workload(args.workload)
     T, W, N, ndim = w["T"] * world, w["W"], w["n"], spec.ndim
     eng = LikelihoodEngine(spec, data.t, data.y, data.yerr, data.flag, device=local_rank)
+    eng.set_solver(args.solver)
     samp = PTSampler(W, ndim, eng, ntemps=T, seed=2026, store="device")
     p0 = samp.initial_positions(spec) if rank == 0 else None
     if world > 1:
@@ -345,7 +348,7 @@ def main():
            "dtype": "f64", "data": "synthetic (seeded, SURVEY.md §8d row D2)",
            "config": {"workload": w["desc"], "name": args.workload, "n_points": N, "n_keplerians": w["kplan"],
                       "n_instruments": w["nins"], "ndim": ndim, "ntemps": T, "nwalkers": W,
-                      "parallelism": f"temperature ladder sharded over {world} GPU(s)",
+                      "parallelism": f"temperature ladder sharded over {world} GPU(s)", "solver": args.solver,
                       "l2": "each step's inputs (draws 2.4 MB/step + state 18 MB) differ per step; the 280 KB "
                             "data set is L2-resident by design (re-read by every CTA)"},
            "logl_evals_per_s": T * W * args.steps / (ms * 1e-3),
