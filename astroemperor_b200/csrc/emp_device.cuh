@@ -404,6 +404,23 @@ __device__ __noinline__ double kep_rv_robust(const KepConst& k, double t) {
   const HotConsts H = make_hot_consts();
   return kep_rv_checked(k, t, H);
 }
+// the same for the four points of a lane at once: the four refinements are independent chains, so the
+// out-of-line path keeps the instruction-level parallelism of the inlined one (EMP_SOLVER_KEPLERPY runs here)
+struct Quad { double v0, v1, v2, v3; };
+__device__ __noinline__ Quad kep_rv_robust4(const KepConst& k, double t0, double t1, double t2, double t3) {
+  const HotConsts H = make_hot_consts();
+  bool b0 = false, b1 = false, b2 = false, b3 = false;
+  Quad r;
+  r.v0 = kep_rv<false>(k, t0, H, b0);
+  r.v1 = kep_rv<false>(k, t1, H, b1);
+  r.v2 = kep_rv<false>(k, t2, H, b2);
+  r.v3 = kep_rv<false>(k, t3, H, b3);
+  if (b0 || k.slow_mod) r.v0 = kep_rv_cold(k, t0);  // rare: M ~ 0, non-finite FP32 starter, |M| >= 1e12
+  if (b1 || k.slow_mod) r.v1 = kep_rv_cold(k, t1);
+  if (b2 || k.slow_mod) r.v2 = kep_rv_cold(k, t2);
+  if (b3 || k.slow_mod) r.v3 = kep_rv_cold(k, t3);
+  return r;
+}
 
 // ---- grid-anchored Kepler core (likelihood kernel v6) ----------------------------------------
 // Same root as kepler.solve (Kepler's equation has ONE root), reached with

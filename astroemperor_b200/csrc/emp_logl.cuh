@@ -419,8 +419,8 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
             for (int j = 0; j < 4; ++j)  // straight-line code: the scheduler interleaves the four chains
               m[j] = kep_rv_grid(kc, t[j], m[j], P.H, tab, tabf);
           } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) m[j] += kep_rv_robust(kc, t[j]);
+            const Quad r = kep_rv_robust4(kc, t[0], t[1], t[2], t[3]);
+            m[0] += r.v0; m[1] += r.v1; m[2] += r.v2; m[3] += r.v3;
           }
         }
         if (cnt == kTilePoints)  // warp-uniform: every tile but the last
