@@ -1,0 +1,62 @@
+"""CPU check of what the compiled library contains (cuobjdump -sass on the in-tree .so): the likelihood
+kernels are sm_100a code that stages its data with bulk TMA + mbarriers, computes in FP64 with MUFU-seeded
+reciprocals, keeps nothing in local memory in the hot kernels and uses no tensor-core instruction
+(this path is not a contraction)."""
+import re
+import shutil
+import subprocess
+
+import pytest
+
+
+@pytest.fixture(scope="module")
+def sass(built_lib):
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    try:
+        out = subprocess.run([exe, "-sass", built_lib], capture_output=True, text=True, timeout=300)
+    except FileNotFoundError:
+        pytest.skip("cuobjdump not available")
+    assert out.returncode == 0, out.stderr[-500:]
+    funcs, name = {}, None
+    for line in out.stdout.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            funcs[name] = []
+        elif name and "/*" in line:
+            funcs[name].append(line)
+    assert "sm_100a" in out.stdout or "EF_CUDA_SM100" in out.stdout or "sm_100" in out.stdout
+    return funcs
+
+
+def _ops(lines):
+    ops = []
+    for l in lines:
+        m = re.match(r"\s*/\*[0-9a-f]+\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", l)
+        if m:
+            ops.append(m.group(1))
+    return ops
+
+
+def test_likelihood_kernels_are_tma_fp64_and_register_resident(sass):
+    logl = {k: v for k, v in sass.items() if "logl_rv_kernel" in k}
+    assert len(logl) == 12  # one instantiation per model-feature mask (emp_logl.cuh)
+    for name, lines in logl.items():
+        ops = _ops(lines)
+        joined = " ".join(ops)
+        assert any(o.startswith("UBLKCP") for o in ops), f"{name}: no bulk-TMA copy"
+        assert "SYNCS.ARRIVE.TRANS64" in joined and "SYNCS.PHASECHK.TRANS64.TRYWAIT" in joined, name
+        assert ops.count("DFMA") > 150 and "MUFU.RCP64H" in ops and "MUFU.LG2" in ops and "MUFU.EX2" in ops, name
+        assert not any(o.startswith(("HMMA", "IMMA", "DMMA", "UTCHMMA", "UTCQMMA", "UTCMMA")) for o in ops), name
+        # local memory only in the out-of-line libm slow paths, never in the kernel's own loops:
+        # every LDL/STL sits behind a CALL target, i.e. after the kernel's EXIT
+        first_exit = next(i for i, o in enumerate(ops) if o == "EXIT")
+        assert not any(o.startswith(("LDL", "STL")) for o in ops[:first_exit]), name
+
+
+def test_every_kernel_of_the_path_is_present(sass):
+    names = " ".join(sass)
+    for k in ("prior_compact_kernel", "pt_propose_kernel", "pt_accept_kernel", "pt_swap_plan_smem_kernel",
+              "pt_gather_rows_kernel", "am_logl_kernel", "model_rv_kernel", "kepler_solve_kernel",
+              "kepler_grid_kernel", "fp64_peak_kernel"):
+        assert k in names, k
