@@ -205,6 +205,16 @@ def _dist_worker(rank, world, port, T, W, C, seed, layout, q):
         st, sw = sg // W, sg % W
         pos = sh.owner_of_temp(st) * (sh.n_local * W) + sh.local_of_temp(st) * W + sw
         ok = ok and np.array_equal(allr[pos].numpy().reshape(sh.n_local, W, C), p[sh.local_slice])
+        # sharded swap draws: each rank draws the pair rows of its own temperatures (per-pair streams);
+        # the all-gather restores the ladder order and equals what a single process draws
+        from astroemperor_b200.draws import DrawStreams, draw_sweep
+        full = draw_sweep(DrawStreams(seed, T), W, 4, 1)
+        mine = draw_sweep(DrawStreams(seed, T), W, 4, 1, temps=sh.local_slice, swap_rows=range(T)[sh.local_slice])
+        assert mine.perm.shape == (sh.n_local, 2, W) and mine.zz.shape[1] == sh.n_local
+        gp = sh.all_gather_rows(torch.from_numpy(mine.perm))[: T - 1].numpy()
+        gu = sh.all_gather_rows(torch.from_numpy(mine.lnu_swap))[: T - 1].numpy()
+        ok = ok and np.array_equal(gp, full.perm) and np.array_equal(gu, full.lnu_swap)
+        ok = ok and np.array_equal(mine.zz, full.zz[:, sh.local_slice])
         q.put((rank, ok, n_remote))
     finally:
         td.destroy_process_group()
