@@ -443,16 +443,16 @@ class PTSampler:
         from .postproc import evidence_ti
         return evidence_ti(self.get_log_like(discard=discard), self.betas, pchip=pchip)
 
-    def get_evidence_ss(self, discard=0):
+    def get_evidence_ss(self, discard=0, pchip=False):
         """Stepping-stone log-evidence with a batch-means error."""
         from .postproc import evidence_ss
         return evidence_ss(self.get_log_like(discard=discard), self.betas)
 
-    def get_evidence_hybrid(self, discard=0):
+    def get_evidence_hybrid(self, discard=0, pchip=False):
         """reddemcee's 'hybrid' estimator is not recoverable offline: this returns the
         stepping-stone value with the TI/SS discrepancy added in quadrature to its error."""
         z_ss, e_ss = self.get_evidence_ss(discard=discard)
-        z_ti, e_ti = self.get_evidence_ti(discard=discard)
+        z_ti, e_ti = self.get_evidence_ti(discard=discard, pchip=pchip)
         err = float(np.sqrt(np.nan_to_num(e_ss) ** 2 + (z_ss - z_ti) ** 2))
         return z_ss, err
 
