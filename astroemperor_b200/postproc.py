@@ -163,3 +163,114 @@ def save_backend(sampler, name, discard=0):
             g.create_dataset("beta_history", data=betas[:, t])
             g.create_dataset("accepted", data=accepted[t])
     return name + ".h5"
+
+
+# ---- reading a stored run back (the parent's `_load_sampler_reddemcee`, emp.py:777-807) ----------
+class StoredRun:
+    """A run written by `save_backend`, read back with the getters the reference's parent process calls on
+    the re-created sampler (emp.py:961-965, 1375-1447, 1977-1989): `get_chain / get_log_like / get_log_prob
+    (discard=, thin=, flat=)`, `betas`, `get_betas`, `get_tsw`, `get_smd`, `acceptance_fraction`, the evidence
+    and autocorrelation reductions and the `backend[t]` view.  No device is needed: post-processing of a GPU run
+    can happen anywhere."""
+
+    def __init__(self, chain, log_like, log_prob, beta_history, accepted, tsw_history, smd_history, n_steps=None):
+        self._chain = np.asarray(chain)               # [T, n, W, ndim]
+        self._ll = np.asarray(log_like)               # [T, n, W]
+        self._lpost = np.asarray(log_prob)            # [T, n, W]
+        self._betas = np.asarray(beta_history)        # [n, T]
+        self._accepted = np.asarray(accepted)         # [T, W]
+        self._tsw = np.asarray(tsw_history)
+        self._smd = np.asarray(smd_history)
+        self.ntemps, self.iteration, self.nwalkers, self.ndim = self._chain.shape
+        self._n_steps = n_steps if n_steps is not None else self.iteration
+        self.betas = self._betas[-1].copy() if len(self._betas) else None
+        self.tsw_history_bool, self.smd_history_bool = self._tsw.size > 0, self._smd.size > 0
+
+    @staticmethod
+    def _view(x, discard, thin, flat):
+        x = x[:, discard::thin]
+        return x.reshape((x.shape[0], x.shape[1] * x.shape[2]) + x.shape[3:]) if flat else x
+
+    def get_chain(self, discard=0, thin=1, flat=False):
+        return self._view(self._chain, discard, thin, flat)
+
+    def get_log_like(self, discard=0, thin=1, flat=False):
+        return self._view(self._ll, discard, thin, flat)
+
+    def get_log_prob(self, discard=0, thin=1, flat=False):
+        return self._view(self._lpost, discard, thin, flat)
+
+    def get_betas(self, discard=0):
+        return self._betas[discard:]
+
+    def get_tsw(self, discard=0):
+        return self._tsw[discard:]
+
+    def get_smd(self, discard=0):
+        return self._smd[discard:]
+
+    @property
+    def acceptance_fraction(self):
+        return self._accepted / max(self._n_steps, 1)
+
+    def get_evidence_ti(self, discard=0, pchip=False):
+        return evidence_ti(self.get_log_like(discard=discard), self.betas, pchip=pchip)
+
+    def get_evidence_ss(self, discard=0, pchip=False):
+        return evidence_ss(self.get_log_like(discard=discard), self.betas)
+
+    def get_autocorr_time(self, discard=0, thin=1, quiet=False, tol=50, c=5):
+        ch = self.get_chain(discard=discard, thin=thin)
+        return np.array([thin * integrated_time(ch[t], c=c, tol=tol, quiet=quiet) for t in range(ch.shape[0])])
+
+    @property
+    def backend(self):
+        return _StoredBackend(self)
+
+
+class _StoredBackend:
+    def __init__(self, run):
+        self._r = run
+        self.iteration = run.iteration
+        self.tsw_history_bool, self.smd_history_bool = run.tsw_history_bool, run.smd_history_bool
+        self.tsw_history, self.smd_history = run._tsw, run._smd
+
+    def __len__(self):
+        return self._r.ntemps
+
+    def __getitem__(self, t):
+        r = self._r
+        if not -r.ntemps <= t < r.ntemps:
+            raise IndexError(t)
+        t %= r.ntemps
+
+        class _T:
+            iteration = r.iteration
+            accepted = r._accepted[t]
+            get_chain = staticmethod(lambda: r._chain[t])
+            get_log_like = staticmethod(lambda: r._ll[t])
+            get_log_prob = staticmethod(lambda: r._lpost[t])
+            get_betas = staticmethod(lambda: r._betas[:, t])
+        return _T()
+
+
+def load_backend(name) -> StoredRun:
+    """Read what `save_backend(sampler, name)` wrote: `<name>.npz`, or `<name>.h5` + `<name>_<t>.h5` where h5py
+    is installed (the reference's PTHDFBackend / HDFBackend_plus file layout, emp.py:781-785)."""
+    import os
+    if os.path.exists(name + ".npz"):
+        z = np.load(name + ".npz")
+        return StoredRun(z["chain"], z["log_like"], z["log_prob"], z["beta_history"], z["accepted"],
+                         z["tsw_history"], z["smd_history"])
+    import h5py
+    with h5py.File(name + ".h5", "r") as f:
+        g = f["mcmc"]
+        T = int(g.attrs["ntemps"])
+        tsw, smd = g["tsw_history"][...], g["smd_history"][...]
+    parts = []
+    for t in range(T):
+        with h5py.File(f"{name}_{t}.h5", "r") as f:
+            g = f["mcmc"]
+            parts.append([g[k][...] for k in ("chain", "log_like", "log_prob", "beta_history", "accepted")])
+    ch, ll, lpost, bh, acc = (np.stack([p[i] for p in parts]) for i in range(5))
+    return StoredRun(ch, ll, lpost, bh.T, acc, tsw, smd)

@@ -285,3 +285,46 @@ def test_stepping_stone_matches_thermodynamic_integration_on_gaussian_rungs():
     db = np.diff(betas)
     assert abs(z_ti - m) < 0.02
     assert abs(z_ss - (m + 0.5 * sd ** 2 * np.sum(db ** 2))) < 0.02 and e_ss < 0.02
+
+
+def test_backend_round_trip_without_a_device(tmp_path):
+    """save_backend -> load_backend: the stored run answers the parent's read-back calls (emp.py:777-807,
+    1375-1447) from disk.  The sampler is stubbed: only its getters are used."""
+    from astroemperor_b200.postproc import load_backend, save_backend
+    rng = np.random.default_rng(4)
+    T, n, W, nd = 3, 40, 8, 2
+    betas = np.array([1.0, 0.4, 0.1])
+
+    class Stub:
+        _n_steps = n
+        acceptance_fraction = rng.uniform(0.1, 0.5, (T, W))
+
+        def __init__(self):
+            self.chain = rng.normal(size=(T, n, W, nd))
+            self.ll = -np.abs(rng.normal(size=(T, n, W))) * 3
+            self.lpost = self.ll * betas[:, None, None] - 1.0
+            self.bh = np.tile(betas, (n, 1))
+            self.tsw, self.smd = rng.uniform(size=(n, T - 1)), rng.uniform(size=(n, T - 1))
+
+        def get_chain(self, discard=0): return self.chain[:, discard:]
+        def get_log_like(self, discard=0): return self.ll[:, discard:]
+        def get_log_prob(self, discard=0): return self.lpost[:, discard:]
+        def get_betas(self, discard=0): return self.bh[discard:]
+        def get_tsw(self, discard=0): return self.tsw[discard:]
+        def get_smd(self, discard=0): return self.smd[discard:]
+
+    s = Stub()
+    path = save_backend(s, str(tmp_path / "run"))
+    assert os.path.exists(path)
+    r = load_backend(str(tmp_path / "run"))
+    assert (r.ntemps, r.iteration, r.nwalkers, r.ndim) == (T, n, W, nd)
+    assert np.array_equal(r.get_chain(), s.chain) and np.array_equal(r.betas, betas)
+    assert r.get_chain(discard=10, thin=3, flat=True).shape == (T, 10 * W, nd)
+    assert np.array_equal(r.get_log_like(flat=True)[1], s.ll[1].reshape(-1))
+    assert np.allclose(r.acceptance_fraction, s.acceptance_fraction)
+    be = r.backend
+    assert be.iteration == n and len(be) == T and np.array_equal(be[2].get_chain(), s.chain[2])
+    assert np.array_equal(be[-1].get_betas(), s.bh[:, 2]) and be[0].accepted.shape == (W,)
+    z, e = r.get_evidence_ti(discard=5)
+    assert np.isfinite(z) and np.isfinite(r.get_evidence_ss()[0])
+    assert r.get_autocorr_time(quiet=True).shape == (T, nd)
