@@ -37,9 +37,27 @@ class EmpAmDataC(ctypes.Structure):
                 ("inv_cov", _P), ("log_det_cov", _P), ("astro_gost", _P), ("catalogs", _P)]
 
 
-# every symbol include/emperor_b200.h declares: (name, restype, argtypes)
 _P = ctypes.c_void_p
 _I32, _I64 = ctypes.c_int32, ctypes.c_int64
+EMP_MAX_PEERS = 16
+
+
+class EmpPtSweepC(ctypes.Structure):
+    """EmpPtSweep of include/emperor_b200.h (layout checked against gcc in tests/test_abi.py)."""
+    _fields_ = [("T_loc", _I32), ("W", _I32), ("nsteps", _I32), ("T_all", _I32), ("n_ranks", _I32), ("rank", _I32),
+                ("strided", _I32), ("use_graph", _I32),
+                ("p", _P), ("logl", _P), ("logp", _P), ("p_alt", _P), ("logl_alt", _P), ("logp_alt", _P),
+                ("betas", _P), ("half_idx", _P), ("zz", _P), ("rint", _P), ("factors", _P), ("lnu", _P),
+                ("perm", _P), ("lnu_swap", _P), ("accepted", _P), ("n_accepted", _P), ("src", _P), ("n_acc", _P),
+                ("adapt", _I32), ("thin", _I32), ("adapt_tau", ctypes.c_double), ("adapt_nu", ctypes.c_double),
+                ("sweep_counter", _P), ("step_counter", _P), ("beta_hist", _P), ("nacc_hist", _P), ("smd_hist", _P),
+                ("hist_cap", _I64), ("D", _P), ("chain", _P), ("chain_ll", _P), ("chain_lp", _P),
+                ("store_cap", _I64), ("store_ring", _I32), ("_pad", _I32),
+                ("peer_p", _P * EMP_MAX_PEERS), ("peer_logl", _P * EMP_MAX_PEERS), ("peer_logp", _P * EMP_MAX_PEERS),
+                ("logl_all", _P)]
+
+
+# every symbol include/emperor_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("emp_create", ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _P, ctypes.c_int, ctypes.POINTER(_P)]),
     ("emp_destroy", ctypes.c_int, [_P]),
@@ -58,7 +76,16 @@ SYMBOLS = [
     ("emp_pt_swap_plan", ctypes.c_int, [_P, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     ("emp_pt_gather_rows", ctypes.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P]),
     ("emp_nan_count", ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint32)]),
+    ("emp_pt_sweep", ctypes.c_int, [_P, ctypes.POINTER(EmpPtSweepC)]),
+    ("emp_pt_sweep_stretch", ctypes.c_int, [_P, ctypes.POINTER(EmpPtSweepC)]),
+    ("emp_pt_sweep_swap", ctypes.c_int, [_P, ctypes.POINTER(EmpPtSweepC)]),
+    ("emp_dev_alloc", ctypes.c_int, [ctypes.c_int, _I64, ctypes.POINTER(_P)]),
+    ("emp_dev_free", ctypes.c_int, [ctypes.c_int, _P]),
+    ("emp_ipc_export", ctypes.c_int, [ctypes.c_int, _P, ctypes.c_char_p]),
+    ("emp_ipc_open", ctypes.c_int, [ctypes.c_int, ctypes.c_char_p, ctypes.POINTER(_P)]),
+    ("emp_ipc_close", ctypes.c_int, [ctypes.c_int, _P]),
     ("emp_launch_count", ctypes.c_int, [_P, ctypes.POINTER(_I64)]),
+    ("emp_graph_captures", ctypes.c_int, [_P, ctypes.POINTER(_I64)]),
     ("emp_set_solver", ctypes.c_int, [_P, ctypes.c_int]),
     ("emp_set_timing", ctypes.c_int, [_P, ctypes.c_int]),
     ("emp_timing_collect", ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_I64)]),

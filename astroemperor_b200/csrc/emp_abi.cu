@@ -11,8 +11,8 @@
 
 #include "../../include/emperor_b200.h"
 #include "emp_device.cuh"
-#include "emp_logl.cuh"
 #include "emp_pt.cuh"
+#include "emp_logl.cuh"
 #include "emp_am.cuh"
 
 using namespace emp;
@@ -34,6 +34,15 @@ static int fail(int code, const std::string& msg) {
     if (_e != cudaSuccess)                                                                  \
       return fail(EMP_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));           \
   } while (0)
+
+constexpr size_t kPlanSmemMax = 196 * 1024;  // dynamic shared memory of the swap-plan kernel (+ 24 KB static)
+constexpr int kGraphCache = 8;
+
+struct GraphEntry {
+  EmpPtSweep key;
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches = 0;
+};
 
 struct EmpHandle {
   int device = 0;
@@ -67,6 +76,16 @@ struct EmpHandle {
   int64_t cap_llwork = 0;
   int32_t* d_index = nullptr;  // compact list of evaluations inside the prior support
   int32_t* d_nact = nullptr;   // its length
+  int32_t* d_nact2 = nullptr;  // PT step: one counter per half (the likelihood kernel of one half re-zeroes the other)
+  bool plan_attr_set = false;
+  double* d_smd_part = nullptr;      // swap-mean-distance partial sums of the plan application
+  uint32_t* d_smd_ticket = nullptr;
+  int64_t cap_smd = 0;
+  double *d_model = nullptr, *d_err2 = nullptr;  // emp_model_host scratch
+  GraphEntry graphs[kGraphCache];    // captured sweeps (emp_pt_sweep, use_graph)
+  int graph_next = 0;
+  int64_t graph_captures = 0;
+  cudaStream_t cap_stream = nullptr;
   int64_t cap_index = 0;
   uint32_t* d_nan = nullptr;          // [0] NaN proposals
   unsigned long long* d_cnt = nullptr; // [0] proposals, [1] proposals inside the prior support, [2] accepted
@@ -222,7 +241,7 @@ extern "C" int emp_create(const EmpModelDesc* desc, const double* t, const doubl
   CUDA_TRY(cudaSetDevice(device));
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10)
+  if (prop.major != 10)  // the fatbin holds sm_100a code only: an sm_90 or sm_120 part cannot run it
     return fail(EMP_ENODEV, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
                                 std::to_string(prop.minor) + "; this library is built for sm_100a only");
 
@@ -312,6 +331,10 @@ extern "C" int emp_destroy(EmpHandle* h) {
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
   cudaFree(h->d_desc); cudaFree(h->d_theta); cudaFree(h->d_ll); cudaFree(h->d_lp);
   cudaFree(h->d_q); cudaFree(h->d_llq); cudaFree(h->d_lpq); cudaFree(h->d_llwork); cudaFree(h->d_nan);
+  cudaFree(h->d_nact2); cudaFree(h->d_smd_part); cudaFree(h->d_smd_ticket); cudaFree(h->d_model); cudaFree(h->d_err2);
+  for (GraphEntry& g : h->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   am_free(&h->am);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -343,6 +366,56 @@ extern "C" int emp_synchronize(EmpHandle* h) {
   return EMP_OK;
 }
 
+static LoglParams base_logl_params(EmpHandle* h) {
+  LoglParams P;
+  P.desc = h->d_desc;
+  P.tiles = h->d_tiles;
+  P.n_points = h->n;
+  P.n_tiles = h->n_tiles;
+  P.theta = nullptr;
+  P.eval_index = nullptr;
+  P.n_active = nullptr;
+  P.logl = nullptr;
+  P.t0 = h->t0;
+  P.ll_const = h->ll_const;
+  P.t_absmax = h->t_absmax;
+  P.grid_sc = h->d_grid_sc;
+  P.grid_scf = h->d_grid_scf;
+  P.tile_bytes = h->tile_bytes;
+  P.sai_cols = h->sai_cols;
+  P.solver = h->solver;
+  P.zero_counter = nullptr;
+  P.pt = PtAccept();
+  P.pt.enabled = 0;
+  P.H = make_hot_consts();
+  return P;
+}
+
+// the likelihood kernel over the compact list (n_eval = upper bound of its length), optionally bracketed by
+// timing events
+static int launch_logl_kernel(EmpHandle* h, const LoglParams& P, int64_t n_eval, cudaStream_t st) {
+  if (n_eval > 2147483647LL - kWalkerWarps) return fail(EMP_EINVAL, "n_eval too large for one launch");
+  const unsigned grid = unsigned((n_eval + kWalkerWarps - 1) / kWalkerWarps);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->timing) {
+    if (h->tev_used + 2 > h->tev.size()) {
+      for (int k = 0; k < 2; ++k) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        h->tev.push_back(e);
+      }
+    }
+    e0 = h->tev[h->tev_used];
+    e1 = h->tev[h->tev_used + 1];
+    h->tev_used += 2;
+    CUDA_TRY(cudaEventRecord(e0, st));
+  }
+  h->logl_kernel<<<grid, kLoglThreads, logl_smem_bytes(h->tile_bytes), st>>>(P);
+  if (h->timing) CUDA_TRY(cudaEventRecord(e1, st));
+  h->launches += 1;
+  return EMP_OK;
+}
+
 static int launch_logl(EmpHandle* h, const double* theta_dev, int64_t n_eval, double* logl_dev,
                        double* logp_dev) {
   if (n_eval == 0) return EMP_OK;
@@ -362,46 +435,17 @@ static int launch_logl(EmpHandle* h, const double* theta_dev, int64_t n_eval, do
   prior_compact_kernel<<<grid_p, kPriorWarps * 32, 0, h->stream>>>(h->d_desc, theta_dev, n_eval, logl_dev, logp_dev,
                                                                  h->d_index, h->d_nact);
   h->launches += 1;
-  LoglParams P;
-  P.desc = h->d_desc;
-  P.tiles = h->d_tiles;
-  P.n_points = h->n;
-  P.n_tiles = h->n_tiles;
+  LoglParams P = base_logl_params(h);
   P.theta = theta_dev;
   P.eval_index = h->d_index;
   P.n_active = h->d_nact;
   P.logl = logl_dev;
-  P.t0 = h->t0;
-  P.ll_const = h->ll_const;
-  P.t_absmax = h->t_absmax;
-  P.grid_sc = h->d_grid_sc;
-  P.grid_scf = h->d_grid_scf;
-  P.tile_bytes = h->tile_bytes;
-  P.sai_cols = h->sai_cols;
-  P.solver = h->solver;
-  P.H = make_hot_consts();
-  const unsigned grid = unsigned((n_eval + kWalkerWarps - 1) / kWalkerWarps);
-  cudaEvent_t e0 = h->ev0, e1 = h->ev1;
-  if (h->timing) {
-    if (h->tev_used + 2 > h->tev.size()) {
-      for (int k = 0; k < 2; ++k) {
-        cudaEvent_t e;
-        CUDA_TRY(cudaEventCreate(&e));
-        h->tev.push_back(e);
-      }
-    }
-    e0 = h->tev[h->tev_used];
-    e1 = h->tev[h->tev_used + 1];
-    h->tev_used += 2;
-    CUDA_TRY(cudaEventRecord(e0, h->stream));
-  }
-  h->logl_kernel<<<grid, kLoglThreads, logl_smem_bytes(h->tile_bytes), h->stream>>>(P);
-  if (h->timing) CUDA_TRY(cudaEventRecord(e1, h->stream));
-  h->launches += 1;
+  int rc = launch_logl_kernel(h, P, n_eval, h->stream);
+  if (rc) return rc;
   CUDA_TRY(cudaGetLastError());
   if (h->desc.am_enabled) {
-    int rc = am_launch(&h->am, h->d_desc, theta_dev, n_eval, h->d_index, h->d_nact, logl_dev, h->stream,
-                       &h->launches);
+    rc = am_launch(&h->am, h->d_desc, theta_dev, n_eval, h->d_index, h->d_nact, logl_dev, h->stream,
+                   &h->launches, nullptr);
     if (rc) return rc;
   }
   return EMP_OK;
@@ -450,9 +494,9 @@ extern "C" int emp_model_host(EmpHandle* h, const double* theta_host, double* mo
   CUDA_TRY(cudaSetDevice(h->device));
   int rc = ensure_eval_scratch(h, 1);
   if (rc) return rc;
-  double *d_model = nullptr, *d_err2 = nullptr;
-  CUDA_TRY(cudaMalloc(&d_model, h->n * sizeof(double)));
-  CUDA_TRY(cudaMalloc(&d_err2, h->n * sizeof(double)));
+  if (!h->d_model) CUDA_TRY(cudaMalloc(&h->d_model, h->n * sizeof(double)));
+  if (!h->d_err2) CUDA_TRY(cudaMalloc(&h->d_err2, h->n * sizeof(double)));
+  double *d_model = h->d_model, *d_err2 = h->d_err2;
   CUDA_TRY(cudaMemcpyAsync(h->d_theta, theta_host, h->desc.ndim_free * sizeof(double), cudaMemcpyHostToDevice,
                            h->stream));
   int blocks = int((h->n + 255) / 256);
@@ -474,8 +518,6 @@ extern "C" int emp_model_host(EmpHandle* h, const double* theta_host, double* mo
   if (e == cudaSuccess) e = cudaMemcpyAsync(model_host, d_model, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(err2_host, d_err2, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  cudaFree(d_model);
-  cudaFree(d_err2);
   if (e != cudaSuccess) return fail(EMP_ECUDA, cudaGetErrorString(e));
   return EMP_OK;
 }
@@ -483,6 +525,17 @@ extern "C" int emp_model_host(EmpHandle* h, const double* theta_host, double* mo
 // ---- parallel tempering ------------------------------------------------------------------
 
 static int ensure_q_scratch(EmpHandle* h, int64_t n_prop) {
+  if (!h->d_nact2) {
+    CUDA_TRY(cudaMalloc(&h->d_nact2, 2 * sizeof(int32_t)));
+    CUDA_TRY(cudaMemset(h->d_nact2, 0, 2 * sizeof(int32_t)));
+  }
+  if (n_prop > h->cap_index) {
+    cudaFree(h->d_index);
+    h->d_index = nullptr;
+    h->cap_index = 0;
+    CUDA_TRY(cudaMalloc(&h->d_index, size_t(n_prop) * sizeof(int32_t)));
+    h->cap_index = n_prop;
+  }
   if (n_prop <= h->cap_q) return EMP_OK;
   cudaFree(h->d_q); cudaFree(h->d_llq); cudaFree(h->d_lpq);
   h->d_q = h->d_llq = h->d_lpq = nullptr;
@@ -494,6 +547,72 @@ static int ensure_q_scratch(EmpHandle* h, int64_t n_prop) {
   return EMP_OK;
 }
 
+// what one stretch step needs (a view of EmpPtSweep for step `s`, or of emp_pt_stretch_step's arguments)
+struct StretchArgs {
+  int32_t T, W;
+  double *p, *logl, *logp;
+  const double* betas;
+  int32_t beta_off, beta_stride;
+  const int32_t* half_idx;
+  const double* zz;
+  const int32_t* rint;
+  const double* factors;
+  const double* lnu;
+  uint8_t* accepted;
+  int32_t* n_accepted;
+  long long* step_counter;
+};
+
+// One red/blue stretch step: per half a proposal + prior kernel and the likelihood kernel(s) with the
+// Metropolis accept in the epilogue.  Everything it touches was allocated by ensure_q_scratch (capturable).
+static int enqueue_stretch_step(EmpHandle* h, const StretchArgs& a, cudaStream_t st) {
+  const int32_t H = a.W / 2;
+  const int64_t n_prop = int64_t(a.T) * H;
+  for (int split = 0; split < 2; ++split) {
+    PtPropose pp;
+    pp.desc = h->d_desc;
+    pp.p = a.p; pp.T = a.T; pp.W = a.W; pp.split = split;
+    pp.half_idx = a.half_idx; pp.zz = a.zz; pp.rint = a.rint;
+    pp.q = h->d_q; pp.lpq = h->d_lpq;
+    pp.eval_index = h->d_index;
+    pp.n_active = h->d_nact2 + split;
+    pp.accepted = a.accepted;
+    pp.cnt = h->d_cnt;
+    pp.step_counter = a.step_counter;
+    const unsigned grid_p = unsigned((n_prop + kProposeWarps - 1) / kProposeWarps);
+    pt_propose_prior_kernel<<<grid_p, kProposeWarps * 32, 0, st>>>(pp);
+    h->launches += 1;
+
+    PtAccept pa;
+    pa.enabled = 1;
+    pa.T = a.T; pa.W = a.W; pa.split = split;
+    pa.p = a.p; pa.logl = a.logl; pa.logp = a.logp;
+    pa.q = h->d_q; pa.lpq = h->d_lpq;
+    pa.half_idx = a.half_idx;
+    pa.betas = a.betas; pa.beta_off = a.beta_off; pa.beta_stride = a.beta_stride;
+    pa.factors = a.factors; pa.lnu = a.lnu;
+    pa.accepted = a.accepted; pa.n_accepted = a.n_accepted;
+    pa.cnt = h->d_cnt; pa.n_nan = h->d_nan;
+
+    LoglParams P = base_logl_params(h);
+    P.theta = h->d_q;
+    P.eval_index = h->d_index;
+    P.n_active = h->d_nact2 + split;
+    P.zero_counter = h->d_nact2 + (1 - split);
+    P.logl = h->d_llq;  // only written when the accept is left to the astrometric kernel
+    P.pt = pa;
+    if (h->desc.am_enabled) P.pt.enabled = 0;
+    int rc = launch_logl_kernel(h, P, n_prop, st);
+    if (rc) return rc;
+    if (h->desc.am_enabled) {
+      rc = am_launch(&h->am, h->d_desc, h->d_q, n_prop, h->d_index, h->d_nact2 + split, h->d_llq, st, &h->launches,
+                     &pa);
+      if (rc) return rc;
+    }
+  }
+  return EMP_OK;
+}
+
 extern "C" int emp_pt_stretch_step(EmpHandle* h, int32_t T, int32_t W, double* p, double* logl, double* logp,
                                    const double* betas, const int32_t* half_idx, const double* zz,
                                    const int32_t* rint, const double* factors, const double* lnu,
@@ -501,58 +620,76 @@ extern "C" int emp_pt_stretch_step(EmpHandle* h, int32_t T, int32_t W, double* p
   if (!h || !p || !logl || !logp || !betas || !half_idx || !zz || !rint || !factors || !lnu || !accepted)
     return fail(EMP_EINVAL, "NULL argument");
   if (T < 1 || W < 2 || (W & 1)) return fail(EMP_EINVAL, "need T >= 1 and an even number of walkers");
+  if (h->desc.n_sai > 0 && !h->sai_attached)
+    return fail(EMP_EINVAL, "the model has a StellarActivityBlock: call emp_attach_sai first");
   CUDA_TRY(cudaSetDevice(h->device));
-  const int32_t ndim = h->desc.ndim_free;
-  const int32_t H = W / 2;
-  const int64_t n_prop = int64_t(T) * H;
-  int rc = ensure_q_scratch(h, n_prop);
+  int rc = ensure_q_scratch(h, int64_t(T) * (W / 2));
   if (rc) return rc;
-  const int threads = 256;
-  const int64_t max_blocks = int64_t(h->num_sms) * 8;
-  for (int split = 0; split < 2; ++split) {
-    int64_t total = n_prop * ndim;
-    int blocks = int(std::min<int64_t>((total + threads - 1) / threads, max_blocks));
-    pt_propose_kernel<<<blocks, threads, 0, h->stream>>>(p, T, W, ndim, split, half_idx, zz, rint, h->d_q);
-    h->launches += 1;
-    rc = launch_logl(h, h->d_q, n_prop, h->d_llq, h->d_lpq);
-    if (rc) return rc;
-    blocks = int(std::min<int64_t>((n_prop * 32 + threads - 1) / threads, max_blocks));
-    pt_accept_kernel<<<blocks, threads, 0, h->stream>>>(p, logl, logp, T, W, ndim, split, half_idx, betas, factors,
-                                                        lnu, h->d_q, h->d_llq, h->d_lpq, accepted, h->d_nan, h->d_cnt);
-    h->launches += 1;
-  }
+  StretchArgs a = {T, W, p, logl, logp, betas, 0, 1, half_idx, zz, rint, factors, lnu, accepted, nullptr, nullptr};
+  rc = enqueue_stretch_step(h, a, h->stream);
+  if (rc) return rc;
   CUDA_TRY(cudaGetLastError());
+  return EMP_OK;
+}
+
+static int enqueue_plan(EmpHandle* h, const PtPlan& A, cudaStream_t st) {
+  const int32_t W = A.W;
+  const size_t smem3 = size_t(W) * 36, smem2 = size_t(W) * 24;
+  using PlanKernel = void (*)(const PtPlan);
+  PlanKernel k = nullptr;
+  size_t smem = 0;
+  if (smem3 <= kPlanSmemMax) {
+    k = W <= 1024 ? pt_swap_plan_kernel<1, 3> : W <= 2048 ? pt_swap_plan_kernel<2, 3>
+      : W <= 4096 ? pt_swap_plan_kernel<4, 3> : pt_swap_plan_kernel<6, 3>;
+    smem = smem3;
+  } else if (smem2 <= kPlanSmemMax && W <= 8192) {
+    k = pt_swap_plan_kernel<8, 2>;
+    smem = smem2;
+  }
+  if (k) {
+    k<<<1, 1024, smem, st>>>(A);
+  } else {
+    pt_swap_plan_global_kernel<<<1, 1024, 0, st>>>(A, h->d_llwork);
+  }
+  h->launches += 1;
+  return EMP_OK;
+}
+
+static int ensure_plan_scratch(EmpHandle* h, int32_t W) {
+  if (!h->plan_attr_set) {  // once per handle, not per call
+    const void* ks[] = {(const void*)pt_swap_plan_kernel<1, 3>, (const void*)pt_swap_plan_kernel<2, 3>,
+                        (const void*)pt_swap_plan_kernel<4, 3>, (const void*)pt_swap_plan_kernel<6, 3>,
+                        (const void*)pt_swap_plan_kernel<8, 2>};
+    for (const void* k : ks)
+      CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kPlanSmemMax)));
+    h->plan_attr_set = true;
+  }
+  if (size_t(W) * 24 > kPlanSmemMax || W > 8192) {
+    if (2 * int64_t(W) > h->cap_llwork) {
+      cudaFree(h->d_llwork);
+      h->d_llwork = nullptr;
+      h->cap_llwork = 0;
+      CUDA_TRY(cudaMalloc(&h->d_llwork, 2 * size_t(W) * sizeof(double)));
+      h->cap_llwork = 2 * int64_t(W);
+    }
+  }
   return EMP_OK;
 }
 
 extern "C" int emp_pt_swap_plan(EmpHandle* h, int32_t T, int32_t W, const double* logl_all, const double* betas,
                                 const int32_t* perm, const double* lnu, int32_t* src, int32_t* n_acc) {
   if (!h || !logl_all || !betas || !src || !n_acc) return fail(EMP_EINVAL, "NULL argument");
-  if (T < 1 || W < 1) return fail(EMP_EINVAL, "bad T/W");
+  if (T < 1 || W < 1 || T > kPlanMaxT) return fail(EMP_EINVAL, "bad T/W (T <= 2048)");
   if (T > 1 && (!perm || !lnu)) return fail(EMP_EINVAL, "NULL draws");
   CUDA_TRY(cudaSetDevice(h->device));
-  const size_t plan_smem = size_t(W) * 24;
-  if (plan_smem <= 200 * 1024 && W <= 8192) {
-    using PlanKernel = void (*)(int32_t, int32_t, const double*, const double*, const int32_t*, const double*, int32_t*,
-                                int32_t*);
-    const PlanKernel k = W <= 1024 ? pt_swap_plan_smem_kernel<1>
-                       : W <= 2048 ? pt_swap_plan_smem_kernel<2>
-                       : W <= 4096 ? pt_swap_plan_smem_kernel<4> : pt_swap_plan_smem_kernel<8>;
-    CUDA_TRY(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    k<<<1, 1024, plan_smem, h->stream>>>(T, W, logl_all, betas, perm, lnu, src, n_acc);
-    h->launches += 1;
-    CUDA_TRY(cudaGetLastError());
-    return EMP_OK;
-  }
-  if (2 * int64_t(W) > h->cap_llwork) {
-    cudaFree(h->d_llwork);
-    h->d_llwork = nullptr;
-    h->cap_llwork = 0;
-    CUDA_TRY(cudaMalloc(&h->d_llwork, 2 * size_t(W) * sizeof(double)));
-    h->cap_llwork = 2 * int64_t(W);
-  }
-  pt_swap_plan_kernel<<<1, 1024, 0, h->stream>>>(T, W, logl_all, betas, perm, lnu, src, n_acc, h->d_llwork);
-  h->launches += 1;
+  int rc = ensure_plan_scratch(h, W);
+  if (rc) return rc;
+  PtPlan A = {};
+  A.T = T; A.W = W; A.logl = logl_all; A.betas = const_cast<double*>(betas); A.perm = perm; A.lnu = lnu;
+  A.src = src; A.n_acc = n_acc;
+  A.adapt = 0; A.adapt_tau = 1.0; A.adapt_nu = 1.0;
+  rc = enqueue_plan(h, A, h->stream);
+  if (rc) return rc;
   CUDA_TRY(cudaGetLastError());
   return EMP_OK;
 }
@@ -573,6 +710,241 @@ extern "C" int emp_pt_gather_rows(EmpHandle* h, int64_t n_rows, int32_t ndim, co
   return EMP_OK;
 }
 
+// ---- whole sweeps ------------------------------------------------------------------------------------------
+static int validate_sweep(EmpHandle* h, const EmpPtSweep* s, bool need_swap) {
+  if (!h || !s) return fail(EMP_EINVAL, "NULL argument");
+  if (s->T_loc < 1 || s->W < 2 || (s->W & 1) || s->nsteps < 0) return fail(EMP_EINVAL, "bad T_loc / W / nsteps");
+  if (s->n_ranks < 1 || s->n_ranks > EMP_MAX_PEERS || s->rank < 0 || s->rank >= s->n_ranks)
+    return fail(EMP_EINVAL, "bad n_ranks / rank");
+  if (s->T_all != s->T_loc * s->n_ranks) return fail(EMP_EINVAL, "T_all != T_loc * n_ranks");
+  if (s->T_all > kPlanMaxT) return fail(EMP_EINVAL, "ladder longer than 2048 temperatures");
+  if (!s->p || !s->logl || !s->logp || !s->betas || !s->accepted) return fail(EMP_EINVAL, "NULL state");
+  if (s->nsteps > 0 && (!s->half_idx || !s->zz || !s->rint || !s->factors || !s->lnu))
+    return fail(EMP_EINVAL, "NULL stretch draws");
+  if (s->thin < 1) return fail(EMP_EINVAL, "thin must be >= 1");
+  if (need_swap && s->T_all > 1) {
+    if (!s->perm || !s->lnu_swap || !s->src || !s->n_acc || !s->p_alt || !s->logl_alt || !s->logp_alt)
+      return fail(EMP_EINVAL, "NULL swap draws / plan / alternate buffers");
+    if (s->n_ranks > 1) {
+      if (!s->logl_all) return fail(EMP_EINVAL, "sharded ladder: logl_all is NULL");
+      for (int r = 0; r < s->n_ranks; ++r)
+        if (!s->peer_p[r] || !s->peer_logl[r] || !s->peer_logp[r]) return fail(EMP_EINVAL, "NULL peer buffer");
+    }
+  }
+  if (h->desc.n_sai > 0 && !h->sai_attached)
+    return fail(EMP_EINVAL, "the model has a StellarActivityBlock: call emp_attach_sai first");
+  return EMP_OK;
+}
+
+static int ensure_apply_scratch(EmpHandle* h, const EmpPtSweep* s) {
+  const int nb = (s->W + kApplyRows - 1) / kApplyRows;
+  const int64_t need = int64_t(s->T_loc) * nb * 2;
+  if (need > h->cap_smd) {
+    cudaFree(h->d_smd_part); cudaFree(h->d_smd_ticket);
+    h->d_smd_part = nullptr; h->d_smd_ticket = nullptr; h->cap_smd = 0;
+    CUDA_TRY(cudaMalloc(&h->d_smd_part, size_t(need) * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->d_smd_ticket, size_t(s->T_loc) * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemset(h->d_smd_ticket, 0, size_t(s->T_loc) * sizeof(uint32_t)));
+    h->cap_smd = need;
+  }
+  return EMP_OK;
+}
+
+static void fill_apply(EmpHandle* h, const EmpPtSweep* s, bool with_plan, PtApply& A) {
+  A = PtApply();
+  A.T_loc = s->T_loc; A.W = s->W; A.ndim = h->desc.ndim_free;
+  A.T_all = s->T_all; A.G = s->n_ranks; A.rank = s->rank; A.strided = s->strided;
+  A.src = with_plan ? s->src : nullptr;
+  for (int r = 0; r < kMaxPeers; ++r) { A.p_in[r] = nullptr; A.ll_in[r] = nullptr; A.lp_in[r] = nullptr; }
+  if (s->n_ranks > 1 && with_plan) {
+    for (int r = 0; r < s->n_ranks; ++r) { A.p_in[r] = s->peer_p[r]; A.ll_in[r] = s->peer_logl[r]; A.lp_in[r] = s->peer_logp[r]; }
+  }
+  A.p_in[s->rank] = s->p; A.ll_in[s->rank] = s->logl; A.lp_in[s->rank] = s->logp;
+  A.p_out = with_plan ? s->p_alt : nullptr;
+  A.ll_out = with_plan ? s->logl_alt : nullptr;
+  A.lp_out = with_plan ? s->logp_alt : nullptr;
+  const bool smd = with_plan && s->D && s->smd_hist;
+  A.D = smd ? s->D : nullptr;
+  A.smd_part = h->d_smd_part; A.smd_ticket = h->d_smd_ticket;
+  A.smd_hist = smd ? s->smd_hist : nullptr;
+  A.sweep_counter = (const long long*)s->sweep_counter;
+  A.hist_cap = s->hist_cap;
+  A.chain = s->chain; A.ch_ll = s->chain_ll; A.ch_lp = s->chain_lp;
+  A.step_counter = (const long long*)s->step_counter;
+  A.store_cap = s->store_cap; A.store_ring = s->store_ring; A.thin = s->thin;
+}
+
+static int enqueue_apply(EmpHandle* h, const PtApply& A, cudaStream_t st) {
+  const dim3 grid((A.W + kApplyRows - 1) / kApplyRows, A.T_loc);
+  pt_apply_plan_kernel<<<grid, kApplyWarps * 32, 0, st>>>(A);
+  h->launches += 1;
+  return EMP_OK;
+}
+
+static int enqueue_stretch_phase(EmpHandle* h, const EmpPtSweep* s, bool swap_follows, cudaStream_t st) {
+  const int64_t per_step = int64_t(s->T_loc) * 2 * (s->W / 2);
+  for (int k = 0; k < s->nsteps; ++k) {
+    StretchArgs a;
+    a.T = s->T_loc; a.W = s->W; a.p = s->p; a.logl = s->logl; a.logp = s->logp;
+    a.betas = s->betas;
+    a.beta_off = s->strided ? s->rank : s->rank * s->T_loc;
+    a.beta_stride = s->strided ? s->n_ranks : 1;
+    a.half_idx = s->half_idx + k * per_step; a.zz = s->zz + k * per_step; a.rint = s->rint + k * per_step;
+    a.factors = s->factors + k * per_step; a.lnu = s->lnu + k * per_step;
+    a.accepted = s->accepted; a.n_accepted = s->n_accepted;
+    a.step_counter = (long long*)s->step_counter;
+    int rc = enqueue_stretch_step(h, a, st);
+    if (rc) return rc;
+    // every stretch step is a stored sample (reddemcee: nsweeps*nsteps samples per run); the last one of a
+    // sweep is stored after the swap by the plan application
+    const bool last = (k == s->nsteps - 1);
+    if (s->chain && (!last || !swap_follows)) {
+      PtApply A;
+      fill_apply(h, s, false, A);
+      rc = enqueue_apply(h, A, st);
+      if (rc) return rc;
+    }
+  }
+  return EMP_OK;
+}
+
+static int enqueue_swap_phase(EmpHandle* h, const EmpPtSweep* s, cudaStream_t st) {
+  PtPlan P = {};
+  P.T = s->T_all; P.W = s->W;
+  P.logl = (s->n_ranks > 1) ? s->logl_all : s->logl;
+  P.betas = s->betas; P.perm = s->perm; P.lnu = s->lnu_swap; P.src = s->src; P.n_acc = s->n_acc;
+  P.adapt = s->adapt; P.adapt_tau = s->adapt_tau; P.adapt_nu = s->adapt_nu;
+  P.sweep_counter = (long long*)s->sweep_counter;
+  P.beta_hist = s->beta_hist; P.nacc_hist = s->nacc_hist; P.hist_cap = s->hist_cap;
+  int rc = enqueue_plan(h, P, st);
+  if (rc) return rc;
+  PtApply A;
+  fill_apply(h, s, true, A);
+  return enqueue_apply(h, A, st);
+}
+
+static int enqueue_sweep(EmpHandle* h, const EmpPtSweep* s, cudaStream_t st) {
+  const bool swap = s->T_all > 1;
+  int rc = enqueue_stretch_phase(h, s, swap, st);
+  if (rc) return rc;
+  if (swap) return enqueue_swap_phase(h, s, st);
+  // a single temperature: no swap sweep, but the sweep counter and the beta history still advance
+  PtPlan P = {};
+  P.T = 1; P.W = s->W; P.logl = s->logl; P.betas = s->betas;
+  P.sweep_counter = (long long*)s->sweep_counter;
+  P.beta_hist = s->beta_hist; P.hist_cap = s->hist_cap;
+  return enqueue_plan(h, P, st);
+}
+
+static int prepare_sweep(EmpHandle* h, const EmpPtSweep* s, bool need_swap) {
+  int rc = validate_sweep(h, s, need_swap);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  rc = ensure_q_scratch(h, int64_t(s->T_loc) * (s->W / 2));
+  if (rc) return rc;
+  rc = ensure_plan_scratch(h, s->W);
+  if (rc) return rc;
+  return ensure_apply_scratch(h, s);
+}
+
+extern "C" int emp_pt_sweep(EmpHandle* h, const EmpPtSweep* s) {
+  int rc = prepare_sweep(h, s, true);
+  if (rc) return rc;
+  if (s->n_ranks != 1) return fail(EMP_EINVAL, "emp_pt_sweep is the single-GPU sweep; use emp_pt_sweep_stretch/_swap");
+  if (!s->use_graph || h->timing) {
+    rc = enqueue_sweep(h, s, h->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaGetLastError());
+    return EMP_OK;
+  }
+  // CUDA graph: the sweep is captured once per distinct argument block (the caller alternates between two: the
+  // state and the draw staging are double-buffered) on a private stream, then replayed on the handle's stream
+  GraphEntry* hit = nullptr;
+  for (GraphEntry& g : h->graphs)
+    if (g.exec && memcmp(&g.key, s, sizeof(EmpPtSweep)) == 0) { hit = &g; break; }
+  if (!hit) {
+    if (!h->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    const int64_t l0 = h->launches;
+    CUDA_TRY(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    rc = enqueue_sweep(h, s, h->cap_stream);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
+    const int64_t n_launch = h->launches - l0;
+    h->launches = l0;
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(EMP_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(EMP_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    GraphEntry& slot = h->graphs[h->graph_next];
+    h->graph_next = (h->graph_next + 1) % kGraphCache;
+    if (slot.exec) cudaGraphExecDestroy(slot.exec);
+    slot.key = *s;
+    slot.exec = exec;
+    slot.launches = n_launch;
+    hit = &slot;
+    h->graph_captures += 1;
+  }
+  CUDA_TRY(cudaGraphLaunch(hit->exec, h->stream));
+  h->launches += hit->launches;
+  return EMP_OK;
+}
+
+extern "C" int emp_pt_sweep_stretch(EmpHandle* h, const EmpPtSweep* s) {
+  int rc = prepare_sweep(h, s, false);
+  if (rc) return rc;
+  rc = enqueue_stretch_phase(h, s, s->T_all > 1, h->stream);
+  if (rc) return rc;
+  CUDA_TRY(cudaGetLastError());
+  return EMP_OK;
+}
+
+extern "C" int emp_pt_sweep_swap(EmpHandle* h, const EmpPtSweep* s) {
+  int rc = prepare_sweep(h, s, true);
+  if (rc) return rc;
+  if (s->T_all < 2) return EMP_OK;
+  rc = enqueue_swap_phase(h, s, h->stream);
+  if (rc) return rc;
+  CUDA_TRY(cudaGetLastError());
+  return EMP_OK;
+}
+
+// ---- shareable device memory (CUDA IPC) -------------------------------------------------------------------
+extern "C" int emp_dev_alloc(int device, int64_t bytes, void** ptr) {
+  if (!ptr || bytes < 1) return fail(EMP_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaMalloc(ptr, size_t(bytes)));
+  return EMP_OK;
+}
+extern "C" int emp_dev_free(int device, void* ptr) {
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaFree(ptr));
+  return EMP_OK;
+}
+extern "C" int emp_ipc_export(int device, void* ptr, unsigned char handle64[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  if (!ptr || !handle64) return fail(EMP_EINVAL, "NULL argument");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaIpcMemHandle_t hd;
+  CUDA_TRY(cudaIpcGetMemHandle(&hd, ptr));
+  memcpy(handle64, &hd, 64);
+  return EMP_OK;
+}
+extern "C" int emp_ipc_open(int device, const unsigned char handle64[64], void** ptr) {
+  if (!ptr || !handle64) return fail(EMP_EINVAL, "NULL argument");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle64, 64);
+  CUDA_TRY(cudaIpcOpenMemHandle(ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+  return EMP_OK;
+}
+extern "C" int emp_ipc_close(int device, void* ptr) {
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+  return EMP_OK;
+}
+
 extern "C" int emp_nan_count(EmpHandle* h, uint32_t* count) {
   if (!h || !count) return fail(EMP_EINVAL, "NULL argument");
   CUDA_TRY(cudaSetDevice(h->device));
@@ -585,6 +957,12 @@ extern "C" int emp_nan_count(EmpHandle* h, uint32_t* count) {
 extern "C" int emp_launch_count(EmpHandle* h, int64_t* count) {
   if (!h || !count) return fail(EMP_EINVAL, "NULL argument");
   *count = h->launches;
+  return EMP_OK;
+}
+
+extern "C" int emp_graph_captures(EmpHandle* h, int64_t* count) {
+  if (!h || !count) return fail(EMP_EINVAL, "NULL argument");
+  *count = h->graph_captures;
   return EMP_OK;
 }
 

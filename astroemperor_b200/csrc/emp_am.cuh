@@ -24,6 +24,7 @@
 #include <vector>
 #include "../../include/emperor_b200.h"
 #include "emp_device.cuh"
+#include "emp_pt.cuh"
 
 static int fail(int code, const std::string& msg);
 
@@ -72,6 +73,7 @@ struct AmParams {
   double cat_ref[7];  // GDR3 row (AM_catalogs_[-1]); [1:] = AM_catalogs_obs_ref
   double t_ref_h;     // AM_catalogs_times_refed[0]
   HotConsts H;
+  PtAccept pt;        // PT step: Metropolis accept once the joint RV + AM likelihood is known (emp_pt.cuh)
 };
 
 struct AmPlanet {
@@ -280,8 +282,10 @@ __global__ void __launch_bounds__(kAmWarps * 32) am_logl_kernel(const AmParams P
       quad /= JG2;
       ll += -0.5 * (quad + 5.0 * ljg + P.log_det_cov[c + 1] + 5.0 * kLog2Pi);
     }
-    P.logl[slot] += ll;  // a00.like:8  ll1 + ll2
+    ll = P.logl[slot] + ll;  // a00.like:8  ll1 + ll2
+    if (!P.pt.enabled) P.logl[slot] = ll;
   }
+  if (P.pt.enabled) pt_accept_row(P.pt, d->ndim_free, slot, __shfl_sync(0xffffffffu, ll, 0), lane);
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -352,7 +356,7 @@ inline void am_free(AmDevice* d) {
 // adds loglike_AM to logl for every row of the compact list (built by prior_compact_kernel)
 inline int am_launch(AmDevice* d, const EmpModelDesc* d_desc, const double* theta_dev, int64_t n_eval,
                      const int32_t* eval_index, const int32_t* n_active, double* logl_dev, cudaStream_t stream,
-                     int64_t* launches) {
+                     int64_t* launches, const PtAccept* accept) {
   if (!d->enabled) return fail(EMP_EINVAL, "astrometry data not uploaded");
   AmParams P;
   P.desc = d_desc; P.theta = theta_dev; P.eval_index = eval_index; P.n_active = n_active; P.logl = logl_dev;
@@ -369,6 +373,9 @@ inline int am_launch(AmDevice* d, const EmpModelDesc* d_desc, const double* thet
   memcpy(P.cat_ref, d->catalogs[2], sizeof(P.cat_ref));
   P.t_ref_h = d->times_refed[0];
   P.H = make_hot_consts();
+  P.pt = PtAccept();
+  P.pt.enabled = 0;
+  if (accept) P.pt = *accept;
   const unsigned grid = unsigned((n_eval + kAmWarps - 1) / kAmWarps);
   am_logl_kernel<<<grid, kAmWarps * 32, 0, stream>>>(P);
   *launches += 1;

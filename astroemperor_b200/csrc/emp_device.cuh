@@ -6,13 +6,16 @@
 // Here (B200-first, FP64 CUDA cores, no tensor cores — this is not a contraction):
 //   * M is formed with the reference's two roundings and reduced mod 2pi EXACTLY
 //     (rint + one FMA), so the solver sees bit-identical input to NumPy's fmod path;
-//   * same Markley starter and same single high-order refinement as kepler.py
-//     (oracle/kepler_oracle.c), evaluated with FMAs;
-//   * sin E / (1 - cos E) of the refined E are obtained from the refinement's own
-//     series by a 4th-order rotation (|dE| <= 5e-4), and the RV term is evaluated as
-//       A (cos(f+w) + e cos w) = [a1 (1-e - (1-cos E)) + a2 sin E] / (1 - e cos E) + a3
-//     with a1 = A cos w, a2 = -A sin w sqrt(1-e^2), a3 = A e cos w per walker —
-//     algebraically identical to the tan/atan/cos chain, ~3x fewer FP64 instructions.
+//   * default solver (EMP_SOLVER_GRID): the grid-anchored core below (kep_grid_a / kep_grid_c) —
+//     FP32 starter, sin/cos of the nearest grid point E_h = k 2^-7 from a shared-memory table, one FP32
+//     Halley step in delta-space, one FP64 Newton correction.  Same root as kepler.solve to ~1 ulp
+//     (Kepler's equation has one root), ~half the FP64 instructions of kepler.py's refinement;
+//   * EMP_SOLVER_KEPLERPY and eccentricities above kGridEccMax: the Markley starter and the single
+//     high-order refinement of kepler.py (oracle/kepler_oracle.c), `kepler_refined`, evaluated with FMAs;
+//   * the RV term is evaluated as [b1 cos E + a2 sin E] / (1 - e cos E), b1 = A cos w (1 - e^2),
+//     a2 = -A sin w sqrt(1 - e^2): algebraically identical to the template's tan/atan/cos chain.
+// Element-wise parity of both solvers: tests/test_kepler_gpu.py; SASS evidence: tests/test_sass_evidence.py
+// and profiles/r02_logl_sass.txt.
 #pragma once
 #include <stdint.h>
 #include "../../include/emperor_b200.h"
@@ -36,7 +39,7 @@ constexpr double kGridEccMax = 0.98;  // beyond it the walker/planet takes the k
 
 // Hot-loop FP64 literals travel in the KERNEL PARAMETER bank (c[0x0]) so that DFMA/DADD take them
 // as a direct constant operand: a 64-bit immediate costs two UMOVs per use and a user
-// __constant__ array (bank 3) costs an LDC per use (profiles/r01_sass_notes.md).
+// __constant__ array (bank 3) costs an LDC per use (profiles/r02_logl_sass.txt shows the c[0x0][..] operands).
 //   (v - sin v)/v^3 = 1/3! - w/5! + w^2/7! - ...   (8 terms: next term < 1e-18 relative on [0, pi/4])
 //   (1 - cos v)/v^2 = 1/2! - w/4! + w^2/6! - ...   (9 terms), both stored highest degree first
 struct HotConsts {
@@ -266,7 +269,7 @@ __device__ __noinline__ double markley_starter_f64(double Mr, double e, double o
 
 // Same starter in FP32 on the FMA/MUFU pipes (they issue in the slots the half-rate FP64 pipe
 // leaves free).  The starter is only an initial guess with an intrinsic error of ~4e-4; its
-// FP32 rounding (1e-7) changes the refined root by < 1e-18 (tests/test_kepler_device.py).
+// FP32 rounding (1e-7) changes the refined root by < 1e-18 (tests/test_kepler_gpu.py).
 __device__ __forceinline__ double markley_starter(double Mr, const KepConst& k, bool& bad) {
   const float M = __double2float_rn(Mr);
   const float M2 = M * M;
@@ -620,6 +623,38 @@ __device__ inline double prior_program(const EmpPriorOp* ops, int n_ops, const d
     }
   }
   return lp;
+}
+
+// The same program evaluated by a whole warp: every lane evaluates the priors of the ops it owns (they are
+// independent), lane 0 adds them in program order.  The reference's early `return lp` at the end of a block
+// whose running sum is -inf is the `break` below (values behind it are never added), so the result is
+// bit-identical to prior_program.  vals: EMP_MAX_PRIOR_OPS doubles of shared scratch owned by the warp.
+__device__ __forceinline__ double prior_program_warp(const EmpModelDesc* __restrict__ d, const double* th,
+                                                     double* vals, int lane) {
+  const int n_ops = d->n_prior_ops;
+  for (int k = lane; k < n_ops; k += 32) {
+    const EmpPriorOp& op = d->prior_ops[k];
+    double v = 0.0;
+    if (op.op == EMP_POP_PARAM) {
+      v = prior_value(op, th[op.i0]);
+    } else if (op.op == EMP_POP_SUMSQ) {
+      const double a = th[op.i0], b = th[op.i1];
+      v = prior_value(op, __dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)));
+    }
+    vals[k] = v;
+  }
+  __syncwarp();
+  double lp = 0.0;
+  if (lane == 0) {
+    for (int k = 0; k < n_ops; ++k) {
+      if (d->prior_ops[k].op == EMP_POP_CHECK) {
+        if (lp == -INFINITY) break;
+      } else {
+        lp = __dadd_rn(lp, vals[k]);
+      }
+    }
+  }
+  return __shfl_sync(0xffffffffu, lp, 0);
 }
 
 // ---- small helpers -----------------------------------------------------------------------

@@ -18,6 +18,7 @@
 //      fixed order: results are bit-reproducible run to run and independent of the slot.
 #pragma once
 #include "emp_device.cuh"
+#include "emp_pt.cuh"
 
 namespace emp {
 
@@ -59,6 +60,8 @@ struct LoglParams {
   uint32_t tile_bytes;        // kTileBytes + sai_cols * kTilePoints * 8 (activity columns follow the instrument ids)
   int32_t sai_cols;           // activity columns per point (max over the instruments), 0 = none
   int32_t solver;             // EMP_SOLVER_GRID (default) | EMP_SOLVER_KEPLERPY: every planet takes kep_rv_robust
+  int32_t* zero_counter;      // PT step: the compact-list counter of the OTHER half, zeroed here for its next use
+  PtAccept pt;                // PT step: Metropolis accept in the epilogue (pt.enabled), emp_pt.cuh
   HotConsts H;                // FP64 literals of the hot loop, read as c[0x0][..] operands
 };
 
@@ -138,18 +141,34 @@ prior_compact_kernel(const EmpModelDesc* __restrict__ d, const double* __restric
                      double* __restrict__ logl, double* __restrict__ logp, int32_t* __restrict__ eval_index,
                      int32_t* __restrict__ n_active) {
   __shared__ double th_s[kPriorWarps][EMP_MAX_DIM];
+  __shared__ double val_s[kPriorWarps][EMP_MAX_PRIOR_OPS];
+  __shared__ int s_flag[kPriorWarps];
+  __shared__ int s_base;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t e = int64_t(blockIdx.x) * kPriorWarps + warp;
-  if (e >= n_eval) return;
-  load_full_theta(d, theta + e * d->ndim_free, th_s[warp], lane);
-  if (lane == 0) {
-    const double lp = prior_program(d->prior_ops, d->n_prior_ops, th_s[warp]);
-    logp[e] = lp;
-    if (lp == -INFINITY) {
-      logl[e] = -INFINITY;
-    } else {
-      eval_index[atomicAdd(n_active, 1)] = int32_t(e);
+  bool inside = false;
+  if (e < n_eval) {
+    load_full_theta(d, theta + e * d->ndim_free, th_s[warp], lane);
+    const double lp = prior_program_warp(d, th_s[warp], val_s[warp], lane);
+    inside = !(lp == -INFINITY);
+    if (lane == 0) {
+      logp[e] = lp;
+      if (!inside) logl[e] = -INFINITY;
     }
+  }
+  // rows inside the prior support are appended to the compact list: one atomic per CTA
+  if (lane == 0) s_flag[warp] = inside ? 1 : 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int k = 0; k < kPriorWarps; ++k) n += s_flag[k];
+    s_base = n ? atomicAdd(n_active, n) : 0;
+  }
+  __syncthreads();
+  if (inside && lane == 0) {
+    int r = 0;
+    for (int k = 0; k < warp; ++k) r += s_flag[k];
+    eval_index[s_base + r] = int32_t(e);
   }
 }
 
@@ -340,6 +359,7 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
 
   const int n_active = *P.n_active;
   const int first = blockIdx.x * kWalkerWarps;
+  if (P.zero_counter && blockIdx.x == 0 && threadIdx.x == 0) *P.zero_counter = 0;
   if (first >= n_active) return;  // whole CTA beyond the compact list
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -436,8 +456,10 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
 
   if (active) {
     const double lsum = fma(double(A.esum - 1023 * n_pairs), 0.693147180559945309417, log(A.prod));
-    const double tot = warp_sum(A.chi + lsum);
-    if (lane == 0) P.logl[slot] = fma(-0.5, tot, P.ll_const);
+    const double tot = warp_sum(A.chi + lsum);  // xor butterfly: every lane holds the same sum
+    const double ll = fma(-0.5, tot, P.ll_const);
+    if (P.pt.enabled) pt_accept_row(P.pt, d->ndim_free, slot, ll, lane);  // slot = proposal index of the half
+    else if (lane == 0) P.logl[slot] = ll;
   }
 }
 

@@ -1,4 +1,4 @@
-// emp_pt.cuh — parallel-tempering step kernels.
+// emp_pt.cuh — parallel-tempering step kernels (§8f row N1).
 //
 // The sampler arithmetic of the reference lives in reddemcee / emcee 3.1.6 (not vendored);
 // semantics restated in oracle/pt_oracle.py.  All random numbers are host-supplied so that
@@ -7,115 +7,396 @@
 //   accept        : factors + (beta*ll' + lp') - (beta*ll + lp) > ln u   (emcee RedBlueMove.propose,
 //                   tempered as in ptemcee/reddemcee)
 //   swap (i,i-1)  : (beta_{i-1} - beta_i) * (ll_i[perm_i] - ll_{i-1}[perm_{i-1}]) > ln u, hot -> cold
+//   ladder        : Vousden, Farr & Mandel (2016) dynamics with reddemcee's adapt_tau / adapt_nu
 // Every floating-point expression below uses explicit single-rounding intrinsics (no FMA
 // contraction) so that, given identical log-likelihoods, the decisions are bit-identical to
 // the NumPy oracle.
+//
+// A sweep with nsteps = 1 is SIX launches (round 1: 13 + torch glue + a host synchronisation):
+//   per half-ensemble  pt_propose_prior_kernel   proposal + prior program + compaction
+//                      logl_rv_kernel            likelihood + Metropolis accept in its epilogue
+//   per sweep          pt_swap_plan_kernel       hot->cold swap plan + ladder adaptation + histories
+//                      pt_apply_plan_kernel      row gather (local or peer HBM over NVLink) + swap mean
+//                                                distance + chain store
 #pragma once
 #include <stdint.h>
+#include "emp_device.cuh"
 
 namespace emp {
 
-// Proposal for one half of every temperature: q[t, j, :] for j in [0, H)
-//   half_idx [T, 2, H]: walkers of split 0 / split 1 in ascending order
-//   zz, rint [T, 2, H]: draws of the walkers of split s, in that order
-__global__ void pt_propose_kernel(const double* __restrict__ p, int32_t T, int32_t W, int32_t ndim,
-                                  int32_t split, const int32_t* __restrict__ half_idx,
-                                  const double* __restrict__ zz, const int32_t* __restrict__ rint,
-                                  double* __restrict__ q) {
-  const int32_t H = W / 2;
-  const int64_t total = int64_t(T) * H * ndim;
-  for (int64_t g = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; g < total;
-       g += int64_t(gridDim.x) * blockDim.x) {
-    const int32_t dd = int32_t(g % ndim);
-    const int64_t tj = g / ndim;
-    const int32_t j = int32_t(tj % H), t = int32_t(tj / H);
-    const int64_t o = (int64_t(t) * 2 + split) * H + j;
-    const int32_t i = half_idx[o];
-    const int32_t partner = half_idx[(int64_t(t) * 2 + (1 - split)) * H + rint[o]];
-    const double s = p[(int64_t(t) * W + i) * ndim + dd];
-    const double c = p[(int64_t(t) * W + partner) * ndim + dd];
-    // c[rint] - (c[rint] - s) * zz[:, None]
-    q[g] = __dsub_rn(c, __dmul_rn(__dsub_rn(c, s), zz[o]));
-  }
-}
+constexpr int kMaxPeers = 16;  // GPUs a ladder can be sharded over (one NVSwitch domain)
 
-// Metropolis accept for one half; updates p / logl / logp in place.
-__global__ void pt_accept_kernel(double* __restrict__ p, double* __restrict__ logl, double* __restrict__ logp,
-                                 int32_t T, int32_t W, int32_t ndim, int32_t split,
-                                 const int32_t* __restrict__ half_idx, const double* __restrict__ betas,
-                                 const double* __restrict__ factors, const double* __restrict__ lnu,
-                                 const double* __restrict__ q, const double* __restrict__ llq,
-                                 const double* __restrict__ lpq, uint8_t* __restrict__ accepted,
-                                 uint32_t* __restrict__ n_nan, unsigned long long* __restrict__ cnt) {
-  const int32_t H = W / 2;
-  const int64_t total = int64_t(T) * H;
-  // one warp per proposal so the coordinate copy is coalesced
-  const int lane = threadIdx.x & 31;
-  const int64_t warp_global = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
-  const int64_t n_warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
-  for (int64_t tj = warp_global; tj < total; tj += n_warps) {
-    const int32_t j = int32_t(tj % H), t = int32_t(tj / H);
-    const int64_t o = (int64_t(t) * 2 + split) * H + j;
-    const int32_t i = half_idx[o];
-    const int64_t w = int64_t(t) * W + i;
-    const double beta = betas[t];
-    const double ll_new = llq[tj], lp_new = lpq[tj];
-    const double ll_old = logl[w], lp_old = logp[w];
-    // lnpdiff = f + (beta*ll' + lp') - (beta*ll + lp)
-    const double post_new = __dadd_rn(__dmul_rn(beta, ll_new), lp_new);
-    const double post_old = __dadd_rn(__dmul_rn(beta, ll_old), lp_old);
-    const double lnpdiff = __dsub_rn(__dadd_rn(factors[o], post_new), post_old);
-    const bool acc = lnpdiff > lnu[o];
-    if (lane == 0) {
-      accepted[w] = acc ? 1 : 0;
-      if (ll_new != ll_new && lp_new != -INFINITY) atomicAdd(n_nan, 1u);
-      atomicAdd(&cnt[0], 1ull);
-      if (lp_new != -INFINITY) atomicAdd(&cnt[1], 1ull);
-      if (acc) atomicAdd(&cnt[2], 1ull);
-    }
+// ---- Metropolis accept, run by the warp that just finished a proposal's likelihood ---------------
+struct PtAccept {
+  int32_t enabled;
+  int32_t T, W, split;        // local temperatures, walkers, half being updated
+  double* p;                  // [T, W, ndim] state (updated in place)
+  double* logl;               // [T, W]
+  double* logp;               // [T, W]
+  const double* q;            // [T*H, ndim] proposals of this half
+  const double* lpq;          // [T*H] their log-priors
+  const int32_t* half_idx;    // [T, 2, H]
+  const double* betas;        // beta of local row t = betas[beta_off + t*beta_stride] (the whole ladder's array)
+  int32_t beta_off, beta_stride;
+  const double* factors;      // [T, 2, H] (ndim-1) ln zz
+  const double* lnu;          // [T, 2, H] ln u
+  uint8_t* accepted;          // [T, W]
+  int32_t* n_accepted;        // [T, W] accepted moves per walker since the run began (may be NULL)
+  unsigned long long* cnt;    // [0] proposals [1] inside the prior support [2] accepted
+  uint32_t* n_nan;
+};
+
+// tj: index of the proposal inside the half (t*H + j); ll_new known to every lane
+__device__ __forceinline__ void pt_accept_row(const PtAccept& A, int ndim, int64_t tj, double ll_new, int lane) {
+  const int32_t H = A.W / 2;
+  const int32_t j = int32_t(tj % H), t = int32_t(tj / H);
+  const int64_t o = (int64_t(t) * 2 + A.split) * H + j;
+  const int32_t i = A.half_idx[o];
+  const int64_t w = int64_t(t) * A.W + i;
+  const double beta = A.betas[A.beta_off + t * A.beta_stride];
+  const double lp_new = A.lpq[tj];
+  const double ll_old = A.logl[w], lp_old = A.logp[w];
+  // lnpdiff = f + (beta*ll' + lp') - (beta*ll + lp)
+  const double post_new = __dadd_rn(__dmul_rn(beta, ll_new), lp_new);
+  const double post_old = __dadd_rn(__dmul_rn(beta, ll_old), lp_old);
+  const double lnpdiff = __dsub_rn(__dadd_rn(A.factors[o], post_new), post_old);
+  const bool acc = lnpdiff > A.lnu[o];
+  if (lane == 0) {
+    A.accepted[w] = acc ? 1 : 0;
+    if (ll_new != ll_new) atomicAdd(A.n_nan, 1u);  // emcee raises on a NaN likelihood; here: rejected + counted
     if (acc) {
-      for (int dd = lane; dd < ndim; dd += 32) p[w * ndim + dd] = q[tj * ndim + dd];
-      if (lane == 0) { logl[w] = ll_new; logp[w] = lp_new; }
+      atomicAdd(&A.cnt[2], 1ull);
+      if (A.n_accepted) A.n_accepted[w] += 1;
     }
+  }
+  if (acc) {  // red/blue: only this warp touches walker w during this half-step
+    for (int dd = lane; dd < ndim; dd += 32) A.p[w * ndim + dd] = A.q[tj * ndim + dd];
+    if (lane == 0) { A.logl[w] = ll_new; A.logp[w] = lp_new; }
   }
 }
 
-// Swap plan: sequential over temperature pairs (hot -> cold), parallel over walkers.
-// Single CTA; cur[] holds, for the hotter temperature of the current pair, the flat source
-// index and log-likelihood of what presently sits in each slot.
-//   src [T, W]: flat index of the ORIGINAL slot whose walker ends in (t, w)
-__global__ void pt_swap_plan_kernel(int32_t T, int32_t W, const double* __restrict__ logl,
-                                    const double* __restrict__ betas, const int32_t* __restrict__ perm,
-                                    const double* __restrict__ lnu, int32_t* __restrict__ src,
-                                    int32_t* __restrict__ n_acc, double* __restrict__ ll_work) {
-  // ll_work [2, W] scratch in global memory (W may exceed what fits comfortably in smem)
+// ---- proposal + prior + compaction ------------------------------------------------------------------
+struct PtPropose {
+  const EmpModelDesc* desc;
+  const double* p;            // [T, W, ndim]
+  int32_t T, W, split;
+  const int32_t* half_idx;    // [T, 2, H]
+  const double* zz;           // [T, 2, H]
+  const int32_t* rint;        // [T, 2, H]
+  double* q;                  // [T*H, ndim] out
+  double* lpq;                // [T*H] out
+  int32_t* eval_index;        // compact list of the proposals inside the prior support
+  int32_t* n_active;          // its length (zero on entry; the likelihood kernel of the OTHER half re-zeroes it)
+  uint8_t* accepted;          // [T, W]: 0 written for the proposals that are never evaluated
+  unsigned long long* cnt;
+  long long* step_counter;    // stretch steps begun so far (device scalar; split 0 increments it)
+};
+
+constexpr int kProposeWarps = 8;
+
+// One warp per proposal.  q = c[rint] - (c[rint] - s) zz with the reference's roundings; the prior
+// program is evaluated lane-parallel (one op per lane) and summed in program order by lane 0 — the
+// reference's early `return lp` after a block whose sum is -inf is reproduced by the ordered sum, so
+// logP is bit-identical to my_prior.  Proposals outside the prior support are never evaluated (emcee
+// semantics): they get accepted = 0 here; the others are appended to the compact list with one atomic
+// per CTA.
+__global__ void __launch_bounds__(kProposeWarps * 32) pt_propose_prior_kernel(const PtPropose A) {
+  __shared__ double th_s[kProposeWarps][EMP_MAX_DIM];
+  __shared__ double val_s[kProposeWarps][EMP_MAX_PRIOR_OPS];
+  __shared__ int s_flag[kProposeWarps];
+  __shared__ int s_base;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const EmpModelDesc* __restrict__ d = A.desc;
+  const int32_t H = A.W / 2, ndim = d->ndim_free;
+  const int64_t n_prop = int64_t(A.T) * H;
+  const int64_t tj = int64_t(blockIdx.x) * kProposeWarps + warp;
+  const bool valid = tj < n_prop;
+  bool inside = false;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    atomicAdd(&A.cnt[0], (unsigned long long)n_prop);
+    if (A.split == 0 && A.step_counter) *A.step_counter += 1;
+  }
+  if (valid) {
+    const int32_t j = int32_t(tj % H), t = int32_t(tj / H);
+    const int64_t o = (int64_t(t) * 2 + A.split) * H + j;
+    const int32_t i = A.half_idx[o];
+    const int32_t partner = A.half_idx[(int64_t(t) * 2 + (1 - A.split)) * H + A.rint[o]];
+    const double z = A.zz[o];
+    double* th = th_s[warp];
+    for (int k = lane; k < d->ndim_full; k += 32) th[k] = d->full_init[k];
+    __syncwarp();
+    for (int dd = lane; dd < ndim; dd += 32) {
+      const double s = A.p[(int64_t(t) * A.W + i) * ndim + dd];
+      const double c = A.p[(int64_t(t) * A.W + partner) * ndim + dd];
+      const double qv = __dsub_rn(c, __dmul_rn(__dsub_rn(c, s), z));  // c[rint] - (c[rint] - s) * zz[:, None]
+      A.q[tj * ndim + dd] = qv;
+      th[d->free_to_full[dd]] = qv;
+    }
+    __syncwarp();
+    const double lp = prior_program_warp(d, th, val_s[warp], lane);
+    if (lane == 0) A.lpq[tj] = lp;
+    inside = !(lp == -INFINITY);
+    if (!inside && lane == 0) A.accepted[int64_t(t) * A.W + i] = 0;
+  }
+  if (lane == 0) s_flag[warp] = (valid && inside) ? 1 : 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int k = 0; k < kProposeWarps; ++k) n += s_flag[k];
+    s_base = n ? atomicAdd(A.n_active, n) : 0;
+    if (n) atomicAdd(&A.cnt[1], (unsigned long long)n);
+  }
+  __syncthreads();
+  if (valid && inside && lane == 0) {
+    int r = 0;
+    for (int k = 0; k < warp; ++k) r += s_flag[k];
+    A.eval_index[s_base + r] = int32_t(tj);
+  }
+}
+
+// ---- deterministic exp for the ladder adaptation ---------------------------------------------------
+// exp(x) as a FIXED sequence of individually rounded IEEE operations (no FMA), restated operation by
+// operation in oracle/pt_oracle.py::exp_det, so that the device ladder equals the oracle's bit for bit.
+// |error| <= 1 ulp; NumPy's own exp is neither correctly rounded nor the same on every host (SVML/AVX-512
+// vs libm builds), so "the reference's np.exp" is only defined to that level anyway.
+__device__ __forceinline__ double exp_det(double x) {
+  const double kLog2e = 1.4426950408889634074, kL1 = 6.93147180369123816490e-01, kL2 = 1.90821492927058770002e-10;
+  const double n = rint(__dmul_rn(x, kLog2e));
+  const double r = __dsub_rn(__dsub_rn(x, __dmul_rn(n, kL1)), __dmul_rn(n, kL2));
+  // 1/13! ... 1/2!
+  const double c[12] = {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0,
+                        1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
+  double pz = c[0];
+#pragma unroll
+  for (int k = 1; k < 12; ++k) pz = __dadd_rn(__dmul_rn(pz, r), c[k]);
+  const double y = __dadd_rn(1.0, __dadd_rn(r, __dmul_rn(__dmul_rn(r, r), pz)));
+  return scalbn(y, int(n));
+}
+
+// ---- swap plan + ladder adaptation -------------------------------------------------------------------
+struct PtPlan {
+  int32_t T, W;
+  const double* logl;       // [T, W] log-likelihood of the whole ladder
+  double* betas;            // [T] in: ladder of this sweep; out: adapted ladder (when adapt != 0)
+  const int32_t* perm;      // [T-1, 2, W]
+  const double* lnu;        // [T-1, W]
+  int32_t* src;             // [T, W] out: flat index of the slot whose walker ends in (t, w)
+  int32_t* n_acc;           // [T-1] out: accepted swaps per pair
+  int32_t adapt;            // 1: Vousden ladder dynamics after the sweep (ntemps > 2)
+  double adapt_tau, adapt_nu;
+  long long* sweep_counter; // device scalar: sweeps finished (the reference's `time`); incremented here
+  double* beta_hist;        // [hist_cap, T] ladder after each sweep (may be NULL)
+  int32_t* nacc_hist;       // [hist_cap, T-1] swap counts of each sweep (may be NULL)
+  long long hist_cap;
+};
+
+// The adaptation of oracle/pt_oracle.py::adapt_ladder (same operations, same order):
+//   decay = tau/(time+tau); kappa = decay/nu; dS_i = kappa (A_i - A_{i+1}); dT_i = (1/b_{i+1} - 1/b_i) exp(dS_i);
+//   b_{i+1} = 1/(cumsum(dT)_i + 1/b_0),  i = 0 .. T-3
+// s_x: T doubles of shared scratch.  Called by all threads of the single plan CTA after the last pair.
+__device__ __forceinline__ void plan_tail(const PtPlan& A, double* s_x, const int32_t* s_nacc) {
+  const int tid = threadIdx.x, nt = blockDim.x, T = A.T;
+  const long long row = A.sweep_counter ? *A.sweep_counter : 0;
+  const long long time = row + 1;  // `self.time += 1` precedes the adaptation
+  __syncthreads();
+  if (A.adapt && T > 2) {
+    const double decay = __ddiv_rn(A.adapt_tau, __dadd_rn(double(time), A.adapt_tau));
+    const double kappa = __ddiv_rn(decay, A.adapt_nu);
+    const double Wd = double(A.W);
+    for (int i = tid; i < T - 2; i += nt) {
+      const double r0 = __ddiv_rn(double(s_nacc[i]), Wd), r1 = __ddiv_rn(double(s_nacc[i + 1]), Wd);
+      const double dS = __dmul_rn(kappa, __dsub_rn(r0, r1));
+      const double dT = __dsub_rn(__ddiv_rn(1.0, A.betas[i + 1]), __ddiv_rn(1.0, A.betas[i]));
+      s_x[i] = __dmul_rn(dT, exp_det(dS));
+    }
+    __syncthreads();
+    if (tid == 0) {  // np.cumsum: strictly sequential
+      double c = 0.0;
+      for (int i = 0; i < T - 2; ++i) {
+        c = (i == 0) ? s_x[0] : __dadd_rn(c, s_x[i]);
+        s_x[i] = c;
+      }
+    }
+    __syncthreads();
+    const double t0 = __ddiv_rn(1.0, A.betas[0]);
+    for (int i = tid; i < T - 2; i += nt) A.betas[i + 1] = __ddiv_rn(1.0, __dadd_rn(s_x[i], t0));
+    __syncthreads();
+  }
+  if (row < A.hist_cap) {
+    if (A.beta_hist)
+      for (int i = tid; i < T; i += nt) A.beta_hist[row * T + i] = A.betas[i];
+    if (A.nacc_hist)
+      for (int i = tid; i < T - 1; i += nt) A.nacc_hist[row * (T - 1) + i] = s_nacc[i];
+  }
+  if (tid == 0 && A.sweep_counter) *A.sweep_counter = row + 1;
+}
+
+constexpr int kPlanMaxT = 2048;  // ladder length limit: the sweep's swap counts live in shared memory for the adaptation
+
+// Swap plan: sequential over temperature pairs (hot -> cold), parallel over walkers, single CTA: every rank
+// of a sharded ladder replays all T-1 pairs, so this kernel's latency is the serial (Amdahl) part of a sweep.
+// The active logL rows and their source-index rows live in shared memory.
+//   kBuf = 3 (36 W bytes): ONE block barrier per pair.  The colder row of the NEXT pair is staged into the spare
+//     buffer while the current pair is decided (nothing reads it yet), the finished hot row is written back and
+//     recycled as the next spare by the thread that owns the same elements.
+//   kBuf = 2 (24 W bytes, W > 5600): the cold row is staged in place, which costs a second barrier per pair.
+// The perm rows / uniforms of the next pair and the logL row after it are prefetched into registers under the
+// decision of the current pair; swap counts are warp-aggregated (one shared-memory atomic per warp).
+// kR = elements per thread = ceil(W / 1024).
+template <int kR, int kBuf>
+__global__ void __launch_bounds__(1024) pt_swap_plan_kernel(const PtPlan A) {
+  extern __shared__ __align__(16) unsigned char plan_smem[];
+  const int32_t T = A.T, W = A.W;
+  // roles rotate by pointer: hot = warmer row of the current pair, cold = its colder row, spare = staging
+  double* lh = reinterpret_cast<double*>(plan_smem);
+  double* lc = lh + W;
+  double* ls = lc + (kBuf == 3 ? W : 0);
+  int32_t* sh = reinterpret_cast<int32_t*>(ls + W);
+  int32_t* sc = sh + W;
+  int32_t* ss = sc + (kBuf == 3 ? W : 0);
+  __shared__ int32_t s_count[2];
+  __shared__ int32_t s_nacc[kPlanMaxT];
+  __shared__ double s_x[kPlanMaxT];
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+  const double* __restrict__ logl = A.logl;
+  const int32_t* __restrict__ perm = A.perm;
+  const double* __restrict__ lnu = A.lnu;
+
+  int32_t ca[kR], cb[kR];
+  double cu[kR], nl[kR];
+  // hot row = temperature T-1; cold row of the first pair = temperature T-2
+  for (int w = tid; w < W; w += nt) {
+    lh[w] = logl[int64_t(T - 1) * W + w];
+    sh[w] = (T - 1) * W + w;
+    if (T > 1) {
+      lc[w] = logl[int64_t(T - 2) * W + w];
+      sc[w] = (T - 2) * W + w;
+    }
+  }
+  if (tid < 2) s_count[tid] = 0;
+  if (T > 1) {
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      const int k = tid + r * nt;
+      if (k < W) {
+        ca[r] = perm[(int64_t(T - 2) * 2 + 0) * W + k];
+        cb[r] = perm[(int64_t(T - 2) * 2 + 1) * W + k];
+        cu[r] = lnu[int64_t(T - 2) * W + k];
+      }
+    }
+  }
+  __syncthreads();
+  // pair j couples temperature j+1 (hot) with j (cold)
+  for (int j = T - 2; j >= 0; --j) {
+    int32_t na[kR], nb[kR];
+    double nu[kR];
+    // prefetch: draws of pair j-1, logL row of temperature j-1 (the cold row of pair j-1)
+    if (j >= 1) {
+#pragma unroll
+      for (int r = 0; r < kR; ++r) {
+        const int k = tid + r * nt;
+        if (k < W) {
+          na[r] = perm[(int64_t(j - 1) * 2 + 0) * W + k];
+          nb[r] = perm[(int64_t(j - 1) * 2 + 1) * W + k];
+          nu[r] = lnu[int64_t(j - 1) * W + k];
+          nl[r] = logl[int64_t(j - 1) * W + k];
+        }
+      }
+    }
+    const double dbeta = __dsub_rn(A.betas[j], A.betas[j + 1]);
+    int local = 0;
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      const int k = tid + r * nt;
+      if (k < W) {
+        const int a = ca[r], b = cb[r];  // slot a of temp j+1 <-> slot b of temp j; perm rows are permutations
+        const double la = lh[a], lb = lc[b];
+        if (__dmul_rn(dbeta, __dsub_rn(la, lb)) > cu[r]) {
+          const int32_t sa = sh[a];
+          sh[a] = sc[b];
+          sc[b] = sa;
+          lh[a] = lb;
+          lc[b] = la;
+          ++local;
+        }
+      }
+    }
+    local = __reduce_add_sync(0xffffffffu, local);
+    if (lane == 0 && local) atomicAdd(&s_count[j & 1], local);
+    if (kBuf == 3 && j >= 1) {  // stage the next cold row into the spare buffer (nobody reads it in this phase)
+#pragma unroll
+      for (int r = 0; r < kR; ++r) {
+        const int k = tid + r * nt;
+        if (k < W) {
+          ls[k] = nl[r];
+          ss[k] = (j - 1) * W + k;
+        }
+      }
+    }
+    __syncthreads();
+    // row j+1 of the plan is final: write it back (each thread the elements it re-initialises later)
+    for (int w = tid; w < W; w += nt) A.src[int64_t(j + 1) * W + w] = sh[w];
+    if (tid == 0) {
+      const int32_t c = s_count[j & 1];
+      A.n_acc[j] = c;
+      s_nacc[j] = c;
+      s_count[j & 1] = 0;
+    }
+    if (kBuf == 3) {
+      double* tl = lh; lh = lc; lc = ls; ls = tl;
+      int32_t* ts = sh; sh = sc; sc = ss; ss = ts;
+    } else {
+      double* tl = lh; lh = lc; lc = tl;
+      int32_t* ts = sh; sh = sc; sc = ts;
+      if (j >= 1) {
+#pragma unroll
+        for (int r = 0; r < kR; ++r) {
+          const int k = tid + r * nt;
+          if (k < W) {
+            lc[k] = nl[r];
+            sc[k] = (j - 1) * W + k;
+          }
+        }
+        __syncthreads();
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kR; ++r) { ca[r] = na[r]; cb[r] = nb[r]; cu[r] = nu[r]; }
+  }
+  if (A.src)
+    for (int w = tid; w < W; w += nt) A.src[w] = sh[w];
+  plan_tail(A, s_x, s_nacc);
+}
+
+// Fallback for ensembles whose rows do not fit in shared memory (W > 8192): rows in global scratch.
+__global__ void __launch_bounds__(1024) pt_swap_plan_global_kernel(const PtPlan A, double* __restrict__ ll_work) {
   __shared__ int32_t s_count;
-  double* ll_hot = ll_work;       // current content of temperature i
-  double* ll_cold = ll_work + W;  // current content of temperature i-1
+  __shared__ int32_t s_nacc[kPlanMaxT];
+  __shared__ double s_x[kPlanMaxT];
+  const int32_t T = A.T, W = A.W;
+  double* ll_hot = ll_work;
+  double* ll_cold = ll_work + W;
   const int tid = threadIdx.x, nt = blockDim.x;
-  // identity plan
-  for (int64_t g = tid; g < int64_t(T) * W; g += nt) src[g] = int32_t(g);
-  for (int w = tid; w < W; w += nt) ll_hot[w] = logl[int64_t(T - 1) * W + w];
+  for (int64_t g = tid; g < int64_t(T) * W; g += nt) A.src[g] = int32_t(g);
+  for (int w = tid; w < W; w += nt) ll_hot[w] = A.logl[int64_t(T - 1) * W + w];
   __syncthreads();
   for (int i = T - 1; i >= 1; --i) {
     if (tid == 0) s_count = 0;
-    for (int w = tid; w < W; w += nt) ll_cold[w] = logl[int64_t(i - 1) * W + w];
+    for (int w = tid; w < W; w += nt) ll_cold[w] = A.logl[int64_t(i - 1) * W + w];
     __syncthreads();
-    const double dbeta = __dsub_rn(betas[i - 1], betas[i]);
-    const int32_t* pi = perm + (int64_t(i - 1) * 2 + 0) * W;
-    const int32_t* pi1 = perm + (int64_t(i - 1) * 2 + 1) * W;
-    const double* u = lnu + int64_t(i - 1) * W;
+    const double dbeta = __dsub_rn(A.betas[i - 1], A.betas[i]);
+    const int32_t* pi = A.perm + (int64_t(i - 1) * 2 + 0) * W;
+    const int32_t* pi1 = A.perm + (int64_t(i - 1) * 2 + 1) * W;
+    const double* u = A.lnu + int64_t(i - 1) * W;
     int local = 0;
     for (int k = tid; k < W; k += nt) {
-      const int a = pi[k], b = pi1[k];  // slot a of temp i  <->  slot b of temp i-1
+      const int a = pi[k], b = pi1[k];
       const double la = ll_hot[a], lb = ll_cold[b];
-      const double paccept = __dmul_rn(dbeta, __dsub_rn(la, lb));
-      if (paccept > u[k]) {
-        // perm rows are permutations: no two k touch the same slot
+      if (__dmul_rn(dbeta, __dsub_rn(la, lb)) > u[k]) {
         const int64_t ga = int64_t(i) * W + a, gb = int64_t(i - 1) * W + b;
-        const int32_t sa = src[ga];
-        src[ga] = src[gb];
-        src[gb] = sa;
+        const int32_t sa = A.src[ga];
+        A.src[ga] = A.src[gb];
+        A.src[gb] = sa;
         ll_hot[a] = lb;
         ll_cold[b] = la;
         ++local;
@@ -123,103 +404,134 @@ __global__ void pt_swap_plan_kernel(int32_t T, int32_t W, const double* __restri
     }
     if (local) atomicAdd(&s_count, local);
     __syncthreads();
-    if (tid == 0) n_acc[i - 1] = s_count;
-    // temperature i-1 becomes the hot side of the next pair
+    if (tid == 0) { A.n_acc[i - 1] = s_count; s_nacc[i - 1] = s_count; }
     double* tmp = ll_hot; ll_hot = ll_cold; ll_cold = tmp;
     __syncthreads();
   }
+  plan_tail(A, s_x, s_nacc);
 }
 
-// Same plan with the two active logL rows and their source-index rows resident in shared memory
-// (24*W bytes, W <= 8192).  The sweep is sequential over pairs and every rank of a sharded ladder replays
-// all of them, so this kernel's latency is the serial (Amdahl) part of a sweep.  Per pair: the colder
-// logL row, the two permutation rows and the uniforms of the NEXT pair are prefetched into registers while
-// the current pair is decided out of shared memory (software pipeline: the global-load latency, ~1.5 us of
-// the former 2.9 us per pair, is hidden), two block barriers, one coalesced write-back of the finished row
-// of `src` by the threads that own the same elements in the next pair (no barrier needed for it).
-// kR = elements per thread = ceil(W / 1024).
-template <int kR>
-__global__ void __launch_bounds__(1024) pt_swap_plan_smem_kernel(int32_t T, int32_t W, const double* __restrict__ logl,
-                                                                const double* __restrict__ betas,
-                                                                const int32_t* __restrict__ perm,
-                                                                const double* __restrict__ lnu,
-                                                                int32_t* __restrict__ src, int32_t* __restrict__ n_acc) {
-  extern __shared__ __align__(16) unsigned char plan_smem[];
-  double* ll_hot = reinterpret_cast<double*>(plan_smem);
-  double* ll_cold = ll_hot + W;
-  int32_t* sr_hot = reinterpret_cast<int32_t*>(ll_cold + W);
-  int32_t* sr_cold = sr_hot + W;
-  __shared__ int32_t s_count;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  int32_t pa[kR], pb[kR];
-  double pu[kR], pl[kR];
-  // prefetch of pair j (temperatures j+1 and j): perm rows, uniforms, the colder logL row
-  auto prefetch = [&](int j) {
-#pragma unroll
-    for (int r = 0; r < kR; ++r) {
-      const int k = tid + r * nt;
-      if (k < W) {
-        pa[r] = perm[(int64_t(j) * 2 + 0) * W + k];
-        pb[r] = perm[(int64_t(j) * 2 + 1) * W + k];
-        pu[r] = lnu[int64_t(j) * W + k];
-        pl[r] = logl[int64_t(j) * W + k];
+// ---- plan application: row gather + swap mean distance + chain store ------------------------------------
+struct PtApply {
+  int32_t T_loc, W, ndim;
+  int32_t T_all, G, rank, strided;   // ladder size, ranks, this rank, layout (1: rank r holds r, r+G, ...)
+  const int32_t* src;                // [T_all, W] plan (global flat indices t*W + w); NULL = identity (no swap sweep)
+  // CURRENT buffers of every rank ([T_loc, W, ndim] / [T_loc, W]); entry `rank` is the local one, the others are
+  // peer HBM mapped through CUDA IPC and read over NVLink
+  const double* p_in[kMaxPeers];
+  const double* ll_in[kMaxPeers];
+  const double* lp_in[kMaxPeers];
+  double* p_out; double* ll_out; double* lp_out;  // local target buffers (NULL when src == NULL)
+  // swap mean distance (consumers emp.py:961-965, 1985-1990): per destination temperature, mean over the slots
+  // that received a walker from a hotter rung of |x_new - x_old| in units of the prior widths D_
+  const double* D;                   // [ndim] or NULL
+  double* smd_part;                  // [T_loc, blocks_per_temp, 2] partial (sum, count)
+  uint32_t* smd_ticket;              // [T_loc]
+  double* smd_hist;                  // [hist_cap, T_loc]
+  const long long* sweep_counter;    // already incremented by the plan kernel: row = *counter - 1
+  long long hist_cap;
+  // chain store: slot = (*step_counter - 1) / thin when (*step_counter - 1) % thin == 0
+  double* chain; double* ch_ll; double* ch_lp;  // [cap, T_loc, W, ndim] / [cap, T_loc, W]; NULL = no store
+  const long long* step_counter;
+  long long store_cap, store_ring;   // capacity in samples; ring != 0: slot wraps (host streaming sink)
+  int32_t thin;
+};
+
+constexpr int kApplyWarps = 8;
+constexpr int kApplyRowsPerWarp = 4;
+constexpr int kApplyRows = kApplyWarps * kApplyRowsPerWarp;  // rows of one temperature per CTA
+
+__device__ __forceinline__ long long store_slot(const long long* step_counter, int thin, long long cap, long long ring) {
+  if (!step_counter) return -1;
+  const long long n = *step_counter - 1;
+  if (n < 0 || (n % thin) != 0) return -1;
+  long long s = n / thin;
+  if (ring) s %= cap;
+  return s < cap ? s : -1;
+}
+
+// grid = (blocks_per_temp, T_loc); a CTA owns kApplyRows consecutive walkers of one local temperature
+__global__ void __launch_bounds__(kApplyWarps * 32) pt_apply_plan_kernel(const PtApply A) {
+  __shared__ double s_sum[kApplyWarps];
+  __shared__ int s_cnt[kApplyWarps];
+  __shared__ int s_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tl = blockIdx.y;
+  const int tg = A.strided ? tl * A.G + A.rank : A.rank * A.T_loc + tl;
+  const int ndim = A.ndim, W = A.W;
+  const long long slot = A.chain ? store_slot(A.step_counter, A.thin, A.store_cap, A.store_ring) : -1;
+  double wsum = 0.0;
+  int wcnt = 0;
+  for (int rr = 0; rr < kApplyRowsPerWarp; ++rr) {
+    const int w = (blockIdx.x * kApplyWarps + warp) * kApplyRowsPerWarp + rr;
+    if (w >= W) break;
+    const int64_t r = int64_t(tl) * W + w;
+    int owner = A.rank;
+    int64_t srow = r;
+    int st = tg;
+    if (A.src) {
+      const int32_t s = A.src[int64_t(tg) * W + w];
+      st = s / W;
+      const int sw = s - st * W;
+      owner = A.strided ? st % A.G : st / A.T_loc;
+      const int sl = A.strided ? st / A.G : st % A.T_loc;
+      srow = int64_t(sl) * W + sw;
+    }
+    const double* __restrict__ pin = A.p_in[owner];
+    double dist2 = 0.0;
+    const bool down = A.D && st > tg;
+    for (int dd = lane; dd < ndim; dd += 32) {
+      const double v = pin[srow * ndim + dd];
+      if (A.p_out) A.p_out[r * ndim + dd] = v;
+      if (slot >= 0) A.chain[(slot * A.T_loc * W + r) * ndim + dd] = v;
+      if (down) {
+        const double z = __ddiv_rn(__dsub_rn(v, A.p_in[A.rank][r * ndim + dd]), A.D[dd]);
+        dist2 = __dadd_rn(dist2, __dmul_rn(z, z));
       }
     }
-  };
-  for (int w = tid; w < W; w += nt) {
-    ll_hot[w] = logl[int64_t(T - 1) * W + w];
-    sr_hot[w] = (T - 1) * W + w;
+    if (lane == 0) {
+      const double l = A.ll_in[owner][srow], q = A.lp_in[owner][srow];
+      if (A.ll_out) { A.ll_out[r] = l; A.lp_out[r] = q; }
+      if (slot >= 0) { A.ch_ll[slot * A.T_loc * W + r] = l; A.ch_lp[slot * A.T_loc * W + r] = q; }
+    }
+    if (down) {  // fixed-order butterfly: every lane ends with the same sum
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) dist2 = __dadd_rn(dist2, __shfl_xor_sync(0xffffffffu, dist2, off));
+      wsum = __dadd_rn(wsum, __dsqrt_rn(dist2));
+      ++wcnt;
+    }
   }
-  if (tid == 0) s_count = 0;
-  if (T > 1) prefetch(T - 2);
-  for (int i = T - 1; i >= 1; --i) {
-    int32_t ca[kR], cb[kR];
-    double cu[kR];
-#pragma unroll
-    for (int r = 0; r < kR; ++r) {
-      const int k = tid + r * nt;
-      ca[r] = pa[r]; cb[r] = pb[r]; cu[r] = pu[r];
-      if (k < W) {
-        ll_cold[k] = pl[r];
-        sr_cold[k] = (i - 1) * W + k;
-      }
-    }
-    const double dbeta = __dsub_rn(betas[i - 1], betas[i]);
-    __syncthreads();
-    if (i >= 2) prefetch(i - 2);  // in flight while this pair is decided
-    int local = 0;
-#pragma unroll
-    for (int r = 0; r < kR; ++r) {
-      const int k = tid + r * nt;
-      if (k < W) {
-        const int a = ca[r], b = cb[r];  // slot a of temp i  <->  slot b of temp i-1; perm rows are permutations
-        const double la = ll_hot[a], lb = ll_cold[b];
-        if (__dmul_rn(dbeta, __dsub_rn(la, lb)) > cu[r]) {
-          const int32_t sa = sr_hot[a];
-          sr_hot[a] = sr_cold[b];
-          sr_cold[b] = sa;
-          ll_hot[a] = lb;
-          ll_cold[b] = la;
-          ++local;
-        }
-      }
-    }
-    if (local) atomicAdd(&s_count, local);
-    __syncthreads();
-    // row i of the plan is final: write it back (each thread the elements it overwrites next iteration);
-    // row i-1 becomes the hot side
-    for (int w = tid; w < W; w += nt) src[int64_t(i) * W + w] = sr_hot[w];
-    if (tid == 0) { n_acc[i - 1] = s_count; s_count = 0; }
-    double* tl = ll_hot; ll_hot = ll_cold; ll_cold = tl;
-    int32_t* ts = sr_hot; sr_hot = sr_cold; sr_cold = ts;
+  if (!A.D || !A.smd_hist) return;
+  // deterministic reduction: warps in order inside the CTA, CTAs in order by the last one to finish
+  if (lane == 0) { s_sum[warp] = wsum; s_cnt[warp] = wcnt; }
+  __syncthreads();
+  const int nb = gridDim.x;
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    int c = 0;
+    for (int k = 0; k < kApplyWarps; ++k) { s = __dadd_rn(s, s_sum[k]); c += s_cnt[k]; }
+    A.smd_part[(int64_t(tl) * nb + blockIdx.x) * 2 + 0] = s;
+    A.smd_part[(int64_t(tl) * nb + blockIdx.x) * 2 + 1] = double(c);
+    __threadfence();
+    const unsigned t = atomicAdd(&A.smd_ticket[tl], 1u);
+    s_last = (t == unsigned(nb - 1));
   }
   __syncthreads();
-  for (int w = tid; w < W; w += nt) src[w] = sr_hot[w];
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    double s = 0.0, c = 0.0;
+    const volatile double* part = A.smd_part;
+    for (int b = 0; b < nb; ++b) {
+      s = __dadd_rn(s, part[(int64_t(tl) * nb + b) * 2 + 0]);
+      c += part[(int64_t(tl) * nb + b) * 2 + 1];
+    }
+    const long long row = A.sweep_counter ? *A.sweep_counter - 1 : 0;
+    if (row >= 0 && row < A.hist_cap) A.smd_hist[row * A.T_loc + tl] = __ddiv_rn(s, c > 1.0 ? c : 1.0);
+    A.smd_ticket[tl] = 0;  // ready for the next sweep
+  }
 }
 
-// Apply a plan to rows [t0, t0 + T_loc) held locally; sources must be local too
-// (single-GPU, or after the cross-rank exchange staged remote rows into `p_in`).
-//   src_local: flat index into the *_in arrays (already translated by the caller)
+// Legacy row gather (emp_pt_gather_rows): rows of the *_in arrays picked by `src`.
 __global__ void pt_gather_rows_kernel(int64_t n_rows, int32_t ndim, const int32_t* __restrict__ src,
                                       const double* __restrict__ p_in, const double* __restrict__ ll_in,
                                       const double* __restrict__ lp_in, double* __restrict__ p_out,

@@ -40,6 +40,7 @@ class SweepDraws:
     lnu: np.ndarray       # [nsteps, T_loc, 2, H]  log(u)
     perm: np.ndarray      # [R, 2, W] int32: the row of pair j couples temperature j+1 (row 0) with j (row 1)
     lnu_swap: np.ndarray  # [R, W]   (R = T-1 pairs, or this rank's rows of a sharded ladder)
+    sharded_swap: bool = False  # perm / lnu_swap hold only this rank's pair rows (to be all-gathered)
 
     FIELDS = ("half_idx", "zz", "rint", "factors", "lnu", "perm", "lnu_swap")
 
@@ -114,7 +115,7 @@ def draw_sweep(streams: DrawStreams, W: int, ndim: int, nsteps: int, a: float = 
             perm[k, 1] = rng.permutation(W)
             with np.errstate(divide="ignore"):
                 lnu_swap[k] = np.log(rng.uniform(size=W))
-    return SweepDraws(half_idx, zz, rint, factors, lnu, perm, lnu_swap)
+    return SweepDraws(half_idx, zz, rint, factors, lnu, perm, lnu_swap, sharded_swap=swap_rows is not None)
 
 
 def initial_positions(rng: np.random.RandomState, spec, ntemps: int, nwalkers: int) -> np.ndarray:

@@ -91,6 +91,13 @@ class LikelihoodEngine:
         _lib.check(self._L.emp_launch_count(self._h, ctypes.byref(c)))
         return int(c.value)
 
+    @property
+    def graph_captures(self) -> int:
+        """CUDA graphs captured by emp_pt_sweep so far (a steady run replays two)."""
+        c = ctypes.c_int64()
+        _lib.check(self._L.emp_graph_captures(self._h, ctypes.byref(c)))
+        return int(c.value)
+
     SOLVERS = {"grid": 0, "kepler.py": 1}
 
     def set_solver(self, name: str):
@@ -146,8 +153,10 @@ class LikelihoodEngine:
 
     # ---- scalar-compatible callables (B1 of SURVEY.md §8b) ---------------------------
     def my_likelihood(self, theta) -> float:
-        """my_likelihood(theta) (00.like:3-5).  Like the reference it evaluates the
-        model regardless of the prior; use `logl_batch` for sampler semantics."""
+        """my_likelihood(theta) (00.like:3-5) for theta INSIDE the prior support.  Unlike the
+        reference's scalar callable, the device path never evaluates the model where the prior is
+        -inf (the sampler never asks for it: emcee skips the likelihood there); such a call raises
+        ValueError instead of returning a number nobody uses.  `logl_batch` returns -inf for those rows."""
         th = _np64(theta).reshape(-1, self.ndim)
         ll, lp = self.logl_batch(th)
         if np.any(~np.isfinite(lp)):
@@ -183,11 +192,69 @@ class LikelihoodEngine:
             perm.data_ptr() if perm is not None else None, lnu.data_ptr() if lnu is not None else None,
             src.data_ptr(), n_acc.data_ptr()))
 
+    def pt_sweep(self, args):
+        """One whole single-GPU sweep (emp_pt_sweep); `args` is an `_lib.EmpPtSweepC`."""
+        _lib.check(self._L.emp_pt_sweep(self._h, ctypes.byref(args)))
+
+    def pt_sweep_stretch(self, args):
+        _lib.check(self._L.emp_pt_sweep_stretch(self._h, ctypes.byref(args)))
+
+    def pt_sweep_swap(self, args):
+        _lib.check(self._L.emp_pt_sweep_swap(self._h, ctypes.byref(args)))
+
     def pt_gather_rows(self, src, p_in, ll_in, lp_in, p_out, ll_out, lp_out):
         n_rows = src.numel()
         _lib.check(self._L.emp_pt_gather_rows(
             self._h, n_rows, p_in.shape[-1], src.data_ptr(), p_in.data_ptr(), ll_in.data_ptr(),
             lp_in.data_ptr(), p_out.data_ptr(), ll_out.data_ptr(), lp_out.data_ptr()))
+
+
+class SharedDeviceBuffer:
+    """A cudaMalloc'ed block that the other ranks of the node can map (CUDA IPC, emp_dev_alloc /
+    emp_ipc_export / emp_ipc_open): the sharded swap reads peer ensembles through it over NVLink.
+    `tensor(shape, offset)` gives zero-copy torch views (torch consumes __cuda_array_interface__)."""
+
+    def __init__(self, device: int, nbytes: int, ptr: Optional[int] = None, owner: bool = True):
+        self.device, self.nbytes, self.owner = int(device), int(nbytes), owner
+        if ptr is None:
+            p = ctypes.c_void_p()
+            _lib.check(_lib.lib().emp_dev_alloc(self.device, self.nbytes, ctypes.byref(p)))
+            ptr = p.value
+        self.ptr = int(ptr)
+
+    def export(self) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        _lib.check(_lib.lib().emp_ipc_export(self.device, ctypes.c_void_p(self.ptr), buf))
+        return buf.raw
+
+    @classmethod
+    def open(cls, device: int, handle: bytes, nbytes: int) -> "SharedDeviceBuffer":
+        p = ctypes.c_void_p()
+        _lib.check(_lib.lib().emp_ipc_open(int(device), handle, ctypes.byref(p)))
+        return cls(device, nbytes, ptr=p.value, owner=False)
+
+    def tensor(self, shape, offset_bytes: int = 0, typestr: str = "<f8"):
+        import torch
+
+        class _View:
+            pass
+        v = _View()
+        v.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": typestr,
+                                      "data": (self.ptr + int(offset_bytes), False), "version": 2, "strides": None}
+        v._keepalive = self
+        return torch.as_tensor(v, device=torch.device("cuda", self.device))
+
+    def close(self):
+        if self.ptr:
+            L = _lib.lib()
+            (L.emp_dev_free if self.owner else L.emp_ipc_close)(self.device, ctypes.c_void_p(self.ptr))
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def fp64_peak_tflops(device: int = 0) -> float:

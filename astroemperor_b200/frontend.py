@@ -4,7 +4,7 @@
 (emp.py:2614-2651, block_repo.py:505-867) produce for an RV model: the block
 order (Keplerians first, emp.py:1235; then Acceleration, Offset, Jitter, MOAV),
 the parameter names and the data-derived default limits / priors.  It is checked
-against the REAL reference's output in tests/test_frontend.py via the golden
+against the REAL reference's output in tests/test_host_logic.py::test_default_spec_matches_reference_model via the golden
 `<case>.json` files.
 
 `Simulation` keeps the reference's user-facing names (`load_data`,

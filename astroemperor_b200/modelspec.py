@@ -21,7 +21,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 # ---- limits of the C descriptor (include/emperor_b200.h) --------------------
-EMP_ABI_VERSION = 5
+EMP_ABI_VERSION = 6
 EMP_MAX_KEP = 10
 EMP_MAX_INS = 16
 EMP_MAX_DIM = 128

@@ -4,26 +4,48 @@ support/endit_reddemcee.scr:3 `sampler.run_mcmc(p1, nsweeps=, nsteps=, progress=
 as the parent later reads it back (get_chain / get_log_like /
 get_log_prob / betas / get_betas / get_tsw / acceptance_fraction ...).
 
-State lives on the GPU for the whole run: `p[T,W,ndim]`, `logl[T,W]`, `logp[T,W]`.
-Per sweep the host supplies the random draws (draws.py), the device does
-nsteps x (propose, likelihood, accept) per half-ensemble and one swap sweep; the
-ladder adaptation needs only the T-1 swap counts and runs on the host exactly like
-the oracle (bit-identical beta history).
+Everything of a sweep runs on the GPU (include/emperor_b200.h `emp_pt_sweep`): nsteps x
+(proposal + prior, likelihood + Metropolis accept) per half-ensemble, the hot->cold swap
+plan, the ladder adaptation (reddemcee adapt_tau / adapt_nu, adapt_mode 0), the tsw / smd /
+beta histories and the chain store.  The host only supplies the random draws (draws.py), one
+sweep ahead, through a double-buffered pinned staging area; there is NO host synchronisation
+inside a run: with nsteps = 1 a sweep is six kernel launches, replayed from a CUDA graph.
 
-With `torch.distributed` initialised (one process per GPU) the temperature ladder
-is sharded over the ranks, T/G temperatures each, interleaved by default (dist.py): the
-stretch steps need no communication, the swap sweep all-gathers logL (and the swap draws
-each rank generated for its own pairs) over NCCL and every rank replays the same plan.
+With `torch.distributed` initialised (one process per GPU) the temperature ladder is sharded
+over the ranks, T/G temperatures each, interleaved by default (dist.py): the stretch steps need
+no communication; per sweep logL[T, W] (and the swap draws each rank generated for its own
+pairs) are all-gathered over NCCL, every rank replays the same plan + adaptation, and the swap is
+applied by reading the source rows straight from the owners' HBM over NVLink (CUDA IPC): only
+the rows a rank receives cross the links.
 """
 from __future__ import annotations
 
+import ctypes
 import time as _time
+import warnings
 from typing import Optional
 
 import numpy as np
 
+from . import _lib
 from . import dist as _dist
 from .draws import DrawStreams, SweepDraws, default_betas, draw_sweep, initial_positions
+
+
+class State:
+    """What `run_mcmc` returns (emcee's State as EMPEROR uses it: support/endit_freeze1.scr passes it
+    back into the next `run_mcmc`).  `coords` is the whole ladder [T, W, ndim] on the host; handing the
+    same object back continues the run without re-evaluating anything."""
+
+    def __init__(self, sampler, coords, log_like, log_prior):
+        self._sampler_id, self._iteration = id(sampler), sampler.iteration
+        self.coords, self.log_like, self.log_prior = coords, log_like, log_prior
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(self.coords, dtype=dtype)
+
+    def __iter__(self):
+        return iter((self.coords, self.log_like, self.log_prior))
 
 
 class PTSampler:
@@ -31,10 +53,11 @@ class PTSampler:
                  backend=None, betas=None, tsw_history: bool = True, smd_history: bool = True,
                  adapt_tau: float = 1000, adapt_nu: float = 1, adapt_mode: int = 0, a: float = 2.0,
                  seed: Optional[int] = None, store: str = "device", thin_by: int = 1, adapt: bool = True, group=None,
-                 layout: str = "strided", exchange: str = "allgather"):
-        """`log_like` is the LikelihoodEngine (it carries the prior as well; `log_prior`,
-        `pool` and `backend` are accepted for signature compatibility and ignored — the
-        walkers are evaluated on the GPU, not through a multiprocessing pool)."""
+                 layout: str = "strided", exchange: str = "peer", graph: bool = True):
+        """`log_like` is the LikelihoodEngine (it carries the prior as well; `log_prior` and `pool` are
+        accepted for signature compatibility and ignored — the walkers are evaluated on the GPU, not
+        through a multiprocessing pool).  `backend`: None, or a file name: the run is written there in
+        the reference's HDF5 layout when `run_mcmc` returns (postproc.save_backend)."""
         import torch
         from .engine import LikelihoodEngine
         if not isinstance(log_like, LikelihoodEngine):
@@ -51,26 +74,55 @@ class PTSampler:
         self.a = float(a)
         self.adapt_tau, self.adapt_nu, self.adapt_mode, self.adapt = adapt_tau, adapt_nu, adapt_mode, adapt
         self.tsw_history_bool, self.smd_history_bool = bool(tsw_history), bool(smd_history)
-        self.betas = (np.array(betas, dtype=np.float64) if betas is not None
-                      else default_betas(ndim, ntemps))
-        if len(self.betas) != self.ntemps:
+        b0 = (np.array(betas, dtype=np.float64) if betas is not None else default_betas(ndim, ntemps))
+        if len(b0) != self.ntemps:
             raise ValueError(f"betas should have {ntemps} items")
+        self._betas_host = b0
+        self._betas_initial = b0.copy()
+        self._betas_stale = False
         self.streams = DrawStreams(seed, self.ntemps)
         self.D_ = None
-        self.store, self.thin_by = store, int(thin_by)
+        if store not in ("device", "host", None):
+            raise ValueError("store must be 'device', 'host' or None")
+        self.store, self.thin_by = store, max(int(thin_by), 1)
+        self.backend_file = backend if isinstance(backend, str) else None
         self.torch = torch
         self.dev = self.engine.torch_device
         self.shard = _dist.LadderShard(self.ntemps, group=group, layout=layout)
-        if exchange not in ("allgather", "p2p"):
-            raise ValueError("exchange must be 'allgather' or 'p2p'")
+        if exchange not in ("peer", "allgather"):
+            raise ValueError("exchange must be 'peer' (CUDA IPC over NVLink) or 'allgather' (NCCL)")
         self.exchange = exchange
-        self.iteration = 0  # sweeps done
-        self.time = 0
+        self.graph = bool(graph)
+        self.iteration = 0   # sweeps done
+        self.time = 0        # reddemcee's ladder clock (= sweeps done)
+        self._n_steps = 0    # stretch steps done
+        self._stored = 0     # samples stored
+        self._sample_sweep = []  # sweep index of every stored sample
         self._chain = self._ll = self._lp = None
-        self._beta_hist, self._tsw_hist, self._smd_hist = [], [], []
-        self._n_accepted = None
-        self._n_steps = 0
+        self._hist_cap = 0
+        self._beta_hist = self._nacc_hist = self._smd_hist = None
+        self._D_dev = None
+        self._ring = None
+        self._nan_seen = 0
         self.timings = {"draws": 0.0, "h2d": 0.0}
+
+    # ---- the ladder ------------------------------------------------------------------------------
+    @property
+    def betas(self):
+        """Current ladder (adapted on the device after every sweep; reading it synchronises)."""
+        if self._betas_stale:
+            self._betas_host = self._betas_dev.cpu().numpy().copy()
+            self._betas_stale = False
+        return self._betas_host
+
+    @betas.setter
+    def betas(self, value):
+        b = np.array(value, dtype=np.float64)
+        if len(b) != self.ntemps:
+            raise ValueError(f"betas should have {self.ntemps} items")
+        self._betas_host, self._betas_stale = b, False
+        if hasattr(self, "_betas_dev"):
+            self._betas_dev.copy_(self.torch.from_numpy(b))
 
     # ------------------------------------------------------------------------------
     def initial_positions(self, spec, max_repeats: int = 100) -> np.ndarray:
@@ -92,32 +144,91 @@ class PTSampler:
         t = self.torch.from_numpy(np.ascontiguousarray(arr))
         return t.to(self.dev, non_blocking=True)
 
+    def _alloc_state(self):
+        """Device state, allocated once.  Both copies of (p | logl | logp) live in one block each; when the
+        ladder is sharded the blocks are cudaMalloc'ed through the C-ABI and mapped into every peer (CUDA IPC)
+        so that the swap can read its source rows from the owners' HBM."""
+        torch = self.torch
+        Tl, W, nd = self.shard.n_local, self.nwalkers, self.ndim
+        n_row = Tl * W
+        nbytes = n_row * (nd + 2) * 8
+        self._blocks, self._peer_blocks = [], [[], []]
+        self._state = []
+        peer = self.shard.world > 1 and self.exchange == "peer"
+        for par in range(2):
+            if peer:
+                from .engine import SharedDeviceBuffer
+                blk = SharedDeviceBuffer(self.engine.device, nbytes)
+                self._blocks.append(blk)
+                mk = lambda shape, off, blk=blk: blk.tensor(shape, off)
+            else:
+                raw = torch.empty(n_row * (nd + 2), dtype=torch.float64, device=self.dev)
+                self._blocks.append(raw)
+                mk = lambda shape, off, raw=raw: raw[off // 8: off // 8 + int(np.prod(shape))].view(shape)
+            self._state.append((mk((Tl, W, nd), 0), mk((Tl, W), n_row * nd * 8), mk((Tl, W), n_row * (nd + 1) * 8)))
+        self._par = 0
+        self.p, self.logl, self.logp = self._state[0]
+        if peer:
+            self._exchange_ipc_handles(nbytes)
+        self.accepted = torch.zeros((Tl, W), dtype=torch.uint8, device=self.dev)
+        self._n_accepted = torch.zeros((Tl, W), dtype=torch.int32, device=self.dev)
+        self._src = torch.empty((self.ntemps, W), dtype=torch.int32, device=self.dev)
+        self._n_acc = torch.zeros((max(self.ntemps - 1, 1),), dtype=torch.int32, device=self.dev)
+        self._betas_dev = self._upload(self._betas_host)
+        self._counters = torch.zeros(2, dtype=torch.int64, device=self.dev)  # [0] sweeps, [1] stretch steps
+        self._counters[0] = self.iteration
+        self._counters[1] = self._n_steps
+        self.shard.warm_up(self.dev)
+
+    def _exchange_ipc_handles(self, nbytes):
+        """All ranks publish the CUDA IPC handles of their two state blocks once; every rank maps its peers'."""
+        from .engine import SharedDeviceBuffer
+        td, sh = self.shard.td, self.shard
+        mine = [b.export() for b in self._blocks]
+        allh = [None] * sh.world
+        td.all_gather_object(allh, mine, group=sh.group)
+        for par in range(2):
+            row = []
+            for r in range(sh.world):
+                row.append(self._blocks[par] if r == sh.rank
+                           else SharedDeviceBuffer.open(self.engine.device, allh[r][par], nbytes))
+            self._peer_blocks[par] = row
+
     def _init_state(self, p0):
         torch = self.torch
         p0 = np.asarray(p0, dtype=np.float64)
         if p0.shape != (self.ntemps, self.nwalkers, self.ndim):
             raise ValueError(f"p0 must have shape {(self.ntemps, self.nwalkers, self.ndim)}")
-        sl = self.shard.local_slice
-        self.p = self._upload(p0[sl]).contiguous()
-        Tl = self.shard.n_local
-        self.logl = torch.empty((Tl, self.nwalkers), dtype=torch.float64, device=self.dev)
-        self.logp = torch.empty_like(self.logl)
+        if not hasattr(self, "_state"):
+            self._alloc_state()
+        self.p.copy_(self._upload(p0[self.shard.local_slice]))
         self.engine.logl_batch_device(self.p.view(-1, self.ndim), self.logl.view(-1), self.logp.view(-1))
-        self.accepted = torch.zeros((Tl, self.nwalkers), dtype=torch.uint8, device=self.dev)
-        self._n_accepted = torch.zeros((Tl, self.nwalkers), dtype=torch.int64, device=self.dev)
-        self._p_alt = torch.empty_like(self.p)
-        self._ll_alt = torch.empty_like(self.logl)
-        self._lp_alt = torch.empty_like(self.logp)
-        self._src = torch.empty((self.ntemps, self.nwalkers), dtype=torch.int32, device=self.dev)
-        self._n_acc = torch.zeros((max(self.ntemps - 1, 1),), dtype=torch.int32, device=self.dev)
-        self._betas_dev = self._upload(self.betas)
-        self.shard.warm_up(self.dev)
+        self._prefetched = None
+        if self.shard.world > 1:
+            torch.cuda.synchronize(self.dev)
+            self.shard.td.barrier(group=self.shard.group)  # peers may read this state from the first swap on
 
-    def _alloc_store(self, nsweeps):
-        """Make room for `nsweeps` more stored samples (capacity grows geometrically so repeated
+    def _alloc_hist(self, nsweeps):
+        """Room for `nsweeps` more rows of the per-sweep histories (device; capacity grows geometrically)."""
+        torch = self.torch
+        need = self.iteration + nsweeps
+        if need <= self._hist_cap:
+            return
+        cap = max(need, 2 * self._hist_cap, 16)
+        T, Tl = self.ntemps, self.shard.n_local
+        new = [torch.zeros((cap, T), dtype=torch.float64, device=self.dev),
+               torch.zeros((cap, max(T - 1, 1)), dtype=torch.int32, device=self.dev),
+               torch.zeros((cap, Tl), dtype=torch.float64, device=self.dev)]
+        if self._beta_hist is not None and self.iteration:
+            for dst, srcb in zip(new, (self._beta_hist, self._nacc_hist, self._smd_hist)):
+                dst[: self.iteration].copy_(srcb[: self.iteration])
+        self._beta_hist, self._nacc_hist, self._smd_hist = new
+        self._hist_cap = cap
+
+    def _alloc_store(self, nsamples):
+        """Make room for `nsamples` more stored samples (capacity grows geometrically so repeated
         run_mcmc calls do not re-allocate and copy the chain every time)."""
         torch = self.torch
-        n = (nsweeps + self.thin_by - 1) // self.thin_by
         Tl, W, nd = self.shard.n_local, self.nwalkers, self.ndim
         if self.store == "device":
             dev, pin = self.dev, False
@@ -126,9 +237,7 @@ class PTSampler:
         else:
             self._chain = None
             return
-        if self._chain is None:
-            self._stored = 0
-        need = self._stored + n
+        need = self._stored + nsamples
         cap = 0 if self._chain is None else self._chain.shape[0]
         if need <= cap:
             return
@@ -139,20 +248,39 @@ class PTSampler:
         new = [torch.empty((new_cap, Tl, W, nd), **kw), torch.empty((new_cap, Tl, W), **kw),
                torch.empty((new_cap, Tl, W), **kw)]
         if self._chain is not None and self._stored:
-            for dst, src in zip(new, (self._chain, self._ll, self._lp)):
-                dst[: self._stored].copy_(src[: self._stored])
+            torch.cuda.synchronize(self.dev)
+            for dst, srcb in zip(new, (self._chain, self._ll, self._lp)):
+                dst[: self._stored].copy_(srcb[: self._stored])
         self._chain, self._ll, self._lp = new
+
+    def _alloc_ring(self, nsteps):
+        """store='host': the device writes its samples into a small ring that a copy stream drains into the
+        pinned host chain one sweep behind the compute stream (C5 produces 147 MB per step: nothing of the
+        chain accumulates in HBM)."""
+        torch = self.torch
+        m = (nsteps + self.thin_by - 1) // self.thin_by + 1
+        slots = 2 * m
+        if self._ring is not None and self._ring[0].shape[0] == slots:
+            return
+        torch.cuda.synchronize(self.dev)
+        Tl, W, nd = self.shard.n_local, self.nwalkers, self.ndim
+        kw = dict(dtype=torch.float64, device=self.dev)
+        self._ring = [torch.empty((slots, Tl, W, nd), **kw), torch.empty((slots, Tl, W), **kw),
+                      torch.empty((slots, Tl, W), **kw)]
+        self._copy_stream = torch.cuda.Stream(device=self.dev)
+        self._copy_done = []   # (sweep index, event) of the ring drains still worth waiting for
 
     # ------------------------------------------------------------------------------
     def stage_draws(self, draws: SweepDraws, pinned: bool = False):
         """Copy one sweep's draws to the device (async on the current stream).  `draws` holds the
-        stretch draws of THIS rank's temperatures and the swap draws of the whole ladder.
-        pinned=True packs all seven arrays into one reusable pinned staging buffer and issues a
-        single H2D copy (double-buffered: the previous sweep may still be reading its draws)."""
+        stretch draws of THIS rank's temperatures and the swap draws of the whole ladder (or, sharded, of
+        this rank's pairs).  pinned=True packs all seven arrays into one reusable pinned staging buffer and
+        issues a single H2D copy (double-buffered: the previous sweep may still be reading its draws)."""
         torch = self.torch
         fields = [(f, getattr(draws, f)) for f in SweepDraws.FIELDS
                   if not (f in ("perm", "lnu_swap") and self.ntemps < 2)]
         out = {f: None for f in SweepDraws.FIELDS}
+        out["sharded_swap"] = draws.sharded_swap
         if not pinned:
             for f, a in fields:
                 out[f] = torch.from_numpy(np.ascontiguousarray(a)).to(self.dev, non_blocking=True)
@@ -161,13 +289,16 @@ class PTSampler:
         for f, a in fields:
             offs.append(total)
             total += (a.nbytes + 255) // 256 * 256
-        if getattr(self, "_stage_cap", 0) < total:
+        if getattr(self, "_stage_cap", 0) != total:
+            torch.cuda.synchronize(self.dev)
             self._stage_host = [torch.empty(total, dtype=torch.uint8).pin_memory() for _ in range(2)]
             self._stage_dev = [torch.empty(total, dtype=torch.uint8, device=self.dev) for _ in range(2)]
-            self._stage_evt = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_evt = [torch.cuda.Event(), torch.cuda.Event()]   # H2D of buffer i finished
             self._stage_cap, self._stage_i = total, 0
         i = self._stage_i = 1 - self._stage_i
-        self._stage_evt[i].synchronize()  # the H2D that last used this pinned buffer has finished
+        # the H2D that last used this pinned buffer has finished (this also keeps the host at most two sweeps
+        # ahead of the device: that copy is stream-ordered behind the sweep before it)
+        self._stage_evt[i].synchronize()
         host, dev = self._stage_host[i], self._stage_dev[i]
         hv = host.numpy()
         for (f, a), o in zip(fields, offs):
@@ -177,34 +308,129 @@ class PTSampler:
         for (f, a), o in zip(fields, offs):
             tdt = torch.int32 if a.dtype == np.int32 else torch.float64
             out[f] = dev[o:o + a.nbytes].view(tdt).view(a.shape)
+        out["_stage_index"] = i
         return out
 
+    def _sweep_args(self, draws, nsteps):
+        """The EmpPtSweep argument block of one sweep (include/emperor_b200.h)."""
+        sh = self.shard
+        A = _lib.EmpPtSweepC()
+        A.T_loc, A.W, A.nsteps, A.T_all = sh.n_local, self.nwalkers, nsteps, self.ntemps
+        A.n_ranks, A.rank, A.strided = sh.world, sh.rank, 1 if sh.layout == "strided" else 0
+        # graphs are keyed on the argument block: only the double-buffered pinned staging repeats its pointers
+        A.use_graph = 1 if (self.graph and sh.world == 1 and draws.get("_stage_index") is not None) else 0
+        cur, alt = self._state[self._par], self._state[1 - self._par]
+        A.p, A.logl, A.logp = cur[0].data_ptr(), cur[1].data_ptr(), cur[2].data_ptr()
+        A.p_alt, A.logl_alt, A.logp_alt = alt[0].data_ptr(), alt[1].data_ptr(), alt[2].data_ptr()
+        A.betas = self._betas_dev.data_ptr()
+        for f in ("half_idx", "zz", "rint", "factors", "lnu"):
+            setattr(A, f, draws[f].data_ptr())
+        A.accepted, A.n_accepted = self.accepted.data_ptr(), self._n_accepted.data_ptr()
+        A.src, A.n_acc = self._src.data_ptr(), self._n_acc.data_ptr()
+        A.adapt = 1 if (self.adapt and self.ntemps > 2) else 0
+        A.thin = self.thin_by
+        A.adapt_tau, A.adapt_nu = float(self.adapt_tau), float(self.adapt_nu)
+        A.sweep_counter = self._counters[0:].data_ptr()
+        A.step_counter = self._counters[1:].data_ptr()
+        A.beta_hist = self._beta_hist.data_ptr()
+        A.nacc_hist = self._nacc_hist.data_ptr() if self.ntemps > 1 else None
+        A.hist_cap = self._hist_cap
+        if self.smd_history_bool and self.D_ is not None and self.ntemps > 1:
+            if self._D_dev is None or self._D_dev.shape[0] != self.ndim:
+                self._D_dev = self._upload(np.asarray(self.D_, dtype=np.float64))
+            A.D, A.smd_hist = self._D_dev.data_ptr(), self._smd_hist.data_ptr()
+        if self._chain is not None:
+            tgt = self._ring if self.store == "host" else (self._chain, self._ll, self._lp)
+            A.chain, A.chain_ll, A.chain_lp = tgt[0].data_ptr(), tgt[1].data_ptr(), tgt[2].data_ptr()
+            A.store_cap = tgt[0].shape[0]
+            A.store_ring = 1 if self.store == "host" else 0
+        return A
+
     def sweep_begin(self, draws):
-        """Enqueue nsteps stretch steps of every local temperature + one swap sweep (asynchronous).
+        """Enqueue one whole sweep: nsteps stretch steps of every local temperature, the swap sweep, the ladder
+        adaptation, histories and chain store (asynchronous; nothing here waits for the device).
         `draws`: SweepDraws (host) or the dict `stage_draws` returned (already on the device)."""
-        eng = self.engine
-        sl = self.shard.local_slice
+        torch, eng, sh = self.torch, self.engine, self.shard
         if isinstance(draws, SweepDraws):
             t0 = _time.perf_counter()
             draws = self.stage_draws(draws)
             self.timings["h2d"] += _time.perf_counter() - t0
-        nsteps = draws["zz"].shape[0]
-        betas_loc = self._betas_dev[sl].contiguous()
+        nsteps = int(draws["zz"].shape[0])
+        self._alloc_hist(1)
+        # storage bookkeeping (the device counts the same way: sample n is stored when n % thin == 0)
+        n0 = self._n_steps
+        stored_now = [n for n in range(n0, n0 + nsteps) if n % self.thin_by == 0]
+        if self._chain is not None:
+            if self.store == "host":
+                self._alloc_ring(nsteps)
+                # the ring slots this sweep overwrites were drained two sweeps ago at the latest
+                while self._copy_done and self._copy_done[0][0] <= self.iteration - 2:
+                    torch.cuda.current_stream(self.dev).wait_event(self._copy_done.pop(0)[1])
+            if self._stored + len(stored_now) > self._chain.shape[0]:
+                self._alloc_store(max(len(stored_now), 1))
         self._mark("start")
-        for s in range(nsteps):
-            eng.pt_stretch_step(self.p, self.logl, self.logp, betas_loc, draws["half_idx"][s], draws["zz"][s],
-                                draws["rint"][s], draws["factors"][s], draws["lnu"][s], self.accepted)
-            self._n_accepted += self.accepted
-            self._n_steps += 1
-        self._swap_draws = None
         if self.ntemps > 1:
             perm, lnu_swap = draws["perm"], draws["lnu_swap"]
-            if self.shard.world > 1 and perm.shape[0] == self.shard.n_local:
+        A = self._sweep_args(draws, nsteps)
+        if sh.world == 1:
+            if self.ntemps > 1:
+                A.perm, A.lnu_swap = perm.data_ptr(), lnu_swap.data_ptr()
+            eng.pt_sweep(A)
+            self._mark("sweep")
+        else:
+            eng.pt_sweep_stretch(A)
+            self._mark("stretch")
+            if draws.get("sharded_swap"):
                 # every rank replays the whole plan: gather the pair rows (NCCL, behind the stretch kernels)
-                perm = self.shard.all_gather_rows(perm)[: self.ntemps - 1]
-                lnu_swap = self.shard.all_gather_rows(lnu_swap)[: self.ntemps - 1]
-            self._swap_draws = (perm, lnu_swap)
-        self._mark("stretch")
+                perm = sh.all_gather_rows(perm)[: self.ntemps - 1].contiguous()
+                lnu_swap = sh.all_gather_rows(lnu_swap)[: self.ntemps - 1].contiguous()
+            logl_all = sh.all_gather_rows(self.logl).contiguous()  # [T, W] in ladder order
+            self._mark("allgather")
+            A.perm, A.lnu_swap, A.logl_all = perm.data_ptr(), lnu_swap.data_ptr(), logl_all.data_ptr()
+            self._peer_pointers(A)
+            eng.pt_sweep_swap(A)
+            self._keep = (perm, lnu_swap, logl_all)
+            self._mark("swap")
+        if self.ntemps > 1:
+            self._par = 1 - self._par
+            self.p, self.logl, self.logp = self._state[self._par]
+        # host mirror of the device counters
+        self._n_steps += nsteps
+        first = self._stored
+        self._stored += len(stored_now) if self._chain is not None else 0
+        self._sample_sweep += [self.iteration] * (len(stored_now) if self._chain is not None else 0)
+        if self._chain is not None and self.store == "host" and stored_now:
+            ev = torch.cuda.Event()
+            ev.record()
+            slots = self._ring[0].shape[0]
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(ev)
+                for k, n in enumerate(stored_now):
+                    s = (n // self.thin_by) % slots
+                    for dst, ring in zip((self._chain, self._ll, self._lp), self._ring):
+                        dst[first + k].copy_(ring[s], non_blocking=True)
+                done = torch.cuda.Event()
+                done.record()
+            self._copy_done.append((self.iteration, done))
+        self.time += 1
+        self.iteration += 1
+        self._betas_stale = self._betas_stale or bool(A.adapt)
+
+    def _peer_pointers(self, A):
+        """Where the swap finds the CURRENT (p | logl | logp) block of every rank: peer HBM mapped with CUDA IPC
+        (exchange='peer': only the rows a rank receives cross NVLink), or, with exchange='allgather' (the fallback
+        for platforms without CUDA IPC), one NCCL all-gather of the blocks into a scratch buffer, read by the same
+        kernel through the same pointer table."""
+        sh = self.shard
+        nd, n_row = self.ndim, sh.n_local * self.nwalkers
+        if self.exchange == "peer":
+            bases = [self._peer_blocks[self._par][r].ptr for r in range(sh.world)]
+        else:
+            blk = self._blocks[self._par]
+            self._gathered = sh.all_gather_flat(blk)[0]
+            bases = [self._gathered.data_ptr() + r * blk.numel() * 8 for r in range(sh.world)]
+        for r, base in enumerate(bases):
+            A.peer_p[r], A.peer_logl[r], A.peer_logp[r] = base, base + n_row * nd * 8, base + n_row * (nd + 1) * 8
 
     def _mark(self, name):
         """Optional device-side phase timing (self.profile = True): CUDA events on the stream, read
@@ -227,74 +453,17 @@ class PTSampler:
         return out
 
     def sweep_end(self):
-        """Swap sweep of the sweep begun last (all-gather of logL when sharded, plan, row exchange),
-        then the ladder adaptation on the host from the T-1 swap counts (like the oracle:
-        bit-identical beta history).  Everything that synchronises with the device lives here so
-        that the caller can do host work (next sweep's draws) between sweep_begin and sweep_end."""
-        n_acc = None
-        if self._swap_draws is not None:
-            perm, lnu_swap = self._swap_draws
-            self._mark("host_gap")  # device idle time while the host was busy between begin and end
-            logl_all = self.shard.all_gather_rows(self.logl)  # [T, W]; NCCL all-gather when sharded
-            self._mark("allgather")
-            self.engine.pt_swap_plan(logl_all, self._betas_dev, perm, lnu_swap, self._src, self._n_acc)
-            self._mark("plan")
-            self._apply_plan()
-            self._mark("apply")
-            if self.smd_history_bool and self.D_ is not None:
-                self._record_smd()
-            if not hasattr(self, "_n_acc_host"):
-                self._n_acc_host = self.torch.empty(self._n_acc.shape, dtype=self.torch.int32).pin_memory()
-            self._n_acc_host.copy_(self._n_acc, non_blocking=True)  # 4*(T-1) bytes
-            self.torch.cuda.current_stream(self.dev).synchronize()
-            n_acc = self._n_acc_host.numpy()[: self.ntemps - 1].copy()
-        self.time += 1
-        self.iteration += 1
-        if n_acc is not None:
-            ratios = n_acc / self.nwalkers
-            if self.tsw_history_bool:
-                self._tsw_hist.append(ratios)
-            if self.adapt and self.ntemps > 2:
-                self.betas = _adapt_ladder(self.betas, ratios, self.time, self.adapt_tau, self.adapt_nu)
-                self._betas_dev = self._upload(self.betas)
-        self._beta_hist.append(self.betas.copy())
-        return n_acc
+        """Swap counts of the sweep begun last (synchronises: tests and diagnostics only — run_mcmc never
+        calls this; the histories stay on the device until somebody asks for them)."""
+        if self.ntemps < 2:
+            return None
+        self.torch.cuda.current_stream(self.dev).synchronize()
+        return self._n_acc.cpu().numpy()[: self.ntemps - 1].copy()
 
     def sweep(self, draws):
-        """One full sweep: stretch steps + swap sweep + ladder adaptation."""
+        """One full sweep: stretch steps + swap sweep + ladder adaptation; returns the swap counts."""
         self.sweep_begin(draws)
         return self.sweep_end()
-
-    def _apply_plan(self):
-        eng, sh = self.engine, self.shard
-        if sh.world == 1:
-            eng.pt_gather_rows(self._src.view(-1), self.p.view(-1, self.ndim), self.logl.view(-1),
-                               self.logp.view(-1), self._p_alt.view(-1, self.ndim), self._ll_alt.view(-1),
-                               self._lp_alt.view(-1))
-        elif self.exchange == "p2p":
-            # point-to-point exchange of exactly the rows that change rank (dist.exchange_rows)
-            rows = self.torch.cat([self.p.view(-1, self.ndim), self.logl.view(-1, 1), self.logp.view(-1, 1)], 1)
-            staged, src_local = sh.exchange_rows(self._src, rows, self.nwalkers)
-            pin = staged[:, : self.ndim].contiguous()
-            llin = staged[:, self.ndim].contiguous()
-            lpin = staged[:, self.ndim + 1].contiguous()
-            eng.pt_gather_rows(src_local, pin, llin, lpin, self._p_alt.view(-1, self.ndim),
-                               self._ll_alt.view(-1), self._lp_alt.view(-1))
-        else:
-            # all-gather the ensemble over NVLink and gather locally: no host synchronisation, no
-            # index compaction; T*W*(ndim+2)*8 bytes per sweep (150 MB at 256 x 2048 x 35, ~0.3 ms
-            # of NVSwitch all-gather) buys back ~1.5 ms of latency-bound list building
-            W, nl = self.nwalkers, sh.n_local * self.nwalkers
-            p_all, ll_all, lp_all = sh.all_gather_flat(self.p.view(-1, self.ndim), self.logl.view(-1),
-                                                       self.logp.view(-1))
-            sg = self._src[sh.local_slice].reshape(-1).to(self.torch.int64)
-            st, sw = sg // W, sg % W
-            pos = (sh.owner_of_temp(st) * nl + sh.local_of_temp(st) * W + sw).to(self.torch.int32)
-            eng.pt_gather_rows(pos, p_all, ll_all, lp_all, self._p_alt.view(-1, self.ndim),
-                               self._ll_alt.view(-1), self._lp_alt.view(-1))
-        self.p, self._p_alt = self._p_alt, self.p
-        self.logl, self._ll_alt = self._ll_alt, self.logl
-        self.logp, self._lp_alt = self._lp_alt, self.logp
 
     def draw(self, nsteps: int) -> SweepDraws:
         """Host draws of one sweep for this rank (draws.py)."""
@@ -308,13 +477,20 @@ class PTSampler:
         """sampler.run_mcmc(p1, nsweeps=, nsteps=, progress=) (support/endit_reddemcee.scr:3).
         While the device runs sweep k the host generates the draws of sweep k+1 (same thread: a
         background thread only fights the main thread for the GIL and stalls the launches);
-        they are staged through a reusable pinned buffer.  `on_sweep(sampler, k)` is called after
-        every sweep (bench.py uses it to read logL back)."""
+        they are staged through a reusable pinned buffer.  Nothing synchronises with the device until
+        the run is over.  Every stretch step is a stored sample (thin_by permitting): the chain of a run
+        holds nsweeps*nsteps samples like reddemcee's, the tsw / smd / beta histories one row per sweep.
+        `on_sweep(sampler, k)` is called after every sweep was enqueued (bench.py reads logL back there).
+        Returns a `State`; pass it back (or None) to continue, or new positions to restart from them."""
+        if isinstance(p0, State) and p0._sampler_id == id(self) and p0._iteration == self.iteration:
+            p0 = None
         if p0 is not None:
-            self._init_state(p0)
-        elif not hasattr(self, "p"):
+            self._init_state(np.asarray(p0.coords if isinstance(p0, State) else p0))
+        elif not hasattr(self, "_state"):
             raise ValueError("first call needs initial positions")
-        self._alloc_store(nsweeps)
+        n_new = sum(1 for n in range(self._n_steps, self._n_steps + nsweeps * nsteps) if n % self.thin_by == 0)
+        self._alloc_store(n_new)
+        self._alloc_hist(nsweeps)
         it = range(nsweeps)
         if progress:
             try:
@@ -322,6 +498,7 @@ class PTSampler:
                 it = tqdm(it, total=nsweeps)
             except Exception:
                 pass
+
         def draw():
             t0 = _time.perf_counter()
             d = self.draw(nsteps)
@@ -330,7 +507,7 @@ class PTSampler:
 
         # the draws of the first sweep may already be staged: every call ends by drawing and staging one sweep
         # ahead (below), so that back-to-back calls — adaptation then production (support/endit_freeze1.scr),
-        # warm-up then measurement — do not pay the 5 ms pipeline fill again
+        # warm-up then measurement — do not pay the pipeline fill again
         staged, pre = None, getattr(self, "_prefetched", None)
         self._prefetched = None
         if nsweeps > 0:
@@ -338,22 +515,22 @@ class PTSampler:
         for k in it:
             self.sweep_begin(staged)
             # while the device runs this sweep the host draws the next one, packs it into the other pinned
-            # buffer and enqueues its H2D copy behind the stretch kernels (double-buffered on both sides), so
-            # nothing but the 4(T-1)-byte swap-count read sits between two sweeps
+            # buffer and enqueues its H2D copy (double-buffered on both sides)
             staged = self.stage_draws(draw(), pinned=True)
-            self.sweep_end()
-            if self._chain is not None and (k % self.thin_by == 0):
-                j = self._stored
-                self._chain[j].copy_(self.p, non_blocking=True)
-                self._ll[j].copy_(self.logl, non_blocking=True)
-                self._lp[j].copy_(self.logp, non_blocking=True)
-                self._stored += 1
             if on_sweep is not None:
                 on_sweep(self, k)
         if nsweeps > 0:
             self._prefetched = (nsteps, staged)
         self.torch.cuda.synchronize(self.dev)
-        return self.p
+        nan = self.engine.nan_count()
+        if nan > self._nan_seen:
+            warnings.warn(f"{nan - self._nan_seen} proposal(s) had a NaN log-likelihood and were rejected "
+                          "(emcee raises 'Probability function returned NaN' here)", RuntimeWarning)
+            self._nan_seen = nan
+        if self.backend_file:
+            self.save_backend(self.backend_file)
+        p, ll, lp = self.state_numpy()
+        return State(self, p, ll, lp)
 
     def select_adjustment(self, mode):
         """reddemcee's ladder-adjustment selector as EMPEROR drives it: `support/endit_freeze1.scr:10` calls
@@ -364,11 +541,18 @@ class PTSampler:
         self.adapt = False
 
     # ---- read-back API the reference's parent process uses --------
+    def _sync_store(self):
+        if self._ring is not None:
+            self._copy_stream.synchronize()
+        self.torch.cuda.synchronize(self.dev)
+
     def _get(self, buf, discard, thin, flat):
         if buf is None:
             raise RuntimeError("chain storage is disabled (store=None)")
+        self._sync_store()
         x = buf[: self._stored][discard::thin]
-        x = self.shard.gather_to_all(x, dim=1) if self.shard.world > 1 else x
+        if self.shard.world > 1:
+            x = self.shard.gather_to_all(x.to(self.dev), dim=1)  # NCCL gathers device tensors only
         x = x.cpu().numpy()
         x = np.swapaxes(x, 0, 1)  # [T, n, W, ...]
         if flat:
@@ -381,44 +565,47 @@ class PTSampler:
     def get_log_like(self, discard=0, thin=1, flat=False):
         return self._get(self._ll, discard, thin, flat)
 
+    def get_betas_sweeps(self):
+        """[n_sweeps, T] ladder after the adaptation of every sweep (device history)."""
+        if self._beta_hist is None:
+            return np.zeros((0, self.ntemps))
+        return self._beta_hist[: self.iteration].cpu().numpy()
+
+    def _betas_used(self):
+        """[n_sweeps, T] ladder in force DURING each sweep (the initial one, then the adapted ones)."""
+        bh = self.get_betas_sweeps()
+        return np.concatenate([self._betas_initial[None, :], bh[:-1]], 0) if len(bh) else bh
+
     def get_log_prob(self, discard=0, thin=1, flat=False):
-        """Tempered posterior beta*logL + logP per stored sample."""
+        """Tempered posterior beta*logL + logP per stored sample (beta: the ladder the sample was drawn under)."""
         ll = self._get(self._ll, discard, thin, False)
         lp = self._get(self._lp, discard, thin, False)
-        bh = np.array(self._beta_hist)[:: self.thin_by][discard::thin]  # [n, T]
-        out = bh.T[:, :, None] * ll + lp
+        bu = self._betas_used()[np.asarray(self._sample_sweep, dtype=np.int64)][discard::thin]  # [n, T]
+        out = bu.T[:, :, None] * ll + lp
         return out.reshape(out.shape[0], -1) if flat else out
 
     def get_log_prior(self, discard=0, thin=1, flat=False):
         return self._get(self._lp, discard, thin, flat)
 
     def get_betas(self, discard=0):
-        return np.array(self._beta_hist)[discard:]
+        """[n_samples, T]: per stored sample (EMPEROR discards in steps, emp.py:962), the ladder after the
+        adaptation of the sample's sweep — the ptemcee / reddemcee convention: the last row is `sampler.betas`."""
+        bh = self.get_betas_sweeps()
+        if not len(bh):
+            return np.zeros((0, self.ntemps))
+        return bh[np.asarray(self._sample_sweep, dtype=np.int64)][discard:]
 
     def get_tsw(self, discard=0):
-        return np.array(self._tsw_hist)[discard:]
-
-    def _record_smd(self):
-        """Swap mean distance of this sweep (consumers emp.py:961-965, 1985-1990): for every
-        temperature the mean, over the slots that received a walker from a hotter rung, of the
-        distance between the walker that left and the one that arrived, in units of the prior
-        widths `sampler.D_` (emp.py:595-602).  Device-side torch arithmetic on [T_loc, W, ndim]."""
-        torch, sh, W = self.torch, self.shard, self.nwalkers
-        if getattr(self, "_D_dev", None) is None or self._D_dev.shape[0] != self.ndim:
-            self._D_dev = self._upload(np.asarray(self.D_, dtype=np.float64))
-        src_t = self._src[sh.local_slice].to(torch.int64) // W                      # [T_loc, W]
-        dest_t = torch.arange(self.ntemps, device=self.dev)[sh.local_slice].unsqueeze(1)
-        came_down = src_t > dest_t
-        dist = (((self.p - self._p_alt) / self._D_dev) ** 2).sum(-1).sqrt()           # new vs old content
-        num = (dist * came_down).sum(1)
-        cnt = came_down.sum(1).clamp(min=1)
-        self._smd_hist.append(num / cnt)
+        """[n_sweeps, T-1] swap acceptance ratio of every adjacent pair, per sweep."""
+        if self._nacc_hist is None or self.ntemps < 2 or not self.tsw_history_bool:
+            return np.zeros((0, max(self.ntemps - 1, 0)))
+        return (self._nacc_hist[: self.iteration].cpu().numpy() / self.nwalkers)[discard:]
 
     def get_smd(self, discard=0):
         """[n_sweeps, T-1] swap mean distances (rung j <-> j+1); needs `sampler.D_`."""
-        if not self._smd_hist:
+        if self._smd_hist is None or self.D_ is None or not self.smd_history_bool or self.ntemps < 2:
             return np.zeros((0, max(self.ntemps - 1, 0)))
-        x = self.torch.stack(self._smd_hist)                                         # [n, T_loc]
+        x = self._smd_hist[: self.iteration]                                       # [n, T_loc]
         x = self.shard.gather_to_all(x, dim=1) if self.shard.world > 1 else x
         return x.cpu().numpy()[discard:, : self.ntemps - 1]
 
@@ -433,7 +620,7 @@ class PTSampler:
         """(p, logl, logp) of the whole ladder as NumPy arrays."""
         p, ll, lp = self.p, self.logl, self.logp
         if self.shard.world > 1:
-            p, ll, lp = (self.shard.gather_to_all(x, dim=0) for x in (p, ll, lp))
+            p, ll, lp = (self.shard.gather_to_all(x.contiguous(), dim=0) for x in (p, ll, lp))
         return p.cpu().numpy(), ll.cpu().numpy(), lp.cpu().numpy()
 
     # ---- post-run reductions (emp.py:1375-1385, 1432-1447; host NumPy, postproc.py) ----------
@@ -449,12 +636,11 @@ class PTSampler:
         return evidence_ss(self.get_log_like(discard=discard), self.betas)
 
     def get_evidence_hybrid(self, discard=0, pchip=False):
-        """reddemcee's 'hybrid' estimator is not recoverable offline: this returns the
-        stepping-stone value with the TI/SS discrepancy added in quadrature to its error."""
-        z_ss, e_ss = self.get_evidence_ss(discard=discard)
-        z_ti, e_ti = self.get_evidence_ti(discard=discard, pchip=pchip)
-        err = float(np.sqrt(np.nan_to_num(e_ss) ** 2 + (z_ss - z_ti) ** 2))
-        return z_ss, err
+        """reddemcee's 'hybrid' estimator is NOT recoverable offline (the package is not vendored): this raises
+        so that EMPEROR's own fallback chain takes over — emp.py:1432-1447 wraps the call in try/except and
+        falls back to `get_evidence_ti(..., pchip=False)`.  Ask for 'ss' or 'ti' explicitly instead."""
+        raise NotImplementedError("reddemcee's hybrid evidence estimator is not available; use "
+                                  "evidence_method 'ss' or 'ti' (EMPEROR falls back to TI by itself)")
 
     def get_autocorr_time(self, discard=0, thin=1, quiet=False, tol=50, c=5):
         """[T, ndim] integrated autocorrelation times of the stored chains (emcee's estimator),
@@ -485,7 +671,7 @@ class _TemperatureBackend:
 
     @property
     def iteration(self):
-        return self._v.iteration
+        return self._v.nsamples
 
     def get_chain(self):
         return self._v._chain[self._t]          # [iteration, W, ndim]
@@ -509,9 +695,10 @@ class _BackendView:
         self._chain = s.get_chain()
         self._ll = s.get_log_like()
         self._lpost = s.get_log_prob()
-        self._betas = s.get_betas()[:: s.thin_by]
+        self._betas = s.get_betas()
         self._accepted = np.rint(s.acceptance_fraction * max(s._n_steps, 1)).astype(np.int64)
-        self.iteration = self._chain.shape[1]
+        self.iteration = s.iteration            # sweeps: rows of tsw_history / smd_history (emp.py:733-745)
+        self.nsamples = self._chain.shape[1]    # stored samples = stretch steps: backend[t].iteration (emp.py:748)
         self.ntemps = s.ntemps
         self.tsw_history_bool, self.smd_history_bool = s.tsw_history_bool, s.smd_history_bool
         self.tsw_history = s.get_tsw()
@@ -527,9 +714,10 @@ class _BackendView:
 
 
 def _adapt_ladder(betas, ratios, time, adapt_tau, adapt_nu):
-    """Vousden, Farr & Mandel (2016) ladder dynamics in reddemcee's (adapt_tau, adapt_nu)
-    parameterisation; same arithmetic as oracle/pt_oracle.py::adapt_ladder."""
-    betas = betas.copy()
+    """Host restatement of the device ladder adaptation (emp_pt.cuh::plan_tail): Vousden, Farr & Mandel (2016)
+    dynamics in reddemcee's (adapt_tau, adapt_nu) parameterisation.  Kept for StoredRun / diagnostics; the
+    sampler itself adapts on the device."""
+    betas = np.array(betas, dtype=np.float64)
     decay = adapt_tau / (time + adapt_tau)
     kappa = decay / adapt_nu
     dSs = kappa * (ratios[:-1] - ratios[1:])

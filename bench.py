@@ -4,26 +4,34 @@
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path
 
-Metric (BASELINE.json): logL evals/sec x datapoints = walkers x temps x datapoints / s.
+Metric (BASELINE.json): logL evals/sec x datapoints = walkers x temps x datapoints / s, counting only
+likelihoods that are really EVALUATED: a proposal outside the prior support is rejected without an
+evaluation (emcee semantics), on the GPU and in the reference alike, so it is not counted
+(`value_nominal` keeps the every-proposal figure; the CPU arm evaluates 100 % of what it is given).
 Workload (config.workload): BASELINE configs[3] — synthetic 5-planet RV, 4 instruments +
 global MA(1) noise, 10 000 points, 32 temperatures x 2048 walkers per GPU (weak scaling: N
 GPUs hold 32*N temperatures, interleaved over the ranks, swap sweep every step).
 
 A "step" is one parallel-tempering sweep with nsteps=1: red/blue stretch move of every walker
-of every temperature (propose -> batched likelihood+prior -> accept, per half), the hot->cold
-temperature-swap sweep (logL all-gather over NCCL when N > 1) and the ladder adaptation.
+of every temperature (proposal + prior, batched likelihood + Metropolis accept, per half), the hot->cold
+temperature-swap sweep (logL all-gather over NCCL when N > 1), the ladder adaptation and the chain store —
+six kernel launches, no host synchronisation.
 
   value : all draws of the timed steps already resident in HBM when the clock starts.
-  e2e   : the user-level loop: draws generated on the host every step, staged in pinned
-          memory, copied H2D, the step, and a D2H read of logL[T,W] (+ swap counts).
+  e2e   : the user-level loop (PTSampler.run_mcmc): draws generated on the host every step, staged in
+          pinned memory, copied H2D, the step (replayed from a CUDA graph), the chain streamed to pinned
+          host memory and a D2H read of logL[T,W].
   roofline : the likelihood kernel, timed per launch with CUDA events inside the timed region,
           algorithmic FP64 flops F(K) = 230 K + 30 (+25 MA) per walker-datapoint (SURVEY.md §8d
-          row D4) against the FP64 FMA peak measured in the same run (emp_fp64_peak).
+          row D4) against the FP64 FMA peak measured in the same run (emp_fp64_peak); plus the
+          executed-instruction figures of the committed ncu capture (profiles/kernel_ncu.json).
   cpu_baseline : the oracle (NumPy port of the generated script + C Kepler solver), one call per
           walker through multiprocessing.Pool(all cores) like support/pools/01.pool, on a
-          bounded sample of the same workload.
+          bounded sample of the same workload; plus the single-core rate.
+  configs : short legs of the other BASELINE configs (c1, c2, c3; c5 with 8 GPUs), each next to its CPU rate.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -37,35 +45,90 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 WORKLOADS = {
-    # name: (seed, N, nins, K, ma_global, parameterisation, T per GPU, W)
+    # synthetic: (seed, N, nins, K, MA, parameterisation); golden: real data shipped as a test fixture
+    "c1": dict(golden="c1_51peg_k1_p0", kplan=1, ma=None, T=2, W=100,
+               desc="BASELINE configs[0]: 51Peg RV (256 points), 1 Keplerian, reddemcee setup [2,100,500,1]"),
+    "c2": dict(seed=2, n=2000, nins=2, kplan=3, ma=None, param=1, T=10, W=512,
+               desc="BASELINE configs[1]: synthetic 3-planet RV, 2 instruments with jitter, 2k points, "
+                    "10 temps x 512 walkers"),
+    "c3": dict(golden="c3_hip21850_am_k2", kplan=2, ma=None, T=11, W=256,
+               desc="BASELINE configs[2]: HIP21850 joint RV (97 points) + Hipparcos-Gaia astrometry (148 epochs), "
+                    "2 Keplerians, 11 temps x 256 walkers"),
     "c4": dict(seed=4, n=10000, nins=4, kplan=5, ma="global", param=0, T=32, W=2048,
                desc="BASELINE configs[3]: synthetic 5-planet RV, 4 instruments + MA(1) (global recurrence), "
                     "10k points, 32 temps x 2048 walkers per GPU"),
     "c4noop": dict(seed=4, n=10000, nins=4, kplan=5, ma="perins", param=0, T=32, W=2048,
                    desc="configs[3] with the reference's default per-instrument MA template (no-op on logL)"),
-    "c2": dict(seed=2, n=2000, nins=2, kplan=3, ma=None, param=1, T=10, W=512,
-               desc="BASELINE configs[1]: synthetic 3-planet RV, 2 instruments with jitter, 2k points, "
-                    "10 temps x 512 walkers"),
     "c5": dict(seed=5, n=50000, nins=4, kplan=5, ma=None, param=0, T=8, W=8192,
                desc="BASELINE configs[4]: 5 Keplerians, 50k points, 8 temps x 8192 walkers per GPU"),
     "tiny": dict(seed=1, n=400, nins=2, kplan=2, ma="global", param=0, T=2, W=64, desc="smoke-sized"),
 }
+UNIT = "walker*temp*datapoint/s"
+METRIC = "logL evals/sec (walkers x temps x datapoints / s)"
 
 
 def flops_per_point(kplan, ma):
     return 230.0 * kplan + 30.0 + (25.0 if ma == "global" else 0.0)
 
 
-def build_workload(name):
-    from astroemperor_b200.data import from_instrument_tables
-    from astroemperor_b200.frontend import default_spec
-    from astroemperor_b200.synth import make_synthetic_rv
-    w = WORKLOADS[name]
-    data = from_instrument_tables(make_synthetic_rv(seed=w["seed"], n=w["n"], nins=w["nins"], kplan=w["kplan"],
-                                                    ma=w["ma"] is not None))
-    moav = None if w["ma"] is None else {"order": 1, "global": w["ma"] == "global"}
-    spec = default_spec(data, kplan=w["kplan"], parameterisation=w["param"], moav=moav)
-    return w, data, spec
+class Workload:
+    """Data + model of one BASELINE config."""
+
+    def __init__(self, name):
+        w = dict(WORKLOADS[name])
+        self.name, self.w, self.am = name, w, None
+        if "golden" in w:
+            from astroemperor_b200.modelspec import ModelSpec
+            d = os.path.join(REPO, "tests", "golden")
+            g = np.load(os.path.join(d, w["golden"] + ".npz"))
+            self.spec = ModelSpec.from_json(open(os.path.join(d, w["golden"] + ".json")).read())
+            self.t, self.y, self.yerr, self.flag = g["t"], g["y"], g["yerr"], g["flag"]
+            if any(k.startswith("am_") for k in g.files):
+                self.am = {k[3:]: g[k] for k in g.files if k.startswith("am_")}
+            w["n"] = len(self.t)
+            w["nins"] = int(self.flag.max())
+        else:
+            from astroemperor_b200.data import from_instrument_tables
+            from astroemperor_b200.frontend import default_spec
+            from astroemperor_b200.synth import make_synthetic_rv
+            data = from_instrument_tables(make_synthetic_rv(seed=w["seed"], n=w["n"], nins=w["nins"], kplan=w["kplan"],
+                                                            ma=w["ma"] is not None))
+            moav = None if w["ma"] is None else {"order": 1, "global": w["ma"] == "global"}
+            self.spec = default_spec(data, kplan=w["kplan"], parameterisation=w["param"], moav=moav)
+            self.t, self.y, self.yerr, self.flag = data.t, data.y, data.yerr, data.flag
+        self.n = int(w["n"])
+        # data points one likelihood evaluation touches (the unit of the metric): RV points (+ IAD epochs)
+        self.n_units = self.n + (len(self.am["time_hipp"]) + len(self.am["time_gost"]) if self.am else 0)
+
+    def engine(self, device):
+        from astroemperor_b200.engine import LikelihoodEngine
+        return LikelihoodEngine(self.spec, self.t, self.y, self.yerr, self.flag, am=self.am, device=device)
+
+    def oracle(self):
+        """(theta) -> (logl, logp) the way the generated script computes them (oracle/, CPU)."""
+        from oracle.rv_oracle import RVOracle
+        cm = self.spec.compile()
+        ro = RVOracle(cm, self.t, self.y, self.yerr, self.flag)
+        ao = None
+        if self.am is not None:
+            from oracle.am_oracle import AMOracle
+            ao = AMOracle(cm, self.am)
+
+        def ev(theta):
+            lp = ro.my_prior(theta)
+            if lp == -np.inf:
+                return -np.inf, lp
+            ll = ro.my_likelihood(theta)
+            if ao is not None:
+                with np.errstate(all="ignore"):
+                    ll = float(ll + ao.loglike_AM(theta))
+            return ll, lp
+        return ev
+
+
+def build_workload(name):  # kept for scripts/ that import it
+    wl = Workload(name)
+    return wl.w, wl, wl.spec
 
 
 # ------------------------------------------------------------------ clocks ----
@@ -121,45 +184,249 @@ class ClockSampler:
 
 
 # -------------------------------------------------------------- CPU baseline ----
-_ORC = None
+_EV = None
+_ORACLE_LIB = None
 
 
 def _cpu_init(name):
-    global _ORC
-    from oracle.rv_oracle import RVOracle
-    w, data, spec = build_workload(name)
-    _ORC = RVOracle(spec.compile(), data.t, data.y, data.yerr, data.flag)
+    global _EV
+    _EV = Workload(name).oracle()
 
 
 def _cpu_eval(theta):
-    lp = _ORC.my_prior(theta)
-    if lp == -np.inf:
-        return -np.inf, lp
-    return _ORC.my_likelihood(theta), lp
+    return _EV(theta)
+
+
+def _worker_solver_lib(_):
+    """Which shared object the worker's Kepler solver comes from (proof of what the CPU arm ran)."""
+    out = [ln.split()[-1] for ln in open("/proc/self/maps") if "libemp_oracle" in ln]
+    return out[0] if out else None
 
 
 def valid_thetas(spec, n, seed=0):
-    """Walker positions with test_init semantics (emp.py:617-684): inside the prior support."""
+    """Walker positions with test_init semantics (emp.py:617-684): inside the prior support, i.e. the CPU arm
+    evaluates 100 % of what it is given — like for like with the GPU arm's count of EVALUATED likelihoods."""
     from astroemperor_b200.draws import initial_positions
     rng = np.random.RandomState(seed)
     return initial_positions(rng, spec, 1, n)[0]
 
 
 def cpu_baseline(name, n_eval, cores=None, repeats=1):
-    """Pool.map of the oracle's my_prior + my_likelihood over n_eval walkers (support/pools/01.pool)."""
+    """Pool.map of the oracle's my_prior + my_likelihood over n_eval walkers (support/pools/01.pool);
+    cores = 1: the same calls in this process, no pool."""
     import multiprocessing as mp
-    w, data, spec = build_workload(name)
+    wl = Workload(name)
     cores = cores or os.cpu_count()
-    th = valid_thetas(spec, n_eval, seed=123)
+    th = valid_thetas(wl.spec, n_eval, seed=123)
+    if cores == 1:
+        ev = wl.oracle()
+        ev(th[0])
+        t0 = time.perf_counter()
+        for x in th:
+            ev(x)
+        best = time.perf_counter() - t0
+        return dict(value=n_eval * wl.n_units / best, seconds=best, cores=1, n_eval=n_eval, solver_lib=None)
     ctx = mp.get_context("fork")
     with ctx.Pool(cores, initializer=_cpu_init, initargs=(name,)) as pool:
         pool.map(_cpu_eval, list(th[: cores]))  # warm the workers
+        libs = sorted({x for x in pool.map(_worker_solver_lib, range(cores)) if x})
         best = np.inf
         for _ in range(repeats):
             t0 = time.perf_counter()
             pool.map(_cpu_eval, list(th))
             best = min(best, time.perf_counter() - t0)
-    return dict(value=n_eval * w["n"] / best, seconds=best, cores=cores, n_eval=n_eval)
+    return dict(value=n_eval * wl.n_units / best, seconds=best, cores=cores, n_eval=n_eval,
+                solver_lib=libs[0] if libs else None)
+
+
+def cpu_block(name, budget_s, cores, single_core=True):
+    """cpu_baseline entry of one config: all-core Pool rate (+ single-core rate) on a sample sized for
+    ~budget_s seconds of wall time."""
+    wl = Workload(name)
+    ev = wl.oracle()
+    th = valid_thetas(wl.spec, 8, seed=7)
+    ev(th[0])
+    t0 = time.perf_counter()
+    for x in th[:4]:
+        ev(x)
+    per_call = (time.perf_counter() - t0) / 4
+    n_all = int(max(cores * 4, min(budget_s / per_call * cores * 0.6, 200000)))
+    cb = cpu_baseline(name, n_all, cores)
+    out = {"value": cb["value"], "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": f"{n_all} walkers x {wl.n_units} points of the same workload (all inside the prior support) "
+                     f"through multiprocessing.Pool({cores}) ({cb['seconds']:.1f} s)",
+           "ms_per_call_one_core": per_call * 1e3, "solver_lib": cb["solver_lib"]}
+    if single_core:
+        n_one = int(max(4, min(budget_s * 0.3 / per_call, 20000)))
+        c1 = cpu_baseline(name, n_one, 1)
+        out["single_core"] = {"value": c1["value"], "unit": UNIT, "cores": 1,
+                              "sample": f"{n_one} walkers, one process, no pool ({c1['seconds']:.1f} s)"}
+    return out
+
+
+# ------------------------------------------------------------------- GPU legs ----
+class Ctx:
+    def __init__(self):
+        import torch
+        import torch.distributed as td
+        self.torch, self.td = torch, td
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    def barrier(self):
+        if self.world > 1:
+            self.td.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device="cuda")
+        self.td.all_reduce(t, op=self.td.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device="cuda")
+        self.td.all_reduce(t, op=self.td.ReduceOp.SUM)
+        return float(t.item())
+
+    def gather(self, row):
+        if self.world == 1:
+            return [list(map(float, row))]
+        mine = self.torch.tensor(row, dtype=self.torch.float64, device="cuda")
+        allr = self.torch.empty((self.world, len(row)), dtype=self.torch.float64, device="cuda")
+        self.td.all_gather_into_tensor(allr, mine)
+        return allr.cpu().tolist()
+
+
+def make_sampler(cx, wl, total_sweeps=0, seed=2026, store="host", **kw):
+    from astroemperor_b200.sampler import PTSampler
+    eng = wl.engine(cx.local_rank)
+    T = wl.w["T"] * cx.world
+    samp = PTSampler(wl.w["W"], wl.spec.ndim, eng, ntemps=T, seed=seed, store=store, **kw)
+    samp.D_ = wl.spec.prior_widths()
+    p0 = samp.initial_positions(wl.spec) if cx.rank == 0 else None
+    if cx.world > 1:
+        obj = [p0]
+        cx.td.broadcast_object_list(obj, src=0)
+        p0 = obj[0]
+    samp._init_state(p0)
+    if total_sweeps:  # chain / history storage allocated up front: nothing is (re)allocated inside a timed region
+        samp._alloc_store(total_sweeps)
+        samp._alloc_hist(total_sweeps)
+    return eng, samp, T
+
+
+def run_e2e(cx, samp, eng, steps, T, W):
+    """The user's call: run_mcmc with host draws every sweep + D2H of logL[T_loc, W] every sweep (the chain
+    itself streams to pinned host memory behind the compute stream, store='host')."""
+    torch = cx.torch
+    ll_host = torch.empty((samp.shard.n_local, W), dtype=torch.float64).pin_memory()
+    io = {"d2h": 0}
+
+    def read_back(s, k):
+        ll_host.copy_(s.logl, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        io["d2h"] += ll_host.numel() * 8
+
+    samp.run_mcmc(None, nsweeps=2, nsteps=1, on_sweep=read_back)  # warm the staging buffers and the graphs
+    io["d2h"] = 0
+    draws_bytes = samp.draw(1).nbytes()
+    c0 = eng.counters()
+    cx.barrier()
+    te0 = time.perf_counter()
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ee0.record()
+    samp.run_mcmc(None, nsweeps=steps, nsteps=1, on_sweep=read_back)
+    samp._sync_store()
+    ee1.record()
+    cx.barrier()
+    te1 = time.perf_counter()
+    c1 = eng.counters()
+    ms = cx.max_over_ranks(max(ee0.elapsed_time(ee1), (te1 - te0) * 1e3))  # host-bound loops are wall-clock bound
+    chain_bytes = samp.shard.n_local * W * (samp.ndim + 2) * 8 if samp.store == "host" else 0
+    return dict(ms=ms, evaluated=cx.sum_over_ranks(c1["in_prior"] - c0["in_prior"]),
+                proposals=cx.sum_over_ranks(c1["proposals"] - c0["proposals"]),
+                h2d=draws_bytes, d2h=io["d2h"] // steps + chain_bytes)
+
+
+def run_leg(cx, name, steps, warmup, burn, cpu_budget):
+    """A short leg of another BASELINE config: device-side rate with pre-generated draws and the e2e rate."""
+    wl = Workload(name)
+    eng, samp, T = make_sampler(cx, wl, total_sweeps=burn + warmup + 2 * steps + 8)
+    W, N = wl.w["W"], wl.n_units
+    samp.run_mcmc(None, nsweeps=burn + warmup, nsteps=1)
+    # value: draws pre-generated on the host (no RNG in the timed region), staged through the pinned
+    # double buffer, sweeps replayed from the CUDA graph
+    pre = [samp.draw(1) for _ in range(steps)]
+    cx.barrier()
+    c0 = eng.counters()
+    l0 = eng.launch_count
+    ev0, ev1 = cx.torch.cuda.Event(enable_timing=True), cx.torch.cuda.Event(enable_timing=True)
+    tw0 = time.perf_counter()
+    ev0.record()
+    for d in pre:
+        samp.sweep_begin(samp.stage_draws(d, pinned=True))
+    ev1.record()
+    cx.barrier()
+    tw1 = time.perf_counter()
+    ms = cx.max_over_ranks(max(ev0.elapsed_time(ev1), 0.0))
+    c1 = eng.counters()
+    launches = eng.launch_count - l0
+    evaluated = cx.sum_over_ranks(c1["in_prior"] - c0["in_prior"])
+    proposals = cx.sum_over_ranks(c1["proposals"] - c0["proposals"])
+    samp._prefetched = None
+    e = run_e2e(cx, samp, eng, steps, T, W)
+    out = {"workload": wl.w["desc"], "ntemps": T, "nwalkers": W, "n_points": N, "ndim": wl.spec.ndim, "steps": steps,
+           "value": evaluated * N / (ms * 1e-3), "value_nominal": proposals * N / (ms * 1e-3), "unit": UNIT,
+           "ms_per_step": ms / steps, "evaluated_fraction": evaluated / max(proposals, 1),
+           "e2e": {"value": e["evaluated"] * N / (e["ms"] * 1e-3), "unit": UNIT, "ms_per_step": e["ms"] / steps,
+                   "h2d_bytes_per_step": e["h2d"], "d2h_bytes_per_step": e["d2h"]},
+           "e2e_over_value": (e["evaluated"] / e["ms"]) / (evaluated / ms),
+           "gpu_launches_per_step": launches / steps, "graph_captures": eng.graph_captures,
+           "host_wall_ms_per_step": (tw1 - tw0) * 1e3 / steps}
+    del samp
+    eng.close()
+    if cx.rank == 0 and cpu_budget > 0:
+        out["cpu_baseline"] = cpu_block(name, cpu_budget, os.cpu_count())
+    return out
+
+
+def dist_parity(cx):
+    """N > 1: a fixed small ladder run sharded over the ranks and unsharded on every rank must give the same
+    chains bit for bit (same seed -> same per-temperature draw streams)."""
+    td = cx.td
+    wl = Workload("tiny")
+    from astroemperor_b200.sampler import PTSampler
+    T, W, nsweeps, nsteps = 4 * cx.world, 64, 6, 2
+    eng = wl.engine(cx.local_rank)
+    samp = PTSampler(W, wl.spec.ndim, eng, ntemps=T, seed=77)
+    samp.D_ = wl.spec.prior_widths()
+    obj = [samp.initial_positions(wl.spec) if cx.rank == 0 else None]
+    td.broadcast_object_list(obj, src=0)
+    p0 = obj[0]
+    samp.run_mcmc(p0, nsweeps=nsweeps, nsteps=nsteps)
+    got = [samp.get_chain(), samp.get_log_like(), samp.get_betas(), samp.get_tsw(), samp.get_smd()]
+    solo_group = None
+    for r in range(cx.world):
+        grp = td.new_group([r])
+        if r == cx.rank:
+            solo_group = grp
+    solo = PTSampler(W, wl.spec.ndim, eng, ntemps=T, seed=77, group=solo_group)
+    solo.D_ = wl.spec.prior_widths()
+    solo.run_mcmc(p0, nsweeps=nsweeps, nsteps=nsteps)
+    ref = [solo.get_chain(), solo.get_log_like(), solo.get_betas(), solo.get_tsw(), solo.get_smd()]
+    same = all(np.array_equal(a, b) for a, b in zip(got[:4], ref[:4])) and np.allclose(got[4], ref[4], rtol=1e-12)
+    res = cx.torch.tensor([1 if same else 0], device="cuda")
+    td.all_reduce(res, op=td.ReduceOp.MIN)
+    h = hashlib.sha1(np.ascontiguousarray(got[0]).tobytes()).hexdigest()[:16]
+    del samp, solo
+    eng.close()
+    return {"dist_parity": bool(res.item() == 1), "chain_sha1": h, "ntemps": T, "nwalkers": W,
+            "sweeps": nsweeps, "nsteps": nsteps, "exchange": "peer"}
 
 
 # ------------------------------------------------------------------- main ----
@@ -172,12 +439,16 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-evals", type=int, default=0, help="walkers in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--legs", default="auto", help="comma list of extra configs to run after the main one "
+                    "(auto: c1,c2,c3 and c5 with 8 GPUs; none)")
     ap.add_argument("--solver", default="grid", choices=["grid", "kepler.py"],
                     help="Kepler solver of the likelihood kernel (A/B; the default is the product path)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "allgather"],
+                    help="sharded swap: rows read from the owners' HBM over NVLink (CUDA IPC), or NCCL all-gather")
     ap.add_argument("--burn", type=int, default=40,
                     help="untimed sweeps before the warm-up so that the ensemble has left its uniform "
                          "initial state (a young chain proposes ~40%% of its moves outside the prior box, "
-                         "which are never evaluated and would flatter the step time)")
+                         "which are never evaluated)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -196,36 +467,19 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         td.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from astroemperor_b200.engine import LikelihoodEngine, fp64_peak_tflops
-    from astroemperor_b200.sampler import PTSampler
+    from astroemperor_b200.engine import fp64_peak_tflops
+    cx = Ctx()
 
-    w, data, spec = build_workload(args.workload)
-    T, W, N, ndim = w["T"] * world, w["W"], w["n"], spec.ndim
-    eng = LikelihoodEngine(spec, data.t, data.y, data.yerr, data.flag, device=local_rank)
+    parity = dist_parity(cx) if world > 1 else None
+
+    wl = Workload(args.workload)
+    w, N = wl.w, wl.n_units
+    eng, samp, T = make_sampler(cx, wl, total_sweeps=args.burn + args.warmup + 2 * args.steps + 8,
+                                exchange=args.exchange)
+    W, ndim = w["W"], wl.spec.ndim
     eng.set_solver(args.solver)
-    samp = PTSampler(W, ndim, eng, ntemps=T, seed=2026, store="device")
-    p0 = samp.initial_positions(spec) if rank == 0 else None
-    if world > 1:
-        obj = [p0]
-        td.broadcast_object_list(obj, src=0)
-        p0 = obj[0]
-    samp._init_state(p0)
-    samp._alloc_store(2 * args.steps + args.warmup + 4)
-    for _ in range(args.burn):
-        samp.sweep(samp.draw(1))
+    samp.run_mcmc(None, nsweeps=args.burn, nsteps=1)
     peak_tf = fp64_peak_tflops(local_rank)
-
-    def barrier():
-        if world > 1:
-            td.barrier()
-        torch.cuda.synchronize()
-
-    def store():
-        j = samp._stored
-        samp._chain[j].copy_(samp.p, non_blocking=True)
-        samp._ll[j].copy_(samp.logl, non_blocking=True)
-        samp._lp[j].copy_(samp.logp, non_blocking=True)
-        samp._stored += 1
 
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -233,74 +487,50 @@ def main():
 
     # ---------------- value: draws resident in HBM -----------------------------------------
     for _ in range(args.warmup):
-        samp.sweep(samp.draw(1)); store()
+        samp.sweep_begin(samp.draw(1))
     staged = [samp.stage_draws(samp.draw(1)) for _ in range(args.steps)]
-    eng.set_timing(True)
+    eng.set_timing(True)   # per-launch events around the likelihood kernel (the sweep then runs un-graphed)
     samp.profile = True
     samp.phase_times()
     c0 = eng.counters()
     l0 = eng.launch_count
-    barrier()
+    cx.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.perf_counter()
     ev0.record()
     for k in range(args.steps):
-        samp.sweep(staged[k]); store()
+        samp.sweep_begin(staged[k])
     ev1.record()
-    barrier()
+    cx.barrier()
     tw1 = time.perf_counter()
-    ms = ev0.elapsed_time(ev1)
+    ms_local = ev0.elapsed_time(ev1)
     kern_ms, kern_n = eng.timing_collect()
     eng.set_timing(False)
     phases = samp.phase_times()
     samp.profile = False
     launches = eng.launch_count - l0
     c1 = eng.counters()
-    per_rank = [[ms, kern_ms, float(c1["in_prior"] - c0["in_prior"])]]
-    if world > 1:
-        mine = torch.tensor(per_rank[0], dtype=torch.float64, device="cuda")
-        allr = torch.empty((world, 3), dtype=torch.float64, device="cuda")
-        td.all_gather_into_tensor(allr, mine)
-        per_rank = allr.cpu().tolist()
-        ms = max(r[0] for r in per_rank)  # max over ranks
-    value = T * W * N * args.steps / (ms * 1e-3)
+    per_rank = cx.gather([ms_local, kern_ms, float(c1["in_prior"] - c0["in_prior"]),
+                          float(c1["proposals"] - c0["proposals"])])
+    ms = max(r[0] for r in per_rank)  # max over ranks
+    evaluated = sum(r[2] for r in per_rank)
+    proposals = sum(r[3] for r in per_rank)
+    value = evaluated * N / (ms * 1e-3)
+    value_nominal = proposals * N / (ms * 1e-3)
     del staged
+    samp._prefetched = None
 
     # ---------------- e2e: the user's call (PTSampler.run_mcmc) with host buffers -----------------
-    # every sweep: host RNG draws -> pinned staging -> H2D -> step -> D2H read of logL[T,W]
-    ll_host = torch.empty((samp.shard.n_local, W), dtype=torch.float64).pin_memory()
-    io = {"d2h": 0}
-
-    def read_back(s, k):
-        ll_host.copy_(s.logl, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        io["d2h"] += ll_host.numel() * 8 + 4 * (T - 1)
-
-    samp.run_mcmc(None, nsweeps=2, nsteps=1, on_sweep=read_back)  # warm the staging buffers / thread
-    io["d2h"] = 0
-    h2d = samp.draw(1).nbytes() * args.steps  # same size every sweep
-    barrier()
-    te0 = time.perf_counter()
-    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ee0.record()
-    samp.run_mcmc(None, nsweeps=args.steps, nsteps=1, on_sweep=read_back)
-    ee1.record()
-    barrier()
-    te1 = time.perf_counter()
-    d2h = io["d2h"]
-    e2e_ms = max(ee0.elapsed_time(ee1), (te1 - te0) * 1e3)  # host-bound loops are wall-clock bound
-    if world > 1:
-        tms = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-        td.all_reduce(tms, op=td.ReduceOp.MAX)
-        e2e_ms = float(tms.item())
-    e2e_value = T * W * N * args.steps / (e2e_ms * 1e-3)
+    e = run_e2e(cx, samp, eng, args.steps, T, W)
+    e2e_value = e["evaluated"] * N / (e["ms"] * 1e-3)
 
     # ---------------- the likelihood callable alone, host buffers (emp_logl_batch_host) -----------------
     # what an unmodified CPU sampler would call instead of Pool.map(my_likelihood): theta[n, ndim] in pageable
-    # host memory -> H2D -> prior + likelihood kernels -> D2H of logL, logP; n = this rank's walkers
+    # host memory -> H2D -> prior + likelihood kernels -> D2H of logL, logP; n = this rank's walkers (all inside
+    # the prior support: every one is evaluated)
     th_host = samp.p.reshape(-1, ndim).cpu().numpy().copy()
     eng.logl_batch(th_host[:64])
-    barrier()
+    cx.barrier()
     tc0 = time.perf_counter()
     for _ in range(max(args.steps // 2, 2)):
         eng.logl_batch(th_host)
@@ -309,6 +539,23 @@ def main():
 
     if rank == 0:
         clocks.stop()
+    nan_total = eng.counters()["nan"]
+    del samp
+    eng.close()
+
+    # ---------------- the other BASELINE configs, short legs -----------------------------------------------
+    if args.legs == "auto":
+        legs = [c for c in ("c1", "c2", "c3") if c != args.workload] + (["c5"] if world == 8 else [])
+    elif args.legs in ("none", ""):
+        legs = []
+    else:
+        legs = [c for c in args.legs.split(",") if c]
+    leg_out = {}
+    for name in legs:
+        big = name in ("c4", "c5", "c4noop")
+        leg_out[name] = run_leg(cx, name, steps=5 if big else 50, warmup=3, burn=10 if big else 60,
+                                cpu_budget=0 if args.no_cpu_baseline else 6)
+
     if world > 1:
         td.barrier()
         td.destroy_process_group()
@@ -316,11 +563,11 @@ def main():
         return
 
     # ---------------- roofline of the likelihood kernel -----------------------------------------
-    n_eval_active = c1["in_prior"] - c0["in_prior"]  # proposals whose likelihood was really evaluated
+    n_eval_active = c1["in_prior"] - c0["in_prior"]  # this rank's proposals whose likelihood was really evaluated
     F = flops_per_point(w["kplan"], w["ma"])
-    alg_flops = F * n_eval_active * N  # this rank, whole timed region
+    alg_flops = F * n_eval_active * wl.n  # this rank, whole timed region
     achieved_tf = alg_flops / (kern_ms * 1e-3) * 1e-12 if kern_ms > 0 else None
-    traffic, traffic_src = None, None
+    traffic, traffic_src, executed = None, None, {}
     try:  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
         with open(os.path.join(REPO, "profiles", "kernel_traffic.json")) as fh:
             tj = json.load(fh).get(args.workload)
@@ -328,51 +575,81 @@ def main():
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
     except (OSError, ValueError, KeyError):
         pass
+    try:  # executed-instruction figures of the committed ncu capture of the same kernel on the same workload
+        with open(os.path.join(REPO, "profiles", "kernel_ncu.json")) as fh:
+            executed = json.load(fh).get(args.workload) or {}
+    except (OSError, ValueError):
+        pass
     roofline = {"bound": "fp64", "kernel": "emp::logl_rv_kernel", "achieved": achieved_tf, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": traffic,
                 "traffic_unit": "bytes per launch (HBM); the path is compute-bound, see DESIGN.md §4.1",
                 "traffic_source": traffic_src,
-                "note": "achieved = ALGORITHMIC flops (the oracle's operation count, SURVEY.md §8d row D4: 230 per "
-                        "planet-point with libm calls at 20) / launch time; the kernel reaches the same root with "
-                        "~35 FP64 + ~40 FP32 instructions per planet-point, so frac can exceed 1 — the executed-"
-                        "instruction pipe utilisation (ncu) is in profiles/r01_notes.md",
+                "note": "frac = ALGORITHMIC flops (the oracle's operation count, SURVEY.md §8d row D4: 230 per "
+                        "planet-point with libm calls at 20) / launch time / FP64 peak; it can exceed 1 because the "
+                        "kernel reaches the same root with ~35 FP64 + ~40 FP32 instructions per planet-point. "
+                        "frac_executed and the *_pct keys are what the hardware really did (ncu capture of this "
+                        "kernel on this workload, profiles/kernel_ncu.json)",
                 "peak_source": "FP64 FMA microbenchmark measured in this run (emp_fp64_peak); "
                                "MEASURED_PEAKS.json has no FP64 entry",
                 "launches": kern_n, "avg_launch_ms": kern_ms / max(kern_n, 1),
-                "alg_flops_per_walker_point": F, "kernel_share_of_step": kern_ms / ms,
+                "alg_flops_per_walker_point": F, "kernel_share_of_step": kern_ms / ms_local,
                 "evaluated_fraction": n_eval_active / max(c1["proposals"] - c0["proposals"], 1)}
+    for k in ("frac_executed", "fp64_pipe_pct", "issue_active_pct", "xu_pct", "fma_pipe_pct", "l2_to_sm_gbs",
+              "l1_hit_pct", "source"):
+        if k in executed:
+            roofline[k if k != "source" else "executed_source"] = executed[k]
 
-    out = {"metric": "logL evals/sec (walkers x temps x datapoints / s)", "value": value,
-           "unit": "walker*temp*datapoint/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f64", "data": "synthetic (seeded, SURVEY.md §8d row D2)",
-           "config": {"workload": w["desc"], "name": args.workload, "n_points": N, "n_keplerians": w["kplan"],
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic (seeded, SURVEY.md §8d row D2)",
+           "config": {"workload": w["desc"], "name": args.workload, "n_points": wl.n, "n_keplerians": w["kplan"],
                       "n_instruments": w["nins"], "ndim": ndim, "ntemps": T, "nwalkers": W,
                       "parallelism": f"temperature ladder sharded over {world} GPU(s)", "solver": args.solver,
+                      "exchange": args.exchange if world > 1 else None,
                       "l2": "each step's inputs (draws 2.4 MB/step + state 18 MB) differ per step; the 280 KB "
                             "data set is L2-resident by design (re-read by every CTA)"},
-           "logl_evals_per_s": T * W * args.steps / (ms * 1e-3),
-           "e2e": {"value": e2e_value, "unit": "walker*temp*datapoint/s", "h2d_bytes_per_step": h2d // args.steps,
-                   "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_ms / args.steps,
-                   "includes": "host RNG draws, pinned staging, H2D, step, D2H of logL[T,W]"},
-           "callable_host": {"value": callable_value, "unit": "walker*temp*datapoint/s", "ms_per_call": call_s * 1e3,
+           "counts": "value / e2e count EVALUATED likelihoods (proposals inside the prior support) x datapoints; "
+                     "value_nominal counts every proposal",
+           "value_nominal": value_nominal,
+           "evaluated_fraction": evaluated / max(proposals, 1),
+           "logl_evals_per_s": evaluated / (ms * 1e-3),
+           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e["h2d"],
+                   "d2h_bytes_per_step": e["d2h"], "ms_per_step": e["ms"] / args.steps,
+                   "value_nominal": e["proposals"] * N / (e["ms"] * 1e-3),
+                   "includes": "host RNG draws, pinned staging, H2D, the sweep (CUDA graph), the chain sample "
+                               "[T,W,ndim+2] streamed to pinned host memory, D2H of logL[T,W]"},
+           "callable_host": {"value": callable_value, "unit": UNIT, "ms_per_call": call_s * 1e3,
                              "n_eval_per_call": int(len(th_host)),
                              "what": "emp_logl_batch_host on the current ensemble (all inside the prior): pageable "
                                      "host theta -> H2D -> prior + likelihood kernels -> D2H of logL, logP"},
-           "gpu_launches": launches, "burn_in_sweeps": args.burn, "roofline": roofline,
-           "clocks": clocks.summary(tw0, tw1),
+           "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps, "burn_in_sweeps": args.burn,
+           "roofline": roofline, "clocks": clocks.summary(tw0, tw1),
            "phase_ms_per_step_rank0": {k: v / args.steps for k, v in phases.items()},
            "per_rank": [{"ms_per_step": r[0] / args.steps, "kernel_ms_per_step": r[1] / args.steps,
                          "evaluated_per_step": r[2] / args.steps} for r in per_rank],
-           "acceptance_fraction": (c1["accepted"] - c0["accepted"]) / max(c1["proposals"] - c0["proposals"], 1)}
+           "acceptance_fraction": (c1["accepted"] - c0["accepted"]) / max(c1["proposals"] - c0["proposals"], 1),
+           "nan_likelihoods": nan_total}
+    if parity is not None:
+        out.update(parity)
+    if leg_out:
+        out["configs"] = leg_out
 
     if not args.no_cpu_baseline:
         cores = os.cpu_count()
-        n_cpu = args.cpu_evals or max(cores * 600, 640)  # ~10 s of work on all host cores at C4
-        cb = cpu_baseline(args.workload, n_cpu, cores)
-        out["cpu_baseline"] = {"value": cb["value"], "unit": "walker*temp*datapoint/s", "cores": cores, "kind": "port",
-                               "sample": f"{n_cpu} walkers x {N} points of the same workload through "
-                                         f"multiprocessing.Pool({cores}) ({cb['seconds']:.1f} s)"}
+        if args.cpu_evals:
+            cb = cpu_baseline(args.workload, args.cpu_evals, cores)
+            out["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": f"{args.cpu_evals} walkers x {N} points through Pool({cores})",
+                                   "solver_lib": cb["solver_lib"]}
+        else:
+            out["cpu_baseline"] = cpu_block(args.workload, 12, cores)
+        if args.workload == "c4":  # the reference's DEFAULT per-instrument MA template
+            nn = max(cores, 8)
+            cn = cpu_baseline("c4noop", nn, cores)
+            out["cpu_baseline"]["default_ma_template"] = {
+                "value": cn["value"], "unit": UNIT, "cores": cores,
+                "sample": f"{nn} walkers x {N} points, moav00.model (a no-op on logL that costs "
+                          f"{cn['seconds'] * 1e3 * cores / nn:.0f} ms per call), Pool({cores}) ({cn['seconds']:.1f} s)"}
     print(json.dumps(out))
 
 
@@ -382,7 +659,8 @@ def run_reference(args, rank):
     with multiprocessing.Pool(all cores) exactly like support/pools/01.pool."""
     if rank != 0:
         return
-    w = WORKLOADS[args.workload]
+    wl = Workload(args.workload)
+    w = wl.w
     cores = os.cpu_count()
     n_cpu = args.cpu_evals or max(cores * 128, 256)  # ~2 s per step on all host cores at C4
     vals = []
@@ -394,19 +672,22 @@ def run_reference(args, rank):
         if time.perf_counter() - t_all0 > 150:
             break
     sec = float(np.mean([v["seconds"] for v in vals]))
-    value = n_cpu * w["n"] / sec
+    value = n_cpu * wl.n_units / sec
     world = int(os.environ.get("WORLD_SIZE", "1"))
     T = w["T"] * world
-    out = {"impl": "reference", "metric": "logL evals/sec (walkers x temps x datapoints / s)", "value": value,
-           "unit": "walker*temp*datapoint/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
-           "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f64", "data": "synthetic (seeded, SURVEY.md §8d row D2)",
-           "config": {"workload": w["desc"], "name": args.workload, "n_points": w["n"], "n_keplerians": w["kplan"],
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+           "steps": len(vals), "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic (seeded, SURVEY.md §8d row D2)",
+           "config": {"workload": w["desc"], "name": args.workload, "n_points": wl.n, "n_keplerians": w["kplan"],
                       "n_instruments": w["nins"], "ntemps": T, "nwalkers": w["W"]},
-           "cpu_baseline": {"value": value, "unit": "walker*temp*datapoint/s", "cores": cores, "kind": "port",
-                            "sample": f"each step = {n_cpu} walkers x {w['n']} points (of {T * w['W']}) through "
-                                      f"multiprocessing.Pool({cores}); likelihood+prior per walker"},
-           "e2e": {"value": value, "unit": "walker*temp*datapoint/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "counts": "every walker of the sample is inside the prior support: all are evaluated",
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"each step = {n_cpu} walkers x {wl.n_units} points (of {T * w['W']}) through "
+                                      f"multiprocessing.Pool({cores}); likelihood+prior per walker",
+                            "ms_per_call_per_core": sec * 1e3 * cores / n_cpu,
+                            "solver_lib": vals[-1]["solver_lib"]},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
 

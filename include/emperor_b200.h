@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define EMP_ABI_VERSION 5
+#define EMP_ABI_VERSION 6
 
 #define EMP_MAX_KEP 10   /* Keplerian blocks                                  */
 #define EMP_MAX_INS 16   /* instruments (offset / jitter entries)             */
@@ -230,8 +230,9 @@ int emp_kepler_grid_host(const double *M, const double *ecc, int64_t n, int ecc_
  *   factors  [T, 2, H]     (ndim-1)*ln zz   (host computes the log so the decision is bit-exact)
  *   lnu      [T, 2, H]     log of the accept uniform
  *   accepted [T, W] uint8  (output; 1 where the proposal was accepted)
- * Split 0 is proposed/evaluated/accepted first, then split 1 (emcee order):
- * 2 x (propose kernel, likelihood kernel, accept kernel) on the handle's stream. */
+ * Split 0 is proposed/evaluated/accepted first, then split 1 (emcee order): per half one
+ * proposal + prior kernel and one likelihood kernel whose epilogue does the Metropolis accept
+ * (joint RV + astrometry models: a third launch, the astrometric kernel, accepts). */
 int emp_pt_stretch_step(EmpHandle *h, int32_t T, int32_t W, double *p, double *logl, double *logp,
                         const double *betas, const int32_t *half_idx, const double *zz,
                         const int32_t *rint, const double *factors, const double *lnu,
@@ -246,7 +247,8 @@ int emp_pt_stretch_step(EmpHandle *h, int32_t T, int32_t W, double *p, double *l
  * Outputs:
  *   src      [T, W] int32  flat index (t*W + w) of the slot whose walker ends up in (t, w)
  *   n_acc    [T-1] int32   accepted swaps per pair
- * Every rank of a sharded ladder replays this identically from the all-gathered logl. */
+ * Every rank of a sharded ladder replays this identically from the all-gathered logl.
+ * (No ladder adaptation: that is emp_pt_sweep / emp_pt_sweep_swap.)  T <= 2048. */
 int emp_pt_swap_plan(EmpHandle *h, int32_t T, int32_t W, const double *logl_all,
                      const double *betas, const int32_t *perm, const double *lnu, int32_t *src,
                      int32_t *n_acc);
@@ -260,9 +262,72 @@ int emp_pt_gather_rows(EmpHandle *h, int64_t n_rows, int32_t ndim, const int32_t
 /* Proposals whose log-likelihood came out NaN (rejected; emcee would raise). */
 int emp_nan_count(EmpHandle *h, uint32_t *count);
 
+/* One whole sweep of `sampler.run_mcmc(p1, nsweeps=, nsteps=)` (support/endit_reddemcee.scr:3): nsteps
+ * stretch steps of every local temperature, the hot -> cold swap sweep, the ladder adaptation
+ * (reddemcee adapt_tau / adapt_nu / adapt_mode 0, defaults emp.py:2370-2380), the
+ * tsw / smd / beta histories and the chain store — all on the device, no host synchronisation.
+ * All pointers are DEVICE pointers on the handle's device unless stated. */
+#define EMP_MAX_PEERS 16
+typedef struct EmpPtSweep {
+  int32_t T_loc, W, nsteps; /* local temperatures, walkers (even), stretch steps per sweep        */
+  int32_t T_all;            /* temperatures of the whole ladder (= T_loc unless sharded)          */
+  int32_t n_ranks, rank;    /* ladder sharded over n_ranks GPUs; this handle is `rank`            */
+  int32_t strided;          /* 1: rank r holds temperatures r, r+G, ...; 0: contiguous blocks     */
+  int32_t use_graph;        /* 1: the sweep is captured once into a CUDA graph and replayed       */
+  double *p, *logl, *logp;             /* state [T_loc, W, ndim], [T_loc, W], [T_loc, W]          */
+  double *p_alt, *logl_alt, *logp_alt; /* the swap writes the new state here (caller swaps roles) */
+  double *betas;            /* [T_all] ladder; adapted in place when adapt != 0                   */
+  const int32_t *half_idx;  /* stretch draws [nsteps, T_loc, 2, H], see emp_pt_stretch_step        */
+  const double *zz;
+  const int32_t *rint;
+  const double *factors;
+  const double *lnu;
+  const int32_t *perm;      /* swap draws of the whole ladder [T_all-1, 2, W] (NULL if T_all == 1) */
+  const double *lnu_swap;   /* [T_all-1, W]                                                        */
+  uint8_t *accepted;        /* [T_loc, W] accept mask of the last stretch step                     */
+  int32_t *n_accepted;      /* [T_loc, W] accepted moves per walker, accumulated (may be NULL)     */
+  int32_t *src;             /* [T_all, W] swap plan of this sweep (output)                         */
+  int32_t *n_acc;           /* [T_all-1] accepted swaps per pair (output)                          */
+  int32_t adapt;            /* 1: adapt the ladder after the swap sweep (needs T_all > 2)          */
+  int32_t thin;             /* store every thin-th stretch step (>= 1)                             */
+  double adapt_tau, adapt_nu;
+  int64_t *sweep_counter;   /* device scalar: sweeps done (reddemcee's `time`); incremented        */
+  int64_t *step_counter;    /* device scalar: stretch steps begun; incremented                     */
+  double *beta_hist;        /* [hist_cap, T_all] ladder after every sweep (may be NULL)            */
+  int32_t *nacc_hist;       /* [hist_cap, T_all-1] swap counts of every sweep (may be NULL)        */
+  double *smd_hist;         /* [hist_cap, T_loc] swap mean distance per sweep (needs D; may be NULL) */
+  int64_t hist_cap;
+  const double *D;          /* [ndim] prior widths `sampler.D_` (emp.py:595-602) or NULL           */
+  double *chain, *chain_ll, *chain_lp; /* [store_cap, T_loc, W, ndim] / [store_cap, T_loc, W] or NULL */
+  int64_t store_cap;
+  int32_t store_ring;       /* 1: slot index wraps at store_cap (host streams the ring out)        */
+  int32_t _pad;
+  /* sharded ladder only: CURRENT buffers (p, logl, logp) of every rank, peer HBM mapped with
+   * emp_ipc_open; entry `rank` must equal p / logl / logp */
+  const double *peer_p[EMP_MAX_PEERS], *peer_logl[EMP_MAX_PEERS], *peer_logp[EMP_MAX_PEERS];
+  const double *logl_all;   /* [T_all, W] all-gathered logL (sharded) or NULL (= logl)             */
+} EmpPtSweep;
+/* Single GPU: the whole sweep (6 launches at nsteps = 1). */
+int emp_pt_sweep(EmpHandle *h, const EmpPtSweep *s);
+/* Sharded ladder: the stretch phase, then — after the caller all-gathered logL (and the swap draws)
+ * over NCCL — the replicated swap plan + adaptation and the row gather straight from the owners' HBM. */
+int emp_pt_sweep_stretch(EmpHandle *h, const EmpPtSweep *s);
+int emp_pt_sweep_swap(EmpHandle *h, const EmpPtSweep *s);
+
+/* Device memory that can be shared with the other ranks of the node (CUDA IPC over NVLink/NVSwitch):
+ * the sharded swap reads the rows it needs from the owners' ensembles instead of all-gathering them. */
+int emp_dev_alloc(int device, int64_t bytes, void **ptr);
+int emp_dev_free(int device, void *ptr);
+int emp_ipc_export(int device, void *ptr, unsigned char handle64[64]);
+int emp_ipc_open(int device, const unsigned char handle64[64], void **ptr);
+int emp_ipc_close(int device, void *ptr);
+
 /* ---- introspection -------------------------------------------------------- */
 /* Number of kernels this handle has launched since creation (bench.py gpu_launches). */
 int emp_launch_count(EmpHandle *h, int64_t *count);
+/* Number of CUDA graphs emp_pt_sweep has captured so far (a steady run replays two: the state and the
+ * draw staging are double-buffered). */
+int emp_graph_captures(EmpHandle *h, int64_t *count);
 /* Kepler solver of the likelihood kernel.  EMP_SOLVER_GRID (default): Markley starter, then the
  * grid-anchored refinement of emp_device.cuh (same root as kepler.solve to ~1 ulp, about half the FP64
  * instructions).  EMP_SOLVER_KEPLERPY: Markley starter + the single high-order refinement of kepler.py

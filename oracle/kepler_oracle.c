@@ -16,7 +16,7 @@
  *
  * PARITY STATUS: "parity unpinned" — the reference's own tests never call
  * kepler.solve with fixed inputs; the solver is pinned
- * here by its residual |E - e sin E - M| instead (tests/test_oracle_kepler.py).
+ * here by its residual |E - e sin E - M| instead (tests/test_oracle.py::test_kepler_residual_grid).
  *
  * Reference call sites this stands in for:
  *   support/models/kep00.model:6, kep01.model:13, kep02.model:20,

@@ -29,7 +29,7 @@ def test_python_binding_covers_header(built_lib):
     bound = {s[0] for s in _lib.SYMBOLS}
     assert bound == set(_declared_functions())
     from astroemperor_b200.modelspec import EMP_ABI_VERSION
-    assert _lib.lib().emp_abi_version() == EMP_ABI_VERSION == 5
+    assert _lib.lib().emp_abi_version() == EMP_ABI_VERSION == 6
 
 
 def test_descriptor_layout_matches_c(built_lib, tmp_path):
@@ -46,6 +46,22 @@ def test_descriptor_layout_matches_c(built_lib, tmp_path):
     D = EmpModelDescC
     assert [int(x) for x in out] == [ctypes.sizeof(D), D.free_to_full.offset, D.full_init.offset,
                                      D.prior_ops.offset, 64]
+
+
+def test_sweep_struct_layout_matches_c(built_lib, tmp_path):
+    """sizeof/offsetof of EmpPtSweep (the whole-sweep argument block) == its ctypes mirror."""
+    from astroemperor_b200._lib import EmpPtSweepC as S
+    names = ["p", "betas", "perm", "n_acc", "adapt", "adapt_tau", "sweep_counter", "hist_cap", "D", "chain",
+             "store_cap", "store_ring", "peer_p", "peer_logp", "logl_all"]
+    src = tmp_path / "layout2.c"
+    fmt = " ".join(["%zu"] * (len(names) + 1))
+    args = ", ".join(f"offsetof(EmpPtSweep, {n})" for n in names)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "emperor_b200.h"\n'
+                   f'int main(){{printf("{fmt}\\n", sizeof(EmpPtSweep), {args});return 0;}}\n')
+    exe = tmp_path / "layout2"
+    subprocess.check_call(["gcc", "-I", os.path.join(REPO, "include"), str(src), "-o", str(exe)])
+    out = [int(x) for x in subprocess.check_output([str(exe)]).decode().split()]
+    assert out == [ctypes.sizeof(S)] + [getattr(S, n).offset for n in names]
 
 
 def test_create_fails_loudly_without_gpu(built_lib):

@@ -9,7 +9,7 @@ from conftest import load_golden
 pytestmark = pytest.mark.gpu
 
 
-def _setup(name, T, W, seed, betas=None, **kw):
+def _setup(name, T, W, seed, betas=None, with_D=False, **kw):
     from astroemperor_b200.engine import LikelihoodEngine
     from astroemperor_b200.sampler import PTSampler
     from oracle.rv_oracle import RVOracle
@@ -17,65 +17,112 @@ def _setup(name, T, W, seed, betas=None, **kw):
     g, spec = load_golden(name)
     eng = LikelihoodEngine(spec, g["t"], g["y"], g["yerr"], g["flag"])
     samp = PTSampler(W, eng.ndim, eng, ntemps=T, seed=seed, betas=betas, **kw)
+    if with_D:
+        samp.D_ = spec.prior_widths()
     p0 = samp.initial_positions(spec)
     orc = PTOracle(RVOracle(spec.compile(), g["t"], g["y"], g["yerr"], g["flag"]), samp.betas,
-                   adapt_tau=samp.adapt_tau, adapt_nu=samp.adapt_nu, adapt=samp.adapt)
+                   adapt_tau=samp.adapt_tau, adapt_nu=samp.adapt_nu, adapt=samp.adapt,
+                   D=samp.D_ if with_D else None)
     return g, spec, eng, samp, orc, p0
 
 
-@pytest.mark.parametrize("name,T,W,nsweeps,nsteps", [
-    ("c1_51peg_k1_p0", 2, 100, 6, 2),            # BASELINE config 1 shape
-    ("c2_synth3p_2ins_n400", 4, 64, 4, 1),       # 3 planets, S/C parameterisation, derived-ecc prior
-    ("synth_k1_p0_ma1_global", 3, 32, 4, 3),     # global MA recurrence in the likelihood
-    ("synth_k1_p0_acc2_fixed", 5, 24, 4, 1),     # fixed parameter + acceleration, odd T
+@pytest.mark.parametrize("name,T,W,nsweeps,nsteps,graph", [
+    ("c1_51peg_k1_p0", 2, 100, 6, 2, False),            # BASELINE config 1 shape
+    ("c2_synth3p_2ins_n400", 4, 64, 4, 1, False),       # 3 planets, S/C parameterisation, derived-ecc prior
+    ("c2_synth3p_2ins_n400", 4, 64, 8, 1, True),        # the same sweeps replayed from the captured CUDA graph
+    ("synth_k1_p0_ma1_global", 3, 32, 4, 3, True),      # global MA recurrence in the likelihood, graph, nsteps = 3
+    ("synth_k1_p0_acc2_fixed", 5, 24, 4, 1, False),     # fixed parameter + acceleration, odd T
+    ("c4_synth5p_4ins_ma_global_n600", 9, 1100, 3, 1, True),  # W > 1024: two plan elements per thread
 ])
-def test_sweeps_bit_identical_to_oracle(name, T, W, nsweeps, nsteps):
-    g, spec, eng, samp, orc, p0 = _setup(name, T, W, seed=11)
+def test_sweeps_bit_identical_to_oracle(name, T, W, nsweeps, nsteps, graph):
+    """Stretch steps, accept masks, swap plan, swap counts, DEVICE ladder adaptation, swap mean distance: every
+    sweep against oracle/pt_oracle.py with the same draws."""
+    g, spec, eng, samp, orc, p0 = _setup(name, T, W, seed=11, with_D=True)
     samp._init_state(p0)
+    samp._alloc_store(nsweeps * nsteps)
     orc.init_state(p0)
     p, ll, lp = samp.state_numpy()
-    assert np.array_equal(lp, orc.logp)
+
+    def same_logp(a, b):
+        # bit-identical, except where libm's pow(z, 2.0) — what `**2` of Normal.prior:8 is on a NumPy scalar — is
+        # not the correctly rounded square the device computes: 1 ulp in ~1/2600 Normal priors (DESIGN.md §2)
+        return np.array_equal(a, b) or (np.max(np.abs(a - b) / np.abs(b)) < 4e-16 and np.mean(a != b) < 0.02)
+    assert same_logp(lp, orc.logp)
     n_dec = 0
+    captures0 = eng.graph_captures
     for k in range(nsweeps):
         d = samp.draw(nsteps)
-        n_acc = samp.sweep(d)
+        n_acc = samp.sweep(samp.stage_draws(d, pinned=True) if graph else d)
         acc_o, n_acc_o, src_o = orc.sweep(d)
         p, ll, lp = samp.state_numpy()
         assert np.array_equal(n_acc, n_acc_o), (k, n_acc, n_acc_o)
         assert np.array_equal(samp._src.cpu().numpy(), src_o), f"swap plan differs in sweep {k}"
         assert np.array_equal(p, orc.p), f"chain differs from the oracle in sweep {k}"
-        assert np.array_equal(lp, orc.logp)
-        assert np.array_equal(samp.betas, orc.betas), "ladder adaptation differs"
+        assert same_logp(lp, orc.logp)
+        assert np.array_equal(samp.betas, orc.betas), "ladder adaptation (on the device) differs"
         fin = np.isfinite(orc.logl)
         assert np.max(np.abs(ll[fin] - orc.logl[fin]) / np.abs(orc.logl[fin])) < 1e-10
+        smd = samp.get_smd()
+        assert smd.shape == (k + 1, T - 1)
+        assert np.allclose(smd[-1], orc.smd[: T - 1], rtol=1e-12, atol=0), "swap mean distance differs"
         n_dec += T * W * nsteps + (T - 1) * W
     # the last accept mask too (last step of the last sweep)
     assert np.array_equal(samp.accepted.cpu().numpy().astype(bool), acc_o[-1])
+    # histories kept on the device: one row per sweep
+    assert np.array_equal(samp.get_betas()[-1], orc.betas) and samp.get_betas().shape == (nsweeps * nsteps, T)
+    assert samp.get_betas_sweeps().shape == (nsweeps, T)
+    assert np.array_equal(samp.get_tsw()[-1], n_acc_o / W)
+    # every stretch step is a stored sample; the last one of a sweep is the state after the swap
+    ch = samp.get_chain()
+    assert ch.shape == (T, nsweeps * nsteps, W, eng.ndim) and np.array_equal(ch[:, -1], orc.p)
+    if graph:  # two argument blocks alternate (state and staging are double-buffered): two captures, then replays
+        assert eng.graph_captures - captures0 <= 2
     print(f"{name}: {n_dec} decisions identical, min decision margin {orc.min_margin:.3e}")
     assert orc.min_margin > 1e-9  # otherwise the case is too close to call and should be re-seeded
 
 
+def test_launches_per_sweep():
+    """VERDICT r1 #4: a sweep with nsteps = 1 is at most 6 kernel launches (was 13 + torch glue)."""
+    g, spec, eng, samp, orc, p0 = _setup("c2_synth3p_2ins_n400", 10, 512, seed=5, with_D=True)
+    samp.run_mcmc(p0, nsweeps=3, nsteps=1)
+    l0 = eng.launch_count
+    samp.run_mcmc(None, nsweeps=10, nsteps=1)
+    assert (eng.launch_count - l0) == 60, eng.launch_count - l0
+    assert eng.graph_captures <= 2
+
+
 def test_run_mcmc_api_and_storage():
     g, spec, eng, samp, orc, p0 = _setup("c1_51peg_k1_p0", 3, 32, seed=3)
-    samp.run_mcmc(p0, nsweeps=12, nsteps=2, progress=False)
+    state = samp.run_mcmc(p0, nsweeps=12, nsteps=2, progress=False)
     ch = samp.get_chain()
-    assert ch.shape == (3, 12, 32, eng.ndim)
-    assert samp.get_chain(flat=True, discard=2, thin=2).shape == (3, 5 * 32, eng.ndim)
+    # reddemcee stores every stretch step: nsweeps*nsteps samples (emp.py:2514-2516 discards in steps)
+    assert ch.shape == (3, 24, 32, eng.ndim)
+    assert samp.get_chain(flat=True, discard=4, thin=2).shape == (3, 10 * 32, eng.ndim)
     ll = samp.get_log_like()
     lp = samp.get_log_prior()
-    assert ll.shape == (3, 12, 32) and np.all(np.isfinite(ll)) and np.all(np.isfinite(lp))
-    assert samp.get_log_prob(flat=True).shape == (3, 12 * 32)
+    assert ll.shape == (3, 24, 32) and np.all(np.isfinite(ll)) and np.all(np.isfinite(lp))
+    assert samp.get_log_prob(flat=True).shape == (3, 24 * 32)
     af = samp.acceptance_fraction
     assert af.shape == (3, 32) and 0.0 < af.mean() < 1.0
-    assert samp.get_betas().shape == (12, 3) and samp.get_tsw().shape == (12, 2)
+    # per-sweep histories
+    assert samp.get_betas().shape == (24, 3) and samp.get_betas_sweeps().shape == (12, 3) and samp.get_tsw().shape == (12, 2)
     # stored likelihoods are the likelihoods of the stored positions
-    ll_re, _ = eng.logl_batch(ch[:, -1].reshape(-1, eng.ndim))
-    assert np.array_equal(ll_re.reshape(3, 32), ll[:, -1])
-    # continue the run: storage grows
-    samp.run_mcmc(None, nsweeps=3, nsteps=1)
-    assert samp.get_chain().shape[1] == 15
+    for j in (-1, -2, 0):
+        ll_re, _ = eng.logl_batch(ch[:, j].reshape(-1, eng.ndim))
+        assert np.array_equal(ll_re.reshape(3, 32), ll[:, j])
+    assert np.array_equal(state.coords, ch[:, -1])
+    # continue the run (the returned state is accepted like emcee's): storage grows
+    samp.run_mcmc(state, nsweeps=3, nsteps=1)
+    assert samp.get_chain().shape[1] == 27 and samp.get_betas().shape == (27, 3) and samp.get_tsw().shape == (15, 2)
+    assert np.array_equal(samp.get_chain()[:, :24], ch)
     logz, err = samp.get_evidence_ti()
     assert np.isfinite(logz)
+    bk = samp.backend
+    assert bk[0].iteration == 27 and bk[0].get_chain().shape == (27, 32, eng.ndim)
+    # thinning counts stretch steps
+    g, spec, eng, s2, _, p0 = _setup("c1_51peg_k1_p0", 3, 32, seed=3, thin_by=3)
+    s2.run_mcmc(p0, nsweeps=12, nsteps=2)
+    assert s2.get_chain().shape[1] == 8 and np.array_equal(s2.get_chain(), ch[:, 0:24:3])
 
 
 def test_same_seed_same_chain_and_host_store():
@@ -123,14 +170,16 @@ def test_postprocessing_reductions_and_smd(tmp_path):
     samp.run_mcmc(p0, nsweeps=400, nsteps=2, progress=False)
     smd = samp.get_smd()
     assert smd.shape == (400, T - 1) and np.all(smd >= 0) and smd[5:].mean() > 0
-    tau = samp.get_autocorr_time(discard=100, quiet=True)
+    assert samp.get_chain().shape[1] == 800
+    tau = samp.get_autocorr_time(discard=200, quiet=True)
     assert tau.shape == (T, eng.ndim) and np.all(np.isfinite(tau)) and np.all(tau > 0)
     with pytest.raises(RuntimeError):
-        samp.get_autocorr_time(discard=380, quiet=False, tol=1000)
-    z_ti, e_ti = samp.get_evidence_ti(discard=100)
-    z_ss, e_ss = samp.get_evidence_ss(discard=100)
-    z_hy, e_hy = samp.get_evidence_hybrid(discard=100)
-    assert np.isfinite([z_ti, z_ss, z_hy, e_ti, e_hy]).all() and z_hy == z_ss
+        samp.get_autocorr_time(discard=760, quiet=False, tol=1000)
+    z_ti, e_ti = samp.get_evidence_ti(discard=200)
+    z_ss, e_ss = samp.get_evidence_ss(discard=200)
+    assert np.isfinite([z_ti, z_ss, e_ti]).all()
+    with pytest.raises(NotImplementedError):  # reddemcee's own estimator: EMPEROR's try/except falls back to TI
+        samp.get_evidence_hybrid(discard=100)
     # 2-parameter model (offset + jitter): evidence by brute-force quadrature over the prior box
     fp = spec.free_params()
     g0 = np.linspace(fp[0].limits[0], fp[0].limits[1], 1201)
@@ -147,4 +196,4 @@ def test_postprocessing_reductions_and_smd(tmp_path):
     assert path.endswith((".npz", ".h5"))
     if path.endswith(".npz"):
         d = np.load(path)
-        assert d["chain"].shape == (T, 390, 32, eng.ndim) and d["beta_history"].shape == (390, T)
+        assert d["chain"].shape == (T, 790, 32, eng.ndim) and d["beta_history"].shape == (790, T)

@@ -56,7 +56,7 @@ def test_likelihood_kernels_are_tma_fp64_and_register_resident(sass):
 
 def test_every_kernel_of_the_path_is_present(sass):
     names = " ".join(sass)
-    for k in ("prior_compact_kernel", "pt_propose_kernel", "pt_accept_kernel", "pt_swap_plan_smem_kernel",
+    for k in ("prior_compact_kernel", "pt_propose_prior_kernel", "pt_swap_plan_kernel", "pt_apply_plan_kernel",
               "pt_gather_rows_kernel", "am_logl_kernel", "model_rv_kernel", "kepler_solve_kernel",
               "kepler_grid_kernel", "fp64_peak_kernel"):
         assert k in names, k
