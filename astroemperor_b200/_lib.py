@@ -76,6 +76,10 @@ SYMBOLS = [
     ("emp_pt_swap_plan", ctypes.c_int, [_P, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     ("emp_pt_gather_rows", ctypes.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P]),
     ("emp_nan_count", ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint32)]),
+    ("emp_draws_create", ctypes.c_int, [_I32, _P, _P, _I32, ctypes.POINTER(_P)]),
+    ("emp_draws_destroy", ctypes.c_int, [_P]),
+    ("emp_draws_get_state", ctypes.c_int, [_P, _I32, _P, ctypes.POINTER(_I32)]),
+    ("emp_draws_sweep", ctypes.c_int, [_P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _I32, _P, _P]),
     ("emp_pt_sweep", ctypes.c_int, [_P, ctypes.POINTER(EmpPtSweepC)]),
     ("emp_pt_sweep_stretch", ctypes.c_int, [_P, ctypes.POINTER(EmpPtSweepC)]),
     ("emp_pt_sweep_swap", ctypes.c_int, [_P, ctypes.POINTER(EmpPtSweepC)]),

@@ -50,11 +50,15 @@ class SweepDraws:
 
 class DrawStreams:
     """One `RandomState` per temperature (reddemcee keeps one emcee sampler, hence one random
-    state, per temperature) plus one for the swap sweep and one for the initial ensemble, all
+    state, per temperature) plus one per adjacent swap pair and one for the initial ensemble, all
     derived from a single seed.  A rank of a sharded ladder only advances the streams of its
-    own temperatures and of the swap pairs it was assigned."""
+    own temperatures and of the swap pairs it was assigned.
 
-    def __init__(self, seed, ntemps: int):
+    native=True: the temperature and swap-pair streams are handed to the C generator of the C-ABI library
+    (csrc/emp_draws.cpp: the same MT19937 states, the same legacy RandomState algorithms, bit-identical
+    draws — tests/test_host_logic.py compares the two), which fills a whole sweep in one call, in threads."""
+
+    def __init__(self, seed, ntemps: int, native: bool = False, n_threads: int = 0):
         ss = np.random.SeedSequence(seed)
         kids = ss.spawn(2 * ntemps + 1)
         mk = lambda k: np.random.RandomState(np.random.MT19937(k))
@@ -62,6 +66,39 @@ class DrawStreams:
         self.init = mk(kids[ntemps + 1])
         self.swap_pair = [mk(k) for k in kids[ntemps + 2:]]  # pair j: temperatures (j+1, j), j < ntemps-1
         self.ntemps = ntemps
+        self.native = bool(native)
+        import os
+        self.n_threads = int(n_threads) if n_threads else max(1, min(8, (os.cpu_count() or 2) // 2))
+        self._h = None
+
+    def handle(self):
+        """The C generator, created on first use from the RandomStates' current MT19937 states
+        (stream t = temperature t, stream ntemps + j = swap pair j)."""
+        if self._h is None:
+            import ctypes
+            from . import _lib
+            states = [r.get_state(legacy=True) for r in self.temp + self.swap_pair]
+            keys = np.ascontiguousarray(np.stack([st[1] for st in states]), dtype=np.uint32)
+            pos = np.array([st[2] for st in states], dtype=np.int32)
+            h = ctypes.c_void_p()
+            _lib.check(_lib.lib().emp_draws_create(len(states), keys.ctypes.data, pos.ctypes.data, self.n_threads,
+                                                   ctypes.byref(h)))
+            self._h = h
+        return self._h
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                from . import _lib
+                _lib.lib().emp_draws_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def _zz_from_u(u, a):
+    """emcee StretchMove: zz = ((a - 1) u + 1)^2 / a (the same NumPy expression on both draw paths)."""
+    return ((a - 1.0) * u + 1) ** 2.0 / a
 
 
 def draw_stretch(rng: np.random.RandomState, W: int, nsteps: int, a: float = 2.0):
@@ -78,43 +115,67 @@ def draw_stretch(rng: np.random.RandomState, W: int, nsteps: int, a: float = 2.0
         half_idx[s, 0] = np.flatnonzero(inds == 0)
         half_idx[s, 1] = np.flatnonzero(inds == 1)
         for split in (0, 1):
-            zz[s, split] = ((a - 1.0) * rng.rand(H) + 1) ** 2.0 / a
+            zz[s, split] = _zz_from_u(rng.rand(H), a)
             rint[s, split] = rng.randint(H, size=(H,))
             u[s, split] = rng.rand(H)
     return half_idx, zz, rint, u
 
 
+def sweep_shapes(T_loc: int, W: int, nsteps: int, n_rows: int):
+    """(field, shape, dtype) of the seven arrays of a sweep's draws, in SweepDraws.FIELDS order."""
+    H = W // 2
+    s4 = (nsteps, T_loc, 2, H)
+    return [("half_idx", s4, np.int32), ("zz", s4, np.float64), ("rint", s4, np.int32), ("factors", s4, np.float64),
+            ("lnu", s4, np.float64), ("perm", (n_rows, 2, W), np.int32), ("lnu_swap", (n_rows, W), np.float64)]
+
+
 def draw_sweep(streams: DrawStreams, W: int, ndim: int, nsteps: int, a: float = 2.0,
-               temps: slice = None, swap: bool = True, swap_rows=None) -> SweepDraws:
+               temps: slice = None, swap: bool = True, swap_rows=None, out=None) -> SweepDraws:
     """Draws of one sweep: stretch draws for the temperatures in `temps` (default: all), swap
     draws for the pairs in `swap_rows` (default: all T-1; a row index >= T-1 yields a zero row, the
-    padding of a sharded ladder whose ranks hold T/G rows each)."""
+    padding of a sharded ladder whose ranks hold T/G rows each).  `out`: dict of preallocated arrays
+    (e.g. views of a pinned staging buffer) to fill instead of allocating."""
     if W % 2:
         raise ValueError("nwalkers must be even (two equal halves, emcee RedBlueMove nsplits=2)")
     T = streams.ntemps
     tl = range(T)[temps] if temps is not None else range(T)
-    H = W // 2
-    half_idx = np.empty((nsteps, len(tl), 2, H), dtype=np.int32)
-    zz = np.empty((nsteps, len(tl), 2, H))
-    rint = np.empty((nsteps, len(tl), 2, H), dtype=np.int32)
-    u = np.empty((nsteps, len(tl), 2, H))
-    for j, t in enumerate(tl):
-        half_idx[:, j], zz[:, j], rint[:, j], u[:, j] = draw_stretch(streams.temp[t], W, nsteps, a)
-    factors = (ndim - 1.0) * np.log(zz)
-    with np.errstate(divide="ignore"):
-        lnu = np.log(u)
     rows = list(range(max(T - 1, 0))) if swap_rows is None else list(swap_rows)
-    perm = np.zeros((len(rows), 2, W), dtype=np.int32)
-    lnu_swap = np.zeros((len(rows), W))
-    if swap:
-        for k, j in enumerate(rows):
-            if j >= T - 1:
-                continue
-            rng = streams.swap_pair[j]
-            perm[k, 0] = rng.permutation(W)
-            perm[k, 1] = rng.permutation(W)
-            with np.errstate(divide="ignore"):
-                lnu_swap[k] = np.log(rng.uniform(size=W))
+    if out is None:
+        out = {f: (np.zeros if f in ("perm", "lnu_swap") else np.empty)(shp, dtype=dt)
+               for f, shp, dt in sweep_shapes(len(tl), W, nsteps, len(rows))}
+    half_idx, zz, rint, factors, lnu = (out[f] for f in ("half_idx", "zz", "rint", "factors", "lnu"))
+    perm, lnu_swap = out["perm"], out["lnu_swap"]
+    if streams.native:
+        from . import _lib
+        L, h = _lib.lib(), streams.handle()
+        ts = np.array(list(tl), dtype=np.int32)
+        rs = np.array([T + j if j < T - 1 else -1 for j in rows] if swap else [], dtype=np.int32)
+        _lib.check(L.emp_draws_sweep(h, ts.ctypes.data, len(ts), W, nsteps, half_idx.ctypes.data, zz.ctypes.data,
+                                     rint.ctypes.data, lnu.ctypes.data, rs.ctypes.data, len(rs), perm.ctypes.data,
+                                     lnu_swap.ctypes.data))
+        zz[...] = _zz_from_u(zz, a)
+        if not len(rs):
+            perm[...] = 0
+            lnu_swap[...] = 1.0
+    else:
+        H = W // 2
+        for j, t in enumerate(tl):
+            half_idx[:, j], zz[:, j], rint[:, j], lnu[:, j] = draw_stretch(streams.temp[t], W, nsteps, a)
+        perm[...] = 0
+        lnu_swap[...] = 1.0
+        if swap:
+            for k, j in enumerate(rows):
+                if j >= T - 1:
+                    continue
+                rng = streams.swap_pair[j]
+                perm[k, 0] = rng.permutation(W)
+                perm[k, 1] = rng.permutation(W)
+                lnu_swap[k] = rng.uniform(size=W)
+    # the logs are NumPy's on both paths: device and oracle compare against the same bits
+    np.multiply(np.log(zz), ndim - 1.0, out=factors)
+    with np.errstate(divide="ignore"):
+        np.log(lnu, out=lnu)
+        np.log(lnu_swap, out=lnu_swap)
     return SweepDraws(half_idx, zz, rint, factors, lnu, perm, lnu_swap, sharded_swap=swap_rows is not None)
 
 

@@ -29,7 +29,7 @@ import numpy as np
 
 from . import _lib
 from . import dist as _dist
-from .draws import DrawStreams, SweepDraws, default_betas, draw_sweep, initial_positions
+from .draws import DrawStreams, SweepDraws, default_betas, draw_sweep, initial_positions, sweep_shapes
 
 
 class State:
@@ -53,7 +53,7 @@ class PTSampler:
                  backend=None, betas=None, tsw_history: bool = True, smd_history: bool = True,
                  adapt_tau: float = 1000, adapt_nu: float = 1, adapt_mode: int = 0, a: float = 2.0,
                  seed: Optional[int] = None, store: str = "device", thin_by: int = 1, adapt: bool = True, group=None,
-                 layout: str = "strided", exchange: str = "peer", graph: bool = True):
+                 layout: str = "strided", exchange: str = "peer", graph: bool = True, native_draws: bool = True):
         """`log_like` is the LikelihoodEngine (it carries the prior as well; `log_prior` and `pool` are
         accepted for signature compatibility and ignored — the walkers are evaluated on the GPU, not
         through a multiprocessing pool).  `backend`: None, or a file name: the run is written there in
@@ -80,7 +80,8 @@ class PTSampler:
         self._betas_host = b0
         self._betas_initial = b0.copy()
         self._betas_stale = False
-        self.streams = DrawStreams(seed, self.ntemps)
+        # native_draws: the C generator of the C-ABI library (bit-identical to numpy.random.RandomState, threaded)
+        self.streams = DrawStreams(seed, self.ntemps, native=native_draws)
         self.D_ = None
         if store not in ("device", "host", None):
             raise ValueError("store must be 'device', 'host' or None")
@@ -311,8 +312,58 @@ class PTSampler:
         out["_stage_index"] = i
         return out
 
+    def draw_staged(self, nsteps: int):
+        """Draw the next sweep straight into the pinned staging buffer (no intermediate arrays, no packing) and
+        enqueue its H2D copy; returns the dict of device views `sweep_begin` takes.  The NumPy views of the two
+        pinned buffers and the torch views of their device copies are built once per (nsteps) layout."""
+        torch, sh = self.torch, self.shard
+        lay = getattr(self, "_lay", None)
+        if lay is None or lay["nsteps"] != nsteps:
+            n_rows = 0 if self.ntemps < 2 else (self.ntemps - 1 if sh.world == 1 else sh.n_local)
+            shapes = sweep_shapes(sh.n_local, self.nwalkers, nsteps, max(n_rows, 1))
+            offs, total = [], 0
+            for f, shp, dt in shapes:
+                offs.append(total)
+                total += (int(np.prod(shp)) * np.dtype(dt).itemsize + 255) // 256 * 256
+            torch.cuda.synchronize(self.dev)
+            lay = {"nsteps": nsteps, "total": total, "host": [], "dev": [], "np": [], "out": [], "i": 0,
+                   "evt": [torch.cuda.Event(), torch.cuda.Event()]}
+            for i in range(2):
+                host = torch.empty(total, dtype=torch.uint8).pin_memory()
+                dev = torch.empty(total, dtype=torch.uint8, device=self.dev)
+                hv = host.numpy()
+                views, out = {}, {"sharded_swap": sh.world > 1, "_stage_index": i}
+                for (f, shp, dt), o in zip(shapes, offs):
+                    nb = int(np.prod(shp)) * np.dtype(dt).itemsize
+                    views[f] = hv[o:o + nb].view(dt).reshape(shp)
+                    out[f] = dev[o:o + nb].view(torch.int32 if dt == np.int32 else torch.float64).view(shp)
+                lay["host"].append(host), lay["dev"].append(dev), lay["np"].append(views), lay["out"].append(out)
+            self._lay = lay
+        i = lay["i"] = 1 - lay["i"]
+        # the H2D that last used this pinned buffer has finished (this also keeps the host at most two sweeps
+        # ahead of the device: that copy is stream-ordered behind the sweep before it)
+        lay["evt"][i].synchronize()
+        t0 = _time.perf_counter()
+        rows = None if sh.world == 1 else range(self.ntemps)[sh.local_slice]
+        draw_sweep(self.streams, self.nwalkers, self.ndim, nsteps, self.a, temps=sh.local_slice,
+                   swap=self.ntemps > 1, swap_rows=rows, out=lay["np"][i])
+        self.timings["draws"] += _time.perf_counter() - t0
+        lay["dev"][i].copy_(lay["host"][i], non_blocking=True)
+        lay["evt"][i].record()
+        return lay["out"][i]
+
     def _sweep_args(self, draws, nsteps):
-        """The EmpPtSweep argument block of one sweep (include/emperor_b200.h)."""
+        """The EmpPtSweep argument block of one sweep (include/emperor_b200.h).  The blocks of the steady state
+        (double-buffered state x double-buffered staging) are built once and reused."""
+        key = (self._par, draws["zz"].data_ptr() if draws.get("_stage_index") is not None else None, nsteps,
+               self.adapt, self._hist_cap,
+               None if self._chain is None else self._chain.data_ptr(),
+               None if self._ring is None else self._ring[0].data_ptr(), self.D_ is not None)
+        cache = getattr(self, "_args_cache", None)
+        if cache is None:
+            cache = self._args_cache = {}
+        if key[1] is not None and key in cache:
+            return cache[key]
         sh = self.shard
         A = _lib.EmpPtSweepC()
         A.T_loc, A.W, A.nsteps, A.T_all = sh.n_local, self.nwalkers, nsteps, self.ntemps
@@ -344,6 +395,12 @@ class PTSampler:
             A.chain, A.chain_ll, A.chain_lp = tgt[0].data_ptr(), tgt[1].data_ptr(), tgt[2].data_ptr()
             A.store_cap = tgt[0].shape[0]
             A.store_ring = 1 if self.store == "host" else 0
+        if sh.world == 1 and self.ntemps > 1:
+            A.perm, A.lnu_swap = draws["perm"].data_ptr(), draws["lnu_swap"].data_ptr()
+        if key[1] is not None:
+            if len(cache) > 16:
+                cache.clear()
+            cache[key] = A
         return A
 
     def sweep_begin(self, draws):
@@ -373,8 +430,6 @@ class PTSampler:
             perm, lnu_swap = draws["perm"], draws["lnu_swap"]
         A = self._sweep_args(draws, nsteps)
         if sh.world == 1:
-            if self.ntemps > 1:
-                A.perm, A.lnu_swap = perm.data_ptr(), lnu_swap.data_ptr()
             eng.pt_sweep(A)
             self._mark("sweep")
         else:
@@ -499,24 +554,18 @@ class PTSampler:
             except Exception:
                 pass
 
-        def draw():
-            t0 = _time.perf_counter()
-            d = self.draw(nsteps)
-            self.timings["draws"] += _time.perf_counter() - t0
-            return d
-
         # the draws of the first sweep may already be staged: every call ends by drawing and staging one sweep
         # ahead (below), so that back-to-back calls — adaptation then production (support/endit_freeze1.scr),
         # warm-up then measurement — do not pay the pipeline fill again
         staged, pre = None, getattr(self, "_prefetched", None)
         self._prefetched = None
         if nsweeps > 0:
-            staged = pre[1] if (pre is not None and pre[0] == nsteps) else self.stage_draws(draw(), pinned=True)
+            staged = pre[1] if (pre is not None and pre[0] == nsteps) else self.draw_staged(nsteps)
         for k in it:
             self.sweep_begin(staged)
             # while the device runs this sweep the host draws the next one, packs it into the other pinned
             # buffer and enqueues its H2D copy (double-buffered on both sides)
-            staged = self.stage_draws(draw(), pinned=True)
+            staged = self.draw_staged(nsteps)
             if on_sweep is not None:
                 on_sweep(self, k)
         if nsweeps > 0:

@@ -324,13 +324,20 @@ def run_e2e(cx, samp, eng, steps, T, W):
     """The user's call: run_mcmc with host draws every sweep + D2H of logL[T_loc, W] every sweep (the chain
     itself streams to pinned host memory behind the compute stream, store='host')."""
     torch = cx.torch
-    ll_host = torch.empty((samp.shard.n_local, W), dtype=torch.float64).pin_memory()
-    io = {"d2h": 0}
+    ll_host = [torch.empty((samp.shard.n_local, W), dtype=torch.float64).pin_memory() for _ in range(2)]
+    landed = [torch.cuda.Event(), torch.cuda.Event()]
+    io = {"d2h": 0, "sum": 0.0}
 
     def read_back(s, k):
-        ll_host.copy_(s.logl, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        io["d2h"] += ll_host.numel() * 8
+        # every sweep's logL[T_loc, W] is copied to pinned host memory; the host consumes the copy of the
+        # PREVIOUS sweep while this one runs (one sweep of pipelining instead of a stall per sweep)
+        i = k & 1
+        ll_host[i].copy_(s.logl, non_blocking=True)
+        landed[i].record()
+        if k >= 1:
+            landed[1 - i].synchronize()
+            io["sum"] += float(ll_host[1 - i][0, 0])
+        io["d2h"] += ll_host[i].numel() * 8
 
     samp.run_mcmc(None, nsweeps=2, nsteps=1, on_sweep=read_back)  # warm the staging buffers and the graphs
     io["d2h"] = 0

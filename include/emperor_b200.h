@@ -322,6 +322,28 @@ int emp_ipc_export(int device, void *ptr, unsigned char handle64[64]);
 int emp_ipc_open(int device, const unsigned char handle64[64], void **ptr);
 int emp_ipc_close(int device, void *ptr);
 
+/* ---- host-supplied random draws ------------------------------------------- */
+/* The draws of a sweep are what the reference stack consumes from numpy.random.RandomState (emcee 3.1.6
+ * RedBlueMove.propose + StretchMove.get_proposal per temperature, the swap sweep's permutations and uniforms;
+ * order: astroemperor_b200/draws.py).  These entry points restate the legacy RandomState algorithms (MT19937,
+ * random_sample, shuffle / permutation, randint) bit for bit, one stream per temperature and per adjacent swap
+ * pair, and fill caller-owned HOST buffers (e.g. the pinned staging buffer) with several threads.  Host only: no
+ * CUDA call is made. */
+typedef struct EmpDrawStreams EmpDrawStreams;
+/* keys [n_streams, 624], pos [n_streams]: `RandomState.get_state()[1:3]` of every stream; n_threads: size of
+ * the persistent worker pool (the calling thread included). */
+int emp_draws_create(int32_t n_streams, const uint32_t *keys, const int32_t *pos, int32_t n_threads,
+                     EmpDrawStreams **out);
+int emp_draws_destroy(EmpDrawStreams *d);
+int emp_draws_get_state(EmpDrawStreams *d, int32_t stream, uint32_t *key624, int32_t *pos);
+/* All draws of one sweep, streams in parallel.  Stretch: nsteps RedBlue steps of the temperatures whose stream
+ * indices are temp_streams[n_temps]; outputs [nsteps, n_temps, 2, H]: half_idx (walkers of each split, ascending),
+ * u_zz (uniform behind the stretch factor), rint (partner index), u_acc (accept uniform).  Swap: the pairs
+ * pair_streams[n_rows] (index < 0 = padding row): perm [n_rows, 2, W], u_swap [n_rows, W]. */
+int emp_draws_sweep(EmpDrawStreams *d, const int32_t *temp_streams, int32_t n_temps, int32_t W, int32_t nsteps,
+                    int32_t *half_idx, double *u_zz, int32_t *rint, double *u_acc, const int32_t *pair_streams,
+                    int32_t n_rows, int32_t *perm, double *u_swap);
+
 /* ---- introspection -------------------------------------------------------- */
 /* Number of kernels this handle has launched since creation (bench.py gpu_launches). */
 int emp_launch_count(EmpHandle *h, int64_t *count);

@@ -10,6 +10,51 @@ from conftest import REPO, load_golden
 
 
 # ---------------------------------------------------------------- draws ----
+@pytest.mark.parametrize("T,W,nsteps,threads", [(3, 10, 2, 1), (10, 512, 1, 4), (5, 2, 3, 2), (2, 100, 2, 8),
+                                                (7, 1026, 1, 3)])
+def test_native_draws_are_bit_identical_to_numpy_randomstate(built_lib, T, W, nsteps, threads):
+    """csrc/emp_draws.cpp restates MT19937 + the legacy RandomState algorithms (random_sample, shuffle,
+    permutation, randint): every array of a sweep equals what numpy.random.RandomState produces, sweep after
+    sweep, for whole ladders and for the shards of a sharded one (pure host code: no GPU needed)."""
+    from astroemperor_b200.draws import DrawStreams, draw_sweep
+    a, b = DrawStreams(5, T, native=False), DrawStreams(5, T, native=True, n_threads=threads)
+    for it in range(4):
+        da, db = draw_sweep(a, W, 7, nsteps), draw_sweep(b, W, 7, nsteps)
+        for f in da.FIELDS:
+            assert np.array_equal(getattr(da, f), getattr(db, f)), (f, it)
+    for sl in (slice(1, T, 2), slice(0, T, 2)):
+        da = draw_sweep(a, W, 7, nsteps, temps=sl, swap_rows=range(T)[sl])
+        db = draw_sweep(b, W, 7, nsteps, temps=sl, swap_rows=range(T)[sl])
+        assert db.sharded_swap and all(np.array_equal(getattr(da, f), getattr(db, f)) for f in da.FIELDS)
+    # draws written straight into caller-owned buffers (the sampler's pinned staging views)
+    from astroemperor_b200.draws import sweep_shapes
+    out = {f: np.full(shp, 7, dtype=dt) for f, shp, dt in sweep_shapes(T, W, nsteps, T - 1)}
+    da, db = draw_sweep(a, W, 7, nsteps), draw_sweep(b, W, 7, nsteps, out=out)
+    assert db.zz is out["zz"] and all(np.array_equal(getattr(da, f), out[f]) for f in da.FIELDS)
+
+
+def test_deterministic_exp_of_the_ladder_adaptation():
+    """oracle exp_det (replayed operation by operation on the device, emp_pt.cuh) is within 1 ulp of exp; NumPy's own
+    exp is not correctly rounded either, so "the reference's np.exp" is only defined to that level; over 2000
+    adaptations the two ladders stay within 1e-13."""
+    import mpmath as mp
+    from oracle.pt_oracle import adapt_ladder, exp_det
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-1, 1, 3000), rng.uniform(-30, 30, 500), [0.0, 1e-300, -1e-9, 0.34657359, -0.34657359]])
+    mp.mp.dps = 40
+    truth = np.array([float(mp.exp(mp.mpf(float(v)))) for v in x])
+    ulp = np.spacing(truth)
+    assert np.max(np.abs(exp_det(x) - truth) / ulp) <= 1.0
+    assert np.max(np.abs(np.exp(x) - truth) / ulp) <= 1.0
+    assert exp_det(np.array([0.0]))[0] == 1.0
+    b1 = b2 = np.geomspace(1.0, 1e-3, 12)
+    for time in range(1, 2001):
+        ratios = 0.3 + 0.05 * rng.standard_normal(11)
+        b1 = adapt_ladder(b1, ratios, time, 1000, 1, exp=exp_det)
+        b2 = adapt_ladder(b2, ratios, time, 1000, 1, exp=np.exp)
+    assert np.max(np.abs(b1 - b2) / b2) < 1e-13
+
+
 def test_draw_sweep_protocol():
     from astroemperor_b200.draws import DrawStreams, draw_sweep
     T, W, nd, ns = 3, 10, 4, 2
@@ -215,6 +260,27 @@ def _dist_worker(rank, world, port, T, W, C, seed, layout, q):
         gu = sh.all_gather_rows(torch.from_numpy(mine.lnu_swap))[: T - 1].numpy()
         ok = ok and np.array_equal(gp, full.perm) and np.array_equal(gu, full.lnu_swap)
         ok = ok and np.array_equal(mine.zz, full.zz[:, sh.local_slice])
+        # the C generator draws the same shard (host code of the C-ABI library)
+        mine_n = draw_sweep(DrawStreams(seed, T, native=True, n_threads=2), W, 4, 1, temps=sh.local_slice,
+                            swap_rows=range(T)[sh.local_slice])
+        ok = ok and all(np.array_equal(getattr(mine, f), getattr(mine_n, f)) for f in mine.FIELDS)
+        # the product's sharded swap (pt_apply_plan_kernel): every rank's (p | logl | logp) block is addressed through
+        # a table of base pointers, peer HBM (CUDA IPC) or, exchange='allgather', one all-gather of the blocks; the
+        # kernel's owner / local-row arithmetic restated on the gathered blocks
+        lp_ = rng.normal(size=(T, W))
+        blk = np.concatenate([rows[sh.local_slice].ravel(), ll[sh.local_slice].ravel(), lp_[sh.local_slice].ravel()])
+        (gathered,) = sh.all_gather_flat(torch.from_numpy(blk))
+        gathered = gathered.numpy().reshape(world, -1)
+        n_row = sh.n_local * W
+        for tl in range(sh.n_local):
+            tg = sh.temp_of(rank, tl)
+            s_ = src[tg]
+            st, sw = s_ // W, s_ % W
+            owner, srow = sh.owner_of_temp(st), sh.local_of_temp(st) * W + sw
+            got_p = np.stack([gathered[o, r * C:(r + 1) * C] for o, r in zip(owner, srow)])
+            got_ll = np.array([gathered[o, n_row * C + r] for o, r in zip(owner, srow)])
+            ll_exp = ll.copy()
+            ok = ok and np.array_equal(got_p, p[tg])
         q.put((rank, ok, n_remote))
     finally:
         td.destroy_process_group()
