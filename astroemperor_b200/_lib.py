@@ -72,6 +72,7 @@ SYMBOLS = [
     ("emp_model_host", ctypes.c_int, [_P, _P, _P, _P]),
     ("emp_kepler_solve_host", ctypes.c_int, [_P, _P, _I64, ctypes.c_int, _P, ctypes.c_int]),
     ("emp_kepler_grid_host", ctypes.c_int, [_P, _P, _I64, ctypes.c_int, _P, _P, _P, ctypes.c_int]),
+    ("emp_kepler_grid_table_host", ctypes.c_int, [_P, ctypes.c_double, _I64, _P, _P, _P, ctypes.c_int]),
     ("emp_pt_stretch_step", ctypes.c_int, [_P, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("emp_pt_swap_plan", ctypes.c_int, [_P, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     ("emp_pt_gather_rows", ctypes.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P]),

@@ -1112,6 +1112,30 @@ __global__ void kepler_grid_kernel(const double* __restrict__ M, const double* _
   }
 }
 
+// the same with the per-walker starter table (one eccentricity for the whole array, like a walker's planet):
+// every CTA builds the table in shared memory exactly like the likelihood kernel's prologue does
+__global__ void kepler_grid_table_kernel(const double* __restrict__ M, double ecc, int64_t n,
+                                         const double2* __restrict__ tab, const float4* __restrict__ tabf,
+                                         double* __restrict__ E, double* __restrict__ sinE, double* __restrict__ cosE,
+                                         const HotConsts H) {
+  __shared__ float st[3 * kStartStride];
+  __shared__ float scratch[2 * kStartN + 3];
+  KepConst k;
+  kep_constants_ecc(ecc, k);
+  if (threadIdx.x < 32) build_start_table(k, st, scratch, threadIdx.x);
+  __syncthreads();
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    GridStage S;
+    kep_grid_a<true>(k, M[i], H, tab, tabf, S, st);
+    double sE, cE, dd, y1;
+    kep_grid_root(k, S, H, sE, cE, dd, y1);
+    const double Er = S.eh + (S.df + dd);
+    E[i] = S.sign_hi ? H.c[1] - Er : Er;
+    if (sinE) sinE[i] = flip_sign(sE, S.sign_hi);
+    if (cosE) cosE[i] = cE;
+  }
+}
+
 static void make_grid_tables(std::vector<double2>& sc, std::vector<float4>& scf) {
   // (sin, cos)(k 2^-7) correctly rounded from long double; the FP32 entries are rounded from those
   sc.resize(kGridN);
@@ -1123,8 +1147,23 @@ static void make_grid_tables(std::vector<double2>& sc, std::vector<float4>& scf)
   }
 }
 
+static int kepler_grid_host_impl(const double* M, const double* ecc, int64_t n, int ecc_is_scalar, double* E,
+                                 double* sinE, double* cosE, int device, bool use_table);
+
 extern "C" int emp_kepler_grid_host(const double* M, const double* ecc, int64_t n, int ecc_is_scalar, double* E,
                                     double* sinE, double* cosE, int device) {
+  return kepler_grid_host_impl(M, ecc, n, ecc_is_scalar, E, sinE, cosE, device, false);
+}
+
+extern "C" int emp_kepler_grid_table_host(const double* M, double ecc, int64_t n, double* E, double* sinE,
+                                          double* cosE, int device) {
+  if (!(ecc >= 0.0 && ecc <= double(kStartEccMax)) || fabs(ecc) > 1.0)
+    return fail(EMP_EINVAL, "the starter table serves eccentricities in [0, 0.8]");
+  return kepler_grid_host_impl(M, &ecc, n, 1, E, sinE, cosE, device, true);
+}
+
+static int kepler_grid_host_impl(const double* M, const double* ecc, int64_t n, int ecc_is_scalar, double* E,
+                                 double* sinE, double* cosE, int device, bool use_table) {
   if (!M || !ecc || !E || n < 0) return fail(EMP_EINVAL, "bad argument");
   if (n == 0) return EMP_OK;
   int ndev = 0;
@@ -1151,7 +1190,10 @@ extern "C" int emp_kepler_grid_host(const double* M, const double* ecc, int64_t 
   if (e == cudaSuccess) e = cudaMemcpy(dtabf, scf.data(), kGridN * sizeof(float4), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
     int blocks = int(std::min<int64_t>((n + 255) / 256, 148 * 8));
-    kepler_grid_kernel<<<blocks, 256>>>(dM, de, n, ecc_is_scalar, dtab, dtabf, dE, dS, dC, make_hot_consts());
+    if (use_table)
+      kepler_grid_table_kernel<<<blocks, 256>>>(dM, ecc[0], n, dtab, dtabf, dE, dS, dC, make_hot_consts());
+    else
+      kepler_grid_kernel<<<blocks, 256>>>(dM, de, n, ecc_is_scalar, dtab, dtabf, dE, dS, dC, make_hot_consts());
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(E, dE, n * sizeof(double), cudaMemcpyDeviceToHost);

@@ -37,6 +37,27 @@ constexpr double kF2 = 1.6 / (kPi - 6.0 / kPi);
 constexpr int kGridN = 512;
 constexpr double kGridEccMax = 0.98;  // beyond it the walker/planet takes the kepler.py-style refinement
 
+// Per-(walker, planet) starter table (likelihood kernel v10).  The eccentricity is a constant of the walker, so
+// E(M; e) on [0, pi] is ONE smooth curve per planet that every one of the N datapoints looks up: it is tabulated
+// once per walker in the kernel prologue (kStartN cells of pi/kStartN, a quadratic through the cell's two edges and
+// its centre: |error| <= 7e-4 for e <= 0.8, 1.5e-4 for e <= 0.7 with 52 cells — the Markley starter's own error is
+// 4e-4; what the refinement needs is |delta| < ~6e-3 around the grid point, see kep_grid_a) and replaces the Markley
+// starter's 17 FP32 + 4 MUFU instructions per point by 5 FP32 instructions and 3 shared-memory reads.  Amortised
+// over N >= 2k points the build (105 FP32 solves per planet) is < 1 % of the walker's work.  Measured on C4
+// (profiles/r02_variants.log): 6.28 -> 5.62 ms per launch; 5 planets x 52 cells is what fits next to the tile ring
+// with two CTAs per SM (64 cells x 5 planets drops to one CTA per SM: 6.74 ms).
+#ifndef EMP_START_N
+#define EMP_START_N 52
+#endif
+#ifndef EMP_START_PLANETS
+#define EMP_START_PLANETS 5
+#endif
+constexpr int kStartN = EMP_START_N;    // cells; nodes 0 .. kStartN (<= 127: the node index is masked with 127)
+constexpr int kStartStride = kStartN + 1;
+constexpr int kStartPlanets = EMP_START_PLANETS;  // planets per walker that get a table (shared-memory budget)
+constexpr float kStartEccMax = 0.8f;
+constexpr int kStartFloats = kStartPlanets * 3 * kStartStride;  // per walker
+
 // Hot-loop FP64 literals travel in the KERNEL PARAMETER bank (c[0x0]) so that DFMA/DADD take them
 // as a direct constant operand: a 64-bit immediate costs two UMOVs per use and a user
 // __constant__ array (bank 3) costs an LDC per use (profiles/r02_logl_sass.txt shows the c[0x0][..] operands).
@@ -79,6 +100,8 @@ struct KepConst {
   float ef3, om23f, c2f3, efh; // e/3, 2(1-e)/3, 3 c2, e/2: constant factors folded for the grid core
   int slow_mod;                // |M| may exceed 1e12 somewhere in the data set: use the fmod path
   int robust;                  // e outside [0, kGridEccMax]: the grid-anchored core is not used
+  int tab;                     // the walker's starter table for this planet was built (e <= kStartEccMax)
+  int _pad;
 };
 constexpr int kKepConstDoubles = sizeof(KepConst) / sizeof(double);
 
@@ -160,6 +183,8 @@ __device__ inline void kep_constants(int model, const double* th, double t_absma
   const double m_bound = fabs(k.freq) * (t_absmax + fabs(k.tpv)) + fabs(k.phv);
   k.slow_mod = (m_bound < 1.0e12) ? 0 : 1;  // also catches NaN / inf parameters
   k.robust = (e >= 0.0 && e <= kGridEccMax) ? 0 : 1;
+  k.tab = 0;
+  k._pad = 0;
 }
 
 // ---- mean anomaly, reduced to [0, pi] exactly like NumPy's remainder ------------------
@@ -330,6 +355,8 @@ __device__ __forceinline__ void kep_constants_ecc(double ecc, KepConst& k) {
   k.efh = float(0.5 * ecc);
   k.slow_mod = 0;
   k.robust = (ecc >= 0.0 && ecc <= kGridEccMax) ? 0 : 1;
+  k.tab = 0;
+  k._pad = 0;
 }
 
 // kepler.solve(M, ecc) for one element (A13 of SURVEY.md §8a): E in [0, 2pi]
@@ -474,16 +501,28 @@ struct GridStage {   // what stage A hands to stage C, per point
 // tabf holds (sin, cos, sin/2, cos/6)(Eh) in FP32.  No validity flag: for e in [0, kGridEccMax] and a
 // finite mean anomaly the FP32 starter is finite and inside [0, pi + 1e-3] (M = 0 gives E0 = 0), and
 // the table index is masked.
+// kTab: the starter comes from the walker's table `st` ([3][kStartStride] floats: value, slope, curvature per node).
+template <bool kTab = false>
 __device__ __forceinline__ void kep_grid_a(const KepConst& k, double t, const HotConsts& H,
                                            const double2* __restrict__ tab, const float4* __restrict__ tabf,
-                                           GridStage& S) {
+                                           GridStage& S, const float* __restrict__ st = nullptr) {
   const double M = mean_anomaly(k, t);
   // centred remainder r = M - rint(M/2pi) 2pi (exact for ANY integer near M/2pi, so the FMA in the rint is free)
   const double kd = fma(M, H.c[4], H.c[5]) - H.c[5];
   const double rr = fma(-kd, H.c[1], M);
   S.sign_hi = __double2hiint(rr) & 0x80000000;
   const double Mr = fabs(rr);
-  const float E0f = markley_starter_f32(__double2float_rn(Mr), k);
+  const float Mf = __double2float_rn(Mr);
+  float E0f;
+  if (kTab) {
+    // node kn = rint(M kStartN/pi) from the low mantissa bits of x + 1.5*2^23, dx = x - kn in [-0.5, 0.5]
+    const float xs = fmaf(Mf, float(kStartN / 3.14159265358979323846), 12582912.0f);
+    const int kn = __float_as_int(xs) & 127;
+    const float dx = fmaf(Mf, float(kStartN / 3.14159265358979323846), 12582912.0f - xs);
+    E0f = fmaf(dx, fmaf(dx, st[2 * kStartStride + kn], st[kStartStride + kn]), st[kn]);
+  } else {
+    E0f = markley_starter_f32(Mf, k);
+  }
   // grid point: the low mantissa bits of E0*128 + 1.5*2^23 are rint(128 E0)
   const float km = fmaf(E0f, 128.0f, 12582912.0f);
   const float El = fmaf(km - 12582912.0f, -0.0078125f, E0f);
@@ -538,11 +577,46 @@ __device__ __forceinline__ double kep_grid_c(const KepConst& k, const GridStage&
   return fma(num, y2, acc);
 }
 
+template <bool kTab = false>
 __device__ __forceinline__ double kep_rv_grid(const KepConst& k, double t, double acc, const HotConsts& H,
-                                              const double2* __restrict__ tab, const float4* __restrict__ tabf) {
+                                              const double2* __restrict__ tab, const float4* __restrict__ tabf,
+                                              const float* __restrict__ st = nullptr) {
   GridStage S;
-  kep_grid_a(k, t, H, tab, tabf, S);
+  kep_grid_a<kTab>(k, t, H, tab, tabf, S, st);
   return kep_grid_c(k, S, acc, H);
+}
+
+// Build one planet's starter table (all 32 lanes of the walker's warp).  E at the 2*kStartN + 1 half-spaced points
+// M_j = j pi/(2 kStartN) by the FP32 Markley starter + two FP32 Newton steps (MUFU sin/cos: ~2e-6), plus the two
+// ghost points outside [0, pi] by symmetry; node n gets the quadratic through (n - 1/2, n, n + 1/2).
+// scratch: 2*kStartN + 3 floats of shared memory owned by the warp.
+__device__ __forceinline__ void build_start_table(const KepConst& k, float* st, float* scratch, int lane) {
+  const float hh = float(3.14159265358979323846 / (2 * kStartN));
+  for (int j = lane; j <= 2 * kStartN; j += 32) {
+    const float M = hh * float(j);
+    float E = (j == 0) ? 0.0f : markley_starter_f32(M, k);
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const float sE = __sinf(E), cE = __cosf(E);
+      E -= (fmaf(-k.ef, sE, E) - M) * f32_rcp(fmaf(-k.ef, cE, 1.0f));
+    }
+    if (j == 0) E = 0.0f;
+    if (j == 2 * kStartN) E = 3.14159274f;
+    scratch[j + 1] = E;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    scratch[0] = -scratch[2];                                            // E(-M) = -E(M)
+    scratch[2 * kStartN + 2] = 6.28318548f - scratch[2 * kStartN];       // E(pi + d) = 2 pi - E(pi - d)
+  }
+  __syncwarp();
+  for (int n = lane; n <= kStartN; n += 32) {
+    const float em = scratch[2 * n], e0 = scratch[2 * n + 1], ep = scratch[2 * n + 2];
+    st[n] = e0;
+    st[kStartStride + n] = ep - em;                       // slope per cell
+    st[2 * kStartStride + n] = 2.0f * ((ep - e0) - (e0 - em));  // curvature: 2 (E+ + E- - 2 E0)
+  }
+  __syncwarp();
 }
 
 // exp(x) for x <= 0 (decay factors of the MA block): n = rint(x log2 e), r = x - n ln2 (two-part),

@@ -24,7 +24,10 @@ namespace emp {
 
 constexpr int kTilePoints = 512;                       // datapoints per TMA tile
 constexpr int kTileBytes = kTilePoints * (3 * 8 + 4);  // t, y, e2 (FP64) + ins (int32)
-constexpr int kStages = 3;
+#ifndef EMP_STAGES
+#define EMP_STAGES 3
+#endif
+constexpr int kStages = EMP_STAGES;
 constexpr int kWalkerWarps = 8;                        // walkers per CTA
 constexpr int kLoglThreads = kWalkerWarps * 32;
 
@@ -75,8 +78,19 @@ __host__ __device__ constexpr size_t smem_tabf_off(uint32_t tile_bytes) {
 __host__ __device__ constexpr size_t smem_walker_off(uint32_t tile_bytes) {
   return smem_tabf_off(tile_bytes) + kGridN * sizeof(float4);
 }
-__host__ __device__ constexpr size_t logl_smem_bytes(uint32_t tile_bytes) {
+__host__ __device__ constexpr size_t smem_start_off(uint32_t tile_bytes) {
   return smem_walker_off(tile_bytes) + kWalkerWarps * sizeof(WalkerConst);
+}
+#ifndef EMP_STARTER_TABLE
+#define EMP_STARTER_TABLE 1  // per-walker starter tables (emp_device.cuh); 0 builds the Markley-only kernel (A/B)
+#endif
+// the starter tables are used when the rest leaves room for them with two CTAs per SM (no activity columns)
+__host__ __device__ constexpr bool logl_use_start_tables(uint32_t tile_bytes) {
+  return EMP_STARTER_TABLE && tile_bytes == kTileBytes;
+}
+__host__ __device__ constexpr size_t logl_smem_bytes(uint32_t tile_bytes) {
+  return smem_start_off(tile_bytes) +
+         (logl_use_start_tables(tile_bytes) ? size_t(kWalkerWarps) * kStartFloats * sizeof(float) : 0);
 }
 constexpr uint32_t kTileBytesMax = kTileBytes + EMP_MAX_SAI * kTilePoints * 8;
 static_assert(2 * kStages * sizeof(uint64_t) <= 64 && kTileBytes % 16 == 0 && (kTilePoints * 8) % 16 == 0,
@@ -356,6 +370,9 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
   double2* tab = reinterpret_cast<double2*>(smem + smem_tab_off(tile_bytes));
   float4* tabf = reinterpret_cast<float4*>(smem + smem_tabf_off(tile_bytes));
   WalkerConst* wcs = reinterpret_cast<WalkerConst*>(smem + smem_walker_off(tile_bytes));
+  const bool use_tab = logl_use_start_tables(tile_bytes);
+  float* start_tab = reinterpret_cast<float*>(smem + smem_start_off(tile_bytes)) +
+                     size_t(threadIdx.x >> 5) * kStartFloats;
 
   const int n_active = *P.n_active;
   const int first = blockIdx.x * kWalkerWarps;
@@ -394,6 +411,17 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
     load_full_theta(d, P.theta + slot * d->ndim_free, wc.th, lane);
     walker_constants(d, wc, lane, P.t_absmax);
     if (P.solver == EMP_SOLVER_KEPLERPY && lane < d->n_kep) wc.kep[lane].robust = 1;
+    __syncwarp();
+    if (use_tab) {  // starter tables of the planets the grid core serves (wc.th is free again: scratch)
+      const int nk = d->n_kep < kStartPlanets ? d->n_kep : kStartPlanets;
+      for (int k = 0; k < nk; ++k) {
+        KepConst& kc = wc.kep[k];
+        const bool ok = (kc.slow_mod | kc.robust) == 0 && kc.ef <= kStartEccMax;  // warp-uniform
+        if (ok) build_start_table(kc, start_tab + k * 3 * kStartStride, reinterpret_cast<float*>(wc.th), lane);
+        if (lane == 0) kc.tab = ok ? 1 : 0;
+      }
+      __syncwarp();
+    }
   }
   __syncthreads();  // publishes the barrier inits and the grid to all warps
 
@@ -434,7 +462,11 @@ __global__ void __launch_bounds__(kLoglThreads, 2) logl_rv_kernel(const LoglPara
         double m[4] = {0.0, 0.0, 0.0, 0.0};
         for (int k = 0; k < K; ++k) {
           const KepConst& kc = wc.kep[k];
-          if ((kc.slow_mod | kc.robust) == 0) {  // warp-uniform
+          if (kc.tab) {  // warp-uniform: starter from the walker's table
+            const float* st = start_tab + k * 3 * kStartStride;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) m[j] = kep_rv_grid<true>(kc, t[j], m[j], P.H, tab, tabf, st);
+          } else if ((kc.slow_mod | kc.robust) == 0) {  // warp-uniform
 #pragma unroll
             for (int j = 0; j < 4; ++j)  // straight-line code: the scheduler interleaves the four chains
               m[j] = kep_rv_grid(kc, t[j], m[j], P.H, tab, tabf);

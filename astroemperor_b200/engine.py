@@ -288,3 +288,13 @@ def kepler_solve_grid(M, ecc, device: int = 0):
     _lib.check(_lib.lib().emp_kepler_grid_host(M.ctypes.data, ecc.ctypes.data, M.size, 1 if scalar else 0,
                                                E.ctypes.data, s.ctypes.data, c.ctypes.data, int(device)))
     return E, s, c
+
+
+def kepler_solve_grid_table(M, ecc: float, device: int = 0):
+    """The grid core started from the per-walker starter table (what table-served planets run inside the likelihood
+    kernel): (E, sin E, cos E) for one eccentricity in [0, 0.8]."""
+    M = np.ascontiguousarray(M, dtype=np.float64)
+    E, s, c = np.empty_like(M), np.empty_like(M), np.empty_like(M)
+    _lib.check(_lib.lib().emp_kepler_grid_table_host(M.ctypes.data, float(ecc), M.size, E.ctypes.data, s.ctypes.data,
+                                                     c.ctypes.data, int(device)))
+    return E, s, c

@@ -352,6 +352,20 @@ class PTSampler:
         lay["evt"][i].record()
         return lay["out"][i]
 
+    def draw_resident(self, nsteps: int):
+        """Draw one sweep and keep it packed in device memory (bench.py: the draws of the timed steps are
+        resident in HBM before the clock starts); feed it back with `stage_resident`."""
+        out = self.draw_staged(nsteps)
+        return self._lay["dev"][out["_stage_index"]].clone()
+
+    def stage_resident(self, packed):
+        """Device-to-device copy of a `draw_resident` buffer into the next staging slot (the slots are what the
+        captured graphs point at); returns the dict of device views `sweep_begin` takes."""
+        lay = self._lay
+        i = lay["i"] = 1 - lay["i"]
+        lay["dev"][i].copy_(packed, non_blocking=True)
+        return lay["out"][i]
+
     def _sweep_args(self, draws, nsteps):
         """The EmpPtSweep argument block of one sweep (include/emperor_b200.h).  The blocks of the steady state
         (double-buffered state x double-buffered staging) are built once and reused."""

@@ -366,9 +366,9 @@ def run_leg(cx, name, steps, warmup, burn, cpu_budget):
     eng, samp, T = make_sampler(cx, wl, total_sweeps=burn + warmup + 2 * steps + 8)
     W, N = wl.w["W"], wl.n_units
     samp.run_mcmc(None, nsweeps=burn + warmup, nsteps=1)
-    # value: draws pre-generated on the host (no RNG in the timed region), staged through the pinned
-    # double buffer, sweeps replayed from the CUDA graph
-    pre = [samp.draw(1) for _ in range(steps)]
+    # value: the draws of the timed steps are resident in HBM before the clock starts; per step a device-to-device
+    # copy into the staging slot the captured graph reads, then the graph replay
+    pre = [samp.draw_resident(1) for _ in range(steps)]
     cx.barrier()
     c0 = eng.counters()
     l0 = eng.launch_count
@@ -376,7 +376,7 @@ def run_leg(cx, name, steps, warmup, burn, cpu_budget):
     tw0 = time.perf_counter()
     ev0.record()
     for d in pre:
-        samp.sweep_begin(samp.stage_draws(d, pinned=True))
+        samp.sweep_begin(samp.stage_resident(d))
     ev1.record()
     cx.barrier()
     tw1 = time.perf_counter()
@@ -494,8 +494,8 @@ def main():
 
     # ---------------- value: draws resident in HBM -----------------------------------------
     for _ in range(args.warmup):
-        samp.sweep_begin(samp.draw(1))
-    staged = [samp.stage_draws(samp.draw(1)) for _ in range(args.steps)]
+        samp.sweep_begin(samp.draw_staged(1))
+    staged = [samp.draw_resident(1) for _ in range(args.steps)]
     eng.set_timing(True)   # per-launch events around the likelihood kernel (the sweep then runs un-graphed)
     samp.profile = True
     samp.phase_times()
@@ -506,7 +506,7 @@ def main():
     tw0 = time.perf_counter()
     ev0.record()
     for k in range(args.steps):
-        samp.sweep_begin(staged[k])
+        samp.sweep_begin(samp.stage_resident(staged[k]))
     ev1.record()
     cx.barrier()
     tw1 = time.perf_counter()

@@ -215,6 +215,12 @@ int emp_kepler_solve_host(const double *M, const double *ecc, int64_t n, int ecc
 int emp_kepler_grid_host(const double *M, const double *ecc, int64_t n, int ecc_is_scalar, double *E,
                          double *sinE, double *cosE, int device);
 
+/* The same core with the per-walker STARTER TABLE the likelihood kernel builds in its prologue (emp_device.cuh,
+ * kernel v10) instead of the Markley starter: one eccentricity in [0, 0.8] for the whole array, |M| < 1e12.  Exists
+ * so that the production path of table-served planets can be pinned element by element too. */
+int emp_kepler_grid_table_host(const double *M, double ecc, int64_t n, double *E, double *sinE, double *cosE,
+                               int device);
+
 /* ---- parallel-tempering step -------------------------------------------- */
 
 /* One emcee RedBlue stretch-move step of every temperature held by this handle
