@@ -108,7 +108,8 @@ class Workload:
         """(theta) -> (logl, logp) the way the generated script computes them (oracle/, CPU)."""
         from oracle.rv_oracle import RVOracle
         cm = self.spec.compile()
-        ro = RVOracle(cm, self.t, self.y, self.yerr, self.flag)
+        # c4noop: the reference's default per-instrument MA template executes a Python loop whose writes are lost
+        ro = RVOracle(cm, self.t, self.y, self.yerr, self.flag, run_noop_ma_loop=(self.w.get("ma") == "perins"))
         ao = None
         if self.am is not None:
             from oracle.am_oracle import AMOracle

@@ -35,8 +35,11 @@ class RVOracle:
     """One generated script's worth of functions, for a compiled model
     (astroemperor_b200.modelspec.CompiledModel is only read as plain data)."""
 
-    def __init__(self, cm, t, y, yerr, flag, sai=None):
+    def __init__(self, cm, t, y, yerr, flag, sai=None, run_noop_ma_loop=False):
         self.cm = cm
+        # moav00.model's loop has no effect on logL (see my_model) but it is what the reference EXECUTES per call;
+        # run_noop_ma_loop=True runs the same statements so that the CPU baseline can time the default template
+        self.run_noop_ma_loop = bool(run_noop_ma_loop)
         # emp_model.py:425-433: SAI{j}_ = my_data.iloc[:, 3 + j].values, one array per activity column
         self.SAI_ = None if sai is None else np.ascontiguousarray(sai, dtype=np.float64).reshape(len(t), -1)
         self.X_ = np.ascontiguousarray(t, dtype=np.float64)
@@ -169,7 +172,26 @@ class RVOracle:
                 model0 += A1 * np.cos(M1) + A2 * np.cos(M2)
         # cm.ma_mode == 1 (support/models/moav00.model): `model0[mask][i] += MA`
         # writes into a temporary copy, so the block has NO effect on model0 / err20
-        # (SURVEY.md §0 fact 3); nothing to do.
+        # (SURVEY.md §0 fact 3); nothing to do — unless the caller wants the reference's COST:
+        if cm.ma_mode == 1 and self.run_noop_ma_loop:
+            residuals = Y_ - model0  # emp_model.py:757-762
+            order = cm.ma_order
+            for n in range(cm.n_ins):  # moav00.model:4-19, once per instrument
+                mask = self.masks[n]
+                t_ = X_[mask]
+                res_ = residuals[mask]
+                theta_ma = theta[cm.ma_off:cm.ma_off + 2 * order * cm.n_ins][order * 2 * n:order * 2 * (n + 1)]
+                ndat_n = int(np.sum(mask))
+                if order > 0:
+                    for c in range(order):
+                        macoef = theta_ma[2 * c]
+                        matime = theta_ma[2 * c + 1]
+                        for i in range(1, ndat_n):
+                            if i > c:
+                                dt = abs(t_[i] - t_[i - 1 - c])
+                                MA = macoef * np.exp(-dt / matime) * res_[i - 1 - c]
+                                model0[mask][i] += MA      # fancy-index copy: discarded
+                                residuals[mask][i] -= MA   # ditto
         return model0, err20
 
     # support/likelihoods/00.like:3-5

@@ -16,7 +16,9 @@ def main():
     g, spec = load_golden("c2_synth3p_2ins_n400")
     T, W, nsweeps, nsteps = 4 * world, 64, 6, 2
     eng = LikelihoodEngine(spec, g["t"], g["y"], g["yerr"], g["flag"], device=lr)
-    samp = PTSampler(W, eng.ndim, eng, ntemps=T, seed=77)
+    exchange = sys.argv[1] if len(sys.argv) > 1 else "peer"
+    samp = PTSampler(W, eng.ndim, eng, ntemps=T, seed=77, exchange=exchange)
+    samp.D_ = spec.prior_widths()
     obj = [samp.initial_positions(spec) if rank == 0 else None]
     td.broadcast_object_list(obj, src=0)
     p0 = obj[0]
@@ -35,14 +37,15 @@ def main():
         if r == rank:
             solo_group = grp
     solo = PTSampler(W, eng.ndim, eng, ntemps=T, seed=77, group=solo_group)
+    solo.D_ = spec.prior_widths()
     solo.run_mcmc(p0, nsweeps=nsweeps, nsteps=nsteps)
     c1, l1 = solo.get_chain(), solo.get_log_like()
     same = np.array_equal(c1, chain) and np.array_equal(l1, ll) and np.array_equal(solo.get_betas(), betas) \
-        and np.array_equal(solo.get_tsw(), tsw)
+        and np.array_equal(solo.get_tsw(), tsw) and np.allclose(solo.get_smd(), samp.get_smd(), rtol=1e-12)
     res = torch.tensor([1 if same else 0], device="cuda")
     td.all_reduce(res, op=td.ReduceOp.MIN)
     if rank == 0:
-        print(f"dist_parity world={world} T={T} W={W}: sharded == single-GPU chains: {bool(res.item())}; "
+        print(f"dist_parity world={world} T={T} W={W} exchange={exchange}: sharded == single-GPU chains: {bool(res.item())}; "
               f"swap rates {tsw.mean(axis=0).round(3)}")
     td.destroy_process_group()
     sys.exit(0 if res.item() == 1 else 1)
