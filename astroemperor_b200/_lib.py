@@ -52,7 +52,7 @@ class EmpPtSweepC(ctypes.Structure):
                 ("adapt", _I32), ("thin", _I32), ("adapt_tau", ctypes.c_double), ("adapt_nu", ctypes.c_double),
                 ("sweep_counter", _P), ("step_counter", _P), ("beta_hist", _P), ("nacc_hist", _P), ("smd_hist", _P),
                 ("hist_cap", _I64), ("D", _P), ("chain", _P), ("chain_ll", _P), ("chain_lp", _P),
-                ("store_cap", _I64), ("store_ring", _I32), ("_pad", _I32),
+                ("store_cap", _I64), ("store_ring", _I32), ("perm_hot_sorted", _I32),
                 ("peer_p", _P * EMP_MAX_PEERS), ("peer_logl", _P * EMP_MAX_PEERS), ("peer_logp", _P * EMP_MAX_PEERS),
                 ("logl_all", _P)]
 

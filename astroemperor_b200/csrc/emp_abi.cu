@@ -638,7 +638,11 @@ static int enqueue_plan(EmpHandle* h, const PtPlan& A, cudaStream_t st) {
   using PlanKernel = void (*)(const PtPlan);
   PlanKernel k = nullptr;
   size_t smem = 0;
-  if (smem3 <= kPlanSmemMax) {
+  if (A.hot_sorted && smem2 <= kPlanSmemMax && W <= 8192) {
+    k = W <= 1024 ? pt_swap_plan_sorted_kernel<1> : W <= 2048 ? pt_swap_plan_sorted_kernel<2>
+      : W <= 4096 ? pt_swap_plan_sorted_kernel<4> : pt_swap_plan_sorted_kernel<8>;
+    smem = smem2;
+  } else if (smem3 <= kPlanSmemMax) {
     k = W <= 1024 ? pt_swap_plan_kernel<1, 3> : W <= 2048 ? pt_swap_plan_kernel<2, 3>
       : W <= 4096 ? pt_swap_plan_kernel<4, 3> : pt_swap_plan_kernel<6, 3>;
     smem = smem3;
@@ -659,7 +663,9 @@ static int ensure_plan_scratch(EmpHandle* h, int32_t W) {
   if (!h->plan_attr_set) {  // once per handle, not per call
     const void* ks[] = {(const void*)pt_swap_plan_kernel<1, 3>, (const void*)pt_swap_plan_kernel<2, 3>,
                         (const void*)pt_swap_plan_kernel<4, 3>, (const void*)pt_swap_plan_kernel<6, 3>,
-                        (const void*)pt_swap_plan_kernel<8, 2>};
+                        (const void*)pt_swap_plan_kernel<8, 2>, (const void*)pt_swap_plan_sorted_kernel<1>,
+                        (const void*)pt_swap_plan_sorted_kernel<2>, (const void*)pt_swap_plan_sorted_kernel<4>,
+                        (const void*)pt_swap_plan_sorted_kernel<8>};
     for (const void* k : ks)
       CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kPlanSmemMax)));
     h->plan_attr_set = true;
@@ -814,6 +820,7 @@ static int enqueue_swap_phase(EmpHandle* h, const EmpPtSweep* s, cudaStream_t st
   P.logl = (s->n_ranks > 1) ? s->logl_all : s->logl;
   P.betas = s->betas; P.perm = s->perm; P.lnu = s->lnu_swap; P.src = s->src; P.n_acc = s->n_acc;
   P.adapt = s->adapt; P.adapt_tau = s->adapt_tau; P.adapt_nu = s->adapt_nu;
+  P.hot_sorted = s->perm_hot_sorted;
   P.sweep_counter = (long long*)s->sweep_counter;
   P.beta_hist = s->beta_hist; P.nacc_hist = s->nacc_hist; P.hist_cap = s->hist_cap;
   int rc = enqueue_plan(h, P, st);

@@ -215,19 +215,29 @@ static void stretch_stream(Mt19937& g, int j, int n_temps, int W, int nsteps, in
   }
 }
 
-// Swap draws of one adjacent pair, consumed hot -> cold: permutation(W), permutation(W), uniform(size=W).
+// Swap draws of one adjacent pair, consumed hot -> cold: permutation(W), permutation(W), uniform(size=W) — then
+// RELABELLED: the reference pairs slot iperm[k] of the warmer row with slot i1perm[k] of the colder one under the
+// uniform u[k]; the same set of (a, b, u) triples is handed over listed by a (row 0 = identity, row 1 = b(a),
+// u = u(a)), which lets the plan kernel keep the warmer row in registers (emp_pt.cuh).  No decision changes.
 static void swap_stream(Mt19937* g, int W, int32_t* p0, double* uk) {
   if (!g) {  // padding row of a sharded ladder
     memset(p0, 0, 2 * size_t(W) * sizeof(int32_t));
     for (int i = 0; i < W; ++i) uk[i] = 1.0;  // ln 1 = 0
     return;
   }
-  for (int r = 0; r < 2; ++r) {
-    int32_t* p = p0 + size_t(r) * W;
-    for (int i = 0; i < W; ++i) p[i] = i;
-    g->shuffle(p, W);
+  std::vector<int32_t> a(W), b(W);
+  std::vector<double> u(W);
+  for (int i = 0; i < W; ++i) a[i] = i;
+  g->shuffle(a.data(), W);
+  for (int i = 0; i < W; ++i) b[i] = i;
+  g->shuffle(b.data(), W);
+  for (int i = 0; i < W; ++i) u[i] = g->next_double();
+  int32_t* p1 = p0 + W;
+  for (int k = 0; k < W; ++k) {
+    p0[a[k]] = a[k];
+    p1[a[k]] = b[k];
+    uk[a[k]] = u[k];
   }
-  for (int i = 0; i < W; ++i) uk[i] = g->next_double();
 }
 
 // All draws of one sweep in one parallel region: the stretch draws of the temperatures temp_streams[n_temps]

@@ -38,7 +38,8 @@ class SweepDraws:
     rint: np.ndarray      # [nsteps, T_loc, 2, H] int32
     factors: np.ndarray   # [nsteps, T_loc, 2, H]  (ndim-1)*log(zz)
     lnu: np.ndarray       # [nsteps, T_loc, 2, H]  log(u)
-    perm: np.ndarray      # [R, 2, W] int32: the row of pair j couples temperature j+1 (row 0) with j (row 1)
+    perm: np.ndarray      # [R, 2, W] int32: the row of pair j couples temperature j+1 (row 0) with j (row 1);
+                          # relabelled so that row 0 is the identity (relabel_swap_draws)
     lnu_swap: np.ndarray  # [R, W]   (R = T-1 pairs, or this rank's rows of a sharded ladder)
     sharded_swap: bool = False  # perm / lnu_swap hold only this rank's pair rows (to be all-gathered)
 
@@ -121,6 +122,15 @@ def draw_stretch(rng: np.random.RandomState, W: int, nsteps: int, a: float = 2.0
     return half_idx, zz, rint, u
 
 
+def relabel_swap_draws(iperm, i1perm, u):
+    """The reference's swap sweep pairs slot iperm[k] of the warmer row with slot i1perm[k] of the colder one
+    under the uniform u[k].  The same SET of (a, b, u) triples listed by a: row 0 becomes the identity, row 1 the
+    partner b(a), u the uniform of that pair.  Nothing about the sweep changes (the pairs of one sweep are
+    disjoint), but thread a of the plan kernel then owns slot a of the warmer row (emp_pt.cuh)."""
+    order = np.argsort(iperm, kind="stable")  # inverse permutation
+    return iperm[order], i1perm[order], u[order]
+
+
 def sweep_shapes(T_loc: int, W: int, nsteps: int, n_rows: int):
     """(field, shape, dtype) of the seven arrays of a sweep's draws, in SweepDraws.FIELDS order."""
     H = W // 2
@@ -168,9 +178,8 @@ def draw_sweep(streams: DrawStreams, W: int, ndim: int, nsteps: int, a: float = 
                 if j >= T - 1:
                     continue
                 rng = streams.swap_pair[j]
-                perm[k, 0] = rng.permutation(W)
-                perm[k, 1] = rng.permutation(W)
-                lnu_swap[k] = rng.uniform(size=W)
+                iperm, i1perm, u = rng.permutation(W), rng.permutation(W), rng.uniform(size=W)
+                perm[k, 0], perm[k, 1], lnu_swap[k] = relabel_swap_draws(iperm, i1perm, u)
     # the logs are NumPy's on both paths: device and oracle compare against the same bits
     np.multiply(np.log(zz), ndim - 1.0, out=factors)
     with np.errstate(divide="ignore"):

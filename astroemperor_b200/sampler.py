@@ -409,6 +409,7 @@ class PTSampler:
             A.chain, A.chain_ll, A.chain_lp = tgt[0].data_ptr(), tgt[1].data_ptr(), tgt[2].data_ptr()
             A.store_cap = tgt[0].shape[0]
             A.store_ring = 1 if self.store == "host" else 0
+        A.perm_hot_sorted = 1  # draws.py lists every pair by its slot in the warmer row
         if sh.world == 1 and self.ntemps > 1:
             A.perm, A.lnu_swap = draws["perm"].data_ptr(), draws["lnu_swap"].data_ptr()
         if key[1] is not None:

@@ -307,7 +307,8 @@ typedef struct EmpPtSweep {
   double *chain, *chain_ll, *chain_lp; /* [store_cap, T_loc, W, ndim] / [store_cap, T_loc, W] or NULL */
   int64_t store_cap;
   int32_t store_ring;       /* 1: slot index wraps at store_cap (host streams the ring out)        */
-  int32_t _pad;
+  int32_t perm_hot_sorted;  /* 1: perm[j, 0, :] is the identity for every pair (the host lists the pairs by
+                             * their slot in the warmer row): the plan kernel then keeps that row in registers */
   /* sharded ladder only: CURRENT buffers (p, logl, logp) of every rank, peer HBM mapped with
    * emp_ipc_open; entry `rank` must equal p / logl / logp */
   const double *peer_p[EMP_MAX_PEERS], *peer_logl[EMP_MAX_PEERS], *peer_logp[EMP_MAX_PEERS];

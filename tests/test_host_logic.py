@@ -69,7 +69,26 @@ def test_draw_sweep_protocol():
     assert np.array_equal(d.factors, (nd - 1.0) * np.log(d.zz))
     assert np.all(d.rint >= 0) and np.all(d.rint < 5) and np.all(d.lnu <= 0)
     for j in range(T - 1):
-        assert np.array_equal(np.sort(d.perm[j, 0]), np.arange(W))
+        assert np.array_equal(d.perm[j, 0], np.arange(W))  # pairs are listed by their slot in the warmer row
+        assert np.array_equal(np.sort(d.perm[j, 1]), np.arange(W))
+    # ... which is a relabelling of the reference's draw order (permutation, permutation, uniform per pair)
+    from astroemperor_b200.draws import relabel_swap_draws
+    from oracle.pt_oracle import swap_sweep
+    r = DrawStreams(1, T).swap_pair[1]
+    ip, i1p, u = r.permutation(W), r.permutation(W), r.uniform(size=W)
+    assert np.array_equal(d.perm[1, 1][ip], i1p) and np.array_equal(d.lnu_swap[1][ip], np.log(u))
+    # and the swap sweep it drives is the same sweep: same counts, same plan, same state
+    rng = np.random.RandomState(0)
+    raw = [(q.permutation(W), q.permutation(W), q.uniform(size=W)) for q in DrawStreams(1, T).swap_pair]
+    p_a, p_b = rng.normal(size=(T, W, 3)), None
+    p_b = p_a.copy()
+    ll = rng.normal(size=(T, W)) * 3
+    betas = np.linspace(1, 0.2, T)
+    perm_raw = np.array([[a, b] for a, b, _ in raw]).astype(np.int32)
+    lnu_raw = np.log(np.array([c for _, _, c in raw]))
+    na, src_a, _ = swap_sweep(p_a, ll.copy(), np.zeros((T, W)), betas, perm_raw, lnu_raw)
+    nb, src_b, _ = swap_sweep(p_b, ll.copy(), np.zeros((T, W)), betas, d.perm, d.lnu_swap)
+    assert np.array_equal(na, nb) and np.array_equal(src_a, src_b) and np.array_equal(p_a, p_b)
     # each temperature's stream is consumed in emcee's order: re-derive temperature 1 by hand
     r = DrawStreams(1, T).temp[1]
     inds = np.arange(W) % 2
