@@ -126,42 +126,67 @@ def evidence_ss(logl, betas, n_batches=8):
 
 
 # ---- chain sink in the reference's backend layout (emp.py:722-762) ------------------------------
-def save_backend(sampler, name, discard=0):
-    """Dump the run in the layout EMPEROR writes after a reddemcee run: per temperature
-    `chain[iter, W, ndim]`, `log_like`, `log_prob`, `beta_history`, `accepted` (+ `tsw_history`,
-    `smd_history`, `iteration`).  With h5py installed it writes `<name>.h5` and `<name>_<t>.h5`
-    groups named 'mcmc' like `reddemcee.hdf.PTHDFBackend`; without it (this image) an `.npz`
-    with the same dataset names."""
-    chain = sampler.get_chain(discard=discard)           # [T, n, W, ndim]
-    ll = sampler.get_log_like(discard=discard)
-    lpost = sampler.get_log_prob(discard=discard)
-    betas = sampler.get_betas(discard=discard)           # [n, T]
-    accepted = sampler.acceptance_fraction * max(sampler._n_steps, 1)
-    tsw, smd = sampler.get_tsw(discard=discard), sampler.get_smd(discard=discard)
-    T, n = chain.shape[0], chain.shape[1]
+def _h5_write(path, group, attrs, datasets):
+    """One HDF5 file with one group: h5py where it is installed, else the minimal writer of h5min.py."""
     try:
         import h5py
     except ImportError:
-        h5py = None
-    if h5py is None:
-        path = name + ".npz"
-        np.savez_compressed(path, chain=chain, log_like=ll, log_prob=lpost, beta_history=betas,
-                            accepted=accepted, tsw_history=tsw, smd_history=smd, iteration=n)
-        return path
-    with h5py.File(name + ".h5", "w") as f:
-        g = f.create_group("mcmc")
-        g.attrs["iteration"], g.attrs["ntemps"] = n, T
-        g.create_dataset("tsw_history", data=tsw)
-        g.create_dataset("smd_history", data=smd)
+        from .h5min import write_h5
+        return write_h5(path, {group: {"attrs": attrs, "datasets": datasets}})
+    with h5py.File(path, "w") as f:
+        g = f.create_group(group)
+        for k, v in attrs.items():
+            g.attrs[k] = v
+        for k, v in datasets.items():
+            g.create_dataset(k, data=v)
+    return path
+
+
+def _h5_read(path, group):
+    try:
+        import h5py
+    except ImportError:
+        from .h5min import read_h5
+        g = read_h5(path)[group]
+        return g["attrs"], g["datasets"]
+    with h5py.File(path, "r") as f:
+        g = f[group]
+        return dict(g.attrs), {k: g[k][...] for k in g}
+
+
+def save_backend(sampler, name, discard=0, group="mcmc"):
+    """Dump the run in the layout EMPEROR's generated script writes after a reddemcee run (emp.py:722-762) and its
+    parent reads back (emp.py:781-789, `reddemcee.hdf.PTHDFBackend` + one emcee-style `HDFBackend_plus` per
+    temperature): `<name>.h5` with group 'mcmc' {attrs iteration (sweeps), ntemps, nwalkers, ndim; datasets
+    tsw_history, smd_history} and `<name>_<t>.h5` with group 'mcmc' {attrs iteration (stored steps), nwalkers,
+    ndim, has_blobs, version; datasets chain[iter, W, ndim], log_like, log_prob, beta_history[iter], accepted[W]}.
+    `discard` counts stored steps (sweep histories are cut at the sweep of the first kept step).
+    A sharded ladder gathers first (every rank returns the same file name; rank 0 writes)."""
+    chain = sampler.get_chain(discard=discard)           # [T, n, W, ndim]
+    ll = sampler.get_log_like(discard=discard)
+    lpost = sampler.get_log_prob(discard=discard)
+    betas = sampler.get_betas(discard=discard)           # [n, T] per stored step
+    n_steps = int(getattr(sampler, "_n_steps", chain.shape[1]))
+    accepted = np.rint(np.asarray(sampler.acceptance_fraction) * max(n_steps, 1)).astype(np.int64)
+    ss = np.asarray(getattr(sampler, "_sample_sweep", []), dtype=np.int64)
+    d_sweeps = int(ss[discard]) if (discard and len(ss) > discard) else 0
+    tsw, smd = sampler.get_tsw(discard=d_sweeps), sampler.get_smd(discard=d_sweeps)
+    T, n, W, nd = chain.shape
+    shard = getattr(sampler, "shard", None)
+    if shard is not None and shard.world > 1 and shard.rank != 0:
+        return name + ".h5"
+    from . import __version__ as ver
+    _h5_write(name + ".h5", group,
+              dict(iteration=int(len(tsw)), ntemps=T, nwalkers=W, ndim=nd, version=f"b200-{ver}", n_steps=n_steps,
+                   thin_by=int(getattr(sampler, "thin_by", 1)), tsw_history_bool=bool(len(tsw)),
+                   smd_history_bool=bool(np.size(smd))),
+              dict(tsw_history=np.asarray(tsw, dtype=np.float64), smd_history=np.asarray(smd, dtype=np.float64),
+                   betas=np.asarray(sampler.betas, dtype=np.float64)))
     for t in range(T):
-        with h5py.File(f"{name}_{t}.h5", "w") as f:
-            g = f.create_group("mcmc")
-            g.attrs["iteration"] = n
-            g.create_dataset("chain", data=chain[t])
-            g.create_dataset("log_like", data=ll[t])
-            g.create_dataset("log_prob", data=lpost[t])
-            g.create_dataset("beta_history", data=betas[:, t])
-            g.create_dataset("accepted", data=accepted[t])
+        _h5_write(f"{name}_{t}.h5", group,
+                  dict(iteration=n, nwalkers=W, ndim=nd, has_blobs=False, version=f"b200-{ver}"),
+                  dict(chain=chain[t], log_like=ll[t], log_prob=lpost[t], beta_history=betas[:, t],
+                       accepted=accepted[t]))
     return name + ".h5"
 
 
@@ -254,23 +279,22 @@ class _StoredBackend:
         return _T()
 
 
-def load_backend(name) -> StoredRun:
-    """Read what `save_backend(sampler, name)` wrote: `<name>.npz`, or `<name>.h5` + `<name>_<t>.h5` where h5py
-    is installed (the reference's PTHDFBackend / HDFBackend_plus file layout, emp.py:781-785)."""
+def load_backend(name, group="mcmc") -> StoredRun:
+    """Read what `save_backend(sampler, name)` wrote: `<name>.h5` + `<name>_<t>.h5` (the reference's PTHDFBackend /
+    HDFBackend_plus file layout, emp.py:781-785; h5py where installed, h5min otherwise), or the `.npz` of round 1."""
     import os
-    if os.path.exists(name + ".npz"):
+    if not os.path.exists(name + ".h5") and os.path.exists(name + ".npz"):
         z = np.load(name + ".npz")
         return StoredRun(z["chain"], z["log_like"], z["log_prob"], z["beta_history"], z["accepted"],
                          z["tsw_history"], z["smd_history"])
-    import h5py
-    with h5py.File(name + ".h5", "r") as f:
-        g = f["mcmc"]
-        T = int(g.attrs["ntemps"])
-        tsw, smd = g["tsw_history"][...], g["smd_history"][...]
+    a, d = _h5_read(name + ".h5", group)
+    T = int(a["ntemps"])
     parts = []
     for t in range(T):
-        with h5py.File(f"{name}_{t}.h5", "r") as f:
-            g = f["mcmc"]
-            parts.append([g[k][...] for k in ("chain", "log_like", "log_prob", "beta_history", "accepted")])
+        _, dt = _h5_read(f"{name}_{t}.h5", group)
+        parts.append([dt[k] for k in ("chain", "log_like", "log_prob", "beta_history", "accepted")])
     ch, ll, lpost, bh, acc = (np.stack([p[i] for p in parts]) for i in range(5))
-    return StoredRun(ch, ll, lpost, bh.T, acc, tsw, smd)
+    run = StoredRun(ch, ll, lpost, bh.T, acc, d["tsw_history"], d["smd_history"], n_steps=int(a.get("n_steps", 0)) or None)
+    if "betas" in d and len(d["betas"]) == T:
+        run.betas = np.asarray(d["betas"], dtype=np.float64)
+    return run

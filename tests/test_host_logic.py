@@ -382,7 +382,7 @@ def test_backend_round_trip_without_a_device(tmp_path):
 
     class Stub:
         _n_steps = n
-        acceptance_fraction = rng.uniform(0.1, 0.5, (T, W))
+        acceptance_fraction = rng.integers(4, 20, (T, W)) / n
 
         def __init__(self):
             self.chain = rng.normal(size=(T, n, W, nd))
@@ -390,6 +390,7 @@ def test_backend_round_trip_without_a_device(tmp_path):
             self.lpost = self.ll * betas[:, None, None] - 1.0
             self.bh = np.tile(betas, (n, 1))
             self.tsw, self.smd = rng.uniform(size=(n, T - 1)), rng.uniform(size=(n, T - 1))
+            self.betas = betas
 
         def get_chain(self, discard=0): return self.chain[:, discard:]
         def get_log_like(self, discard=0): return self.ll[:, discard:]
@@ -400,7 +401,9 @@ def test_backend_round_trip_without_a_device(tmp_path):
 
     s = Stub()
     path = save_backend(s, str(tmp_path / "run"))
-    assert os.path.exists(path)
+    # the reference's file layout (emp.py:781-786): <name>.h5 + one <name>_<t>.h5 per temperature, HDF5
+    assert path.endswith(".h5") and all(os.path.exists(str(tmp_path / f"run_{t}.h5")) for t in range(T))
+    assert open(path, "rb").read(8) == b"\x89HDF\r\n\x1a\n"
     r = load_backend(str(tmp_path / "run"))
     assert (r.ntemps, r.iteration, r.nwalkers, r.ndim) == (T, n, W, nd)
     assert np.array_equal(r.get_chain(), s.chain) and np.array_equal(r.betas, betas)

@@ -196,7 +196,12 @@ def test_postprocessing_reductions_and_smd(tmp_path):
     print(f"logZ: stepping-stone {z_ss:.3f} +- {e_ss:.3f}, TI {z_ti:.3f} +- {e_ti:.3f}, quadrature {logz_ref:.3f}")
     assert abs(z_ss - logz_ref) < 0.5 and abs(z_ti - logz_ref) < 2.0, (z_ss, z_ti, logz_ref)
     path = samp.save_backend(str(tmp_path / "run"), discard=10)
-    assert path.endswith((".npz", ".h5"))
-    if path.endswith(".npz"):
-        d = np.load(path)
-        assert d["chain"].shape == (T, 790, 32, eng.ndim) and d["beta_history"].shape == (790, T)
+    assert path.endswith(".h5")
+    from astroemperor_b200.postproc import load_backend
+    r = load_backend(str(tmp_path / "run"))   # the reference's per-temperature HDF5 layout, read back without a device
+    assert r.get_chain().shape == (T, 790, 32, eng.ndim) and r.get_betas().shape == (790, T)
+    assert np.array_equal(r.get_chain(), samp.get_chain(discard=10))
+    assert np.array_equal(r.get_log_prob(), samp.get_log_prob(discard=10))
+    assert r.get_tsw().shape == (395, T - 1) and np.array_equal(r.get_tsw(), samp.get_tsw(discard=5))
+    assert np.allclose(r.acceptance_fraction, samp.acceptance_fraction)
+    assert np.isclose(r.get_evidence_ss(discard=190)[0], z_ss)
