@@ -78,6 +78,7 @@ struct EmpHandle {
   int32_t* d_nact = nullptr;   // its length
   int32_t* d_nact2 = nullptr;  // PT step: one counter per half (the likelihood kernel of one half re-zeroes the other)
   bool plan_attr_set = false;
+  bool plan_no_tma = false;          // EMP_PLAN_NO_TMA=1: keep the register-prefetch plan kernels (A/B measurements)
   double* d_smd_part = nullptr;      // swap-mean-distance partial sums of the plan application
   uint32_t* d_smd_ticket = nullptr;
   int64_t cap_smd = 0;
@@ -638,6 +639,12 @@ static int enqueue_plan(EmpHandle* h, const PtPlan& A, cudaStream_t st) {
   using PlanKernel = void (*)(const PtPlan);
   PlanKernel k = nullptr;
   size_t smem = 0;
+  const int tma_stages = int(std::min<size_t>(kPlanSmemMax / (size_t(W) * 24), 8));
+  if (A.hot_sorted && (W % 4) == 0 && tma_stages >= 3 && A.T >= 2 && !h->plan_no_tma) {
+    pt_swap_plan_tma_kernel<<<1, 1024, size_t(tma_stages) * W * 24, st>>>(A, tma_stages);
+    h->launches += 1;
+    return EMP_OK;
+  }
   if (A.hot_sorted && smem2 <= kPlanSmemMax && W <= 8192) {
     k = W <= 1024 ? pt_swap_plan_sorted_kernel<1> : W <= 2048 ? pt_swap_plan_sorted_kernel<2>
       : W <= 4096 ? pt_swap_plan_sorted_kernel<4> : pt_swap_plan_sorted_kernel<8>;
@@ -661,11 +668,13 @@ static int enqueue_plan(EmpHandle* h, const PtPlan& A, cudaStream_t st) {
 
 static int ensure_plan_scratch(EmpHandle* h, int32_t W) {
   if (!h->plan_attr_set) {  // once per handle, not per call
+    const char* env = getenv("EMP_PLAN_NO_TMA");
+    h->plan_no_tma = env && env[0] == '1';
     const void* ks[] = {(const void*)pt_swap_plan_kernel<1, 3>, (const void*)pt_swap_plan_kernel<2, 3>,
                         (const void*)pt_swap_plan_kernel<4, 3>, (const void*)pt_swap_plan_kernel<6, 3>,
                         (const void*)pt_swap_plan_kernel<8, 2>, (const void*)pt_swap_plan_sorted_kernel<1>,
                         (const void*)pt_swap_plan_sorted_kernel<2>, (const void*)pt_swap_plan_sorted_kernel<4>,
-                        (const void*)pt_swap_plan_sorted_kernel<8>};
+                        (const void*)pt_swap_plan_sorted_kernel<8>, (const void*)pt_swap_plan_tma_kernel};
     for (const void* k : ks)
       CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kPlanSmemMax)));
     h->plan_attr_set = true;

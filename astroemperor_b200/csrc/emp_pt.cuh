@@ -485,6 +485,124 @@ __global__ void __launch_bounds__(1024) pt_swap_plan_sorted_kernel(const PtPlan 
   plan_tail(A, s_x, s_nacc);
 }
 
+// The sorted plan fed by the TMA engine.  Measured (profiles/r02_plan_bench.log): the register-prefetch kernels take
+// 0.9 us per pair at W = 512 and +0.43 us per further 1024 walkers — one SM pulling 20 bytes per walker and pair
+// (partner index, uniform, logL) through its load/store unit, one pair of prefetch distance, is what bounds them, not
+// the shared-memory traffic.  Here every pair's three rows are contiguous in global memory, so ONE thread fetches
+// them with three 1-D bulk copies (cp.async.bulk -> mbarrier complete_tx) into a ring of n_stages stages, n_stages - 1
+// pairs ahead of their use; the 1024 threads only touch shared memory.  A stage is [logL row (becomes the colder
+// row, modified in place) | uniforms | partner indices | source indices] = 24 W bytes; W % 4 == 0 (16-byte rows).
+__global__ void __launch_bounds__(1024) pt_swap_plan_tma_kernel(const PtPlan A, int n_stages) {
+  extern __shared__ __align__(128) unsigned char plan_smem[];
+  __shared__ __align__(8) uint64_t s_bar[8];
+  __shared__ int32_t s_count[2];
+  __shared__ int32_t s_nacc[kPlanMaxT];
+  __shared__ double s_x[kPlanMaxT];
+  const int32_t T = A.T, W = A.W;
+  const size_t stage_bytes = size_t(W) * 24;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+  auto st_l = [&](int s) { return reinterpret_cast<double*>(plan_smem + s * stage_bytes); };
+  auto st_u = [&](int s) { return reinterpret_cast<double*>(plan_smem + s * stage_bytes + size_t(W) * 8); };
+  auto st_b = [&](int s) { return reinterpret_cast<int32_t*>(plan_smem + s * stage_bytes + size_t(W) * 16); };
+  auto st_s = [&](int s) { return reinterpret_cast<int32_t*>(plan_smem + s * stage_bytes + size_t(W) * 20); };
+  auto issue = [&](int jj) {  // thread 0: the three rows of pair jj -> stage jj % n_stages
+    const int s = jj % n_stages;
+    fence_proxy_async();
+    mbar_arrive_expect_tx(&s_bar[s], uint32_t(W) * 20u);
+    tma_bulk_g2s(st_l(s), A.logl + int64_t(jj) * W, uint32_t(W) * 8u, &s_bar[s]);
+    tma_bulk_g2s(st_u(s), A.lnu + int64_t(jj) * W, uint32_t(W) * 8u, &s_bar[s]);
+    tma_bulk_g2s(st_b(s), A.perm + (int64_t(jj) * 2 + 1) * W, uint32_t(W) * 4u, &s_bar[s]);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < n_stages; ++s) mbar_init(&s_bar[s], 1);
+    fence_barrier_init();
+  }
+  if (tid < 2) s_count[tid] = 0;
+  __syncthreads();
+  // prologue: the first n_stages - 1 pairs are in flight before anything is decided.  Stage (T-1) % n_stages stays
+  // empty: it is the one the first iteration refills (the stage "of pair T-1", which does not exist)
+  for (int q = 0; q < n_stages - 1; ++q) {
+    const int jj = T - 2 - q;
+    if (jj < 0) break;
+    if (tid == 0) issue(jj);
+    int32_t* sc = st_s(jj % n_stages);
+    for (int k = tid; k < W; k += nt) sc[k] = jj * W + k;
+  }
+  // the warmest row lives in registers: up to 8 slots per thread (W <= 8192)
+  constexpr int kR = 8;
+  double hl[kR];
+  int32_t hs[kR];
+#pragma unroll
+  for (int r = 0; r < kR; ++r) {
+    const int k = tid + r * nt;
+    if (k < W) {
+      hl[r] = A.logl[int64_t(T - 1) * W + k];
+      hs[r] = (T - 1) * W + k;
+    }
+  }
+  __syncthreads();
+  for (int j = T - 2; j >= 0; --j) {  // pair j: temperature j+1 (warmer, registers) with j (colder, its stage)
+    const int s = j % n_stages;
+    mbar_wait(&s_bar[s], uint32_t(((T - 2 - j) / n_stages) & 1));
+    double* lc = st_l(s);
+    const double* us = st_u(s);
+    const int32_t* bs = st_b(s);
+    int32_t* sc = st_s(s);
+    const double dbeta = __dsub_rn(A.betas[j], A.betas[j + 1]);
+    int local = 0;
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      const int k = tid + r * nt;
+      if (k < W) {
+        const int b = bs[k];  // slot k of temp j+1 <-> slot b of temp j; b runs over a permutation
+        const double lb = lc[b];
+        if (__dmul_rn(dbeta, __dsub_rn(hl[r], lb)) > us[k]) {
+          const int32_t sb = sc[b];
+          sc[b] = hs[r];
+          lc[b] = hl[r];
+          hl[r] = lb;
+          hs[r] = sb;
+          ++local;
+        }
+      }
+    }
+    local = __reduce_add_sync(0xffffffffu, local);
+    if (lane == 0 && local) atomicAdd(&s_count[j & 1], local);
+    __syncthreads();
+    // row j+1 of the plan is final (registers); row j, as the swaps left it, becomes the warmer row
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      const int k = tid + r * nt;
+      if (k < W) {
+        A.src[int64_t(j + 1) * W + k] = hs[r];
+        hl[r] = lc[k];
+        hs[r] = sc[k];
+      }
+    }
+    if (tid == 0) {
+      const int32_t c = s_count[j & 1];
+      A.n_acc[j] = c;
+      s_nacc[j] = c;
+      s_count[j & 1] = 0;
+    }
+    // the stage of pair j+1 was read back before this barrier by every thread: refill it, n_stages - 1 pairs ahead
+    const int jj = j + 1 - n_stages;
+    if (jj >= 0) {
+      if (tid == 0) issue(jj);
+      int32_t* sn = st_s(jj % n_stages);
+      for (int k = tid; k < W; k += nt) sn[k] = jj * W + k;
+    }
+  }
+  if (A.src) {
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      const int k = tid + r * nt;
+      if (k < W) A.src[k] = hs[r];
+    }
+  }
+  plan_tail(A, s_x, s_nacc);
+}
+
 // Fallback for ensembles whose rows do not fit in shared memory (W > 8192): rows in global scratch.
 __global__ void __launch_bounds__(1024) pt_swap_plan_global_kernel(const PtPlan A, double* __restrict__ ll_work) {
   __shared__ int32_t s_count;

@@ -31,7 +31,7 @@ def _setup(name, T, W, seed, betas=None, with_D=False, **kw):
     ("c2_synth3p_2ins_n400", 4, 64, 4, 1, False),       # 3 planets, S/C parameterisation, derived-ecc prior
     ("c2_synth3p_2ins_n400", 4, 64, 8, 1, True),        # the same sweeps replayed from the captured CUDA graph
     ("synth_k1_p0_ma1_global", 3, 32, 4, 3, True),      # global MA recurrence in the likelihood, graph, nsteps = 3
-    ("synth_k1_p0_acc2_fixed", 5, 24, 4, 1, False),     # fixed parameter + acceleration, odd T
+    ("synth_k1_p0_acc2_fixed", 5, 26, 4, 1, False),     # fixed parameter + acceleration, odd T, W % 4 != 0
     ("c4_synth5p_4ins_ma_global_n600", 9, 1100, 3, 1, True),  # W > 1024: two plan elements per thread
 ])
 def test_sweeps_bit_identical_to_oracle(name, T, W, nsweeps, nsteps, graph):
