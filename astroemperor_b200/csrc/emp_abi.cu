@@ -639,9 +639,13 @@ static int enqueue_plan(EmpHandle* h, const PtPlan& A, cudaStream_t st) {
   using PlanKernel = void (*)(const PtPlan);
   PlanKernel k = nullptr;
   size_t smem = 0;
-  const int tma_stages = int(std::min<size_t>(kPlanSmemMax / (size_t(W) * 24), 8));
+  // TMA-fed kernel: arrays padded to kR * 1024 entries, at least 3 ring stages -> W <= 2048
+  const int tma_r = (W + 1023) / 1024;
+  const int tma_stages = tma_r <= 2 ? int(std::min<size_t>(kPlanSmemMax / (size_t(tma_r) * 1024 * 24), 8)) : 0;
   if (A.hot_sorted && (W % 4) == 0 && tma_stages >= 3 && A.T >= 2 && !h->plan_no_tma) {
-    pt_swap_plan_tma_kernel<<<1, 1024, size_t(tma_stages) * W * 24, st>>>(A, tma_stages);
+    const size_t bytes = size_t(tma_stages) * tma_r * 1024 * 24;
+    if (tma_r == 1) pt_swap_plan_tma_kernel<1><<<1, 1024, bytes, st>>>(A, tma_stages);
+    else pt_swap_plan_tma_kernel<2><<<1, 1024, bytes, st>>>(A, tma_stages);
     h->launches += 1;
     return EMP_OK;
   }
@@ -674,7 +678,8 @@ static int ensure_plan_scratch(EmpHandle* h, int32_t W) {
                         (const void*)pt_swap_plan_kernel<4, 3>, (const void*)pt_swap_plan_kernel<6, 3>,
                         (const void*)pt_swap_plan_kernel<8, 2>, (const void*)pt_swap_plan_sorted_kernel<1>,
                         (const void*)pt_swap_plan_sorted_kernel<2>, (const void*)pt_swap_plan_sorted_kernel<4>,
-                        (const void*)pt_swap_plan_sorted_kernel<8>, (const void*)pt_swap_plan_tma_kernel};
+                        (const void*)pt_swap_plan_sorted_kernel<8>, (const void*)pt_swap_plan_tma_kernel<1>,
+                        (const void*)pt_swap_plan_tma_kernel<2>};
     for (const void* k : ks)
       CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kPlanSmemMax)));
     h->plan_attr_set = true;

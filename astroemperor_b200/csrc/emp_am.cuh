@@ -12,12 +12,13 @@
 // built); lanes stride the epochs, lanes 0/1 propagate the barycentre, lanes 0..4 do the refit.
 //
 // Precision: the reference mixes FP64 with x87 80-bit `np.longdouble` where it forms
-// `(dec - ref_dec) * 3.6e6` (constants.scr:5-6,13-14; emp_model.py:1423-1431).  A GPU has no
-// 80-bit type; the same quantity is formed here without the cancellation
-// ((bary_dec - ref_dec) * 3.6e6 + orbit_offset_mas, an exact difference of nearby doubles), which
-// agrees with the long-double value to ~1e-12 mas.  The value is NOT reproducible to 1e-10
-// relative on any other libm (the propagated barycentre carries 1-ulp noise of ~5e-8 mas that the
-// Hipparcos term amplifies); parity is tested at 1e-8 relative.
+// `(dec - ref_dec) * 3.6e6` (constants.scr:5-6,13-14; emp_model.py:1423-1431) and propagates ABSOLUTE angles in
+// FP64 before differencing them against the catalogues: its value is only defined to ~4e-9 relative (a 40-digit
+// evaluation of the same formulas, tests/tools/am_truth_mpmath.py, differs from the reference's float by up to
+// 3.9e-9).  A GPU has no 80-bit type and does not need one: every catalogue difference is formed here from
+// offsets that never cancel (lin_prop_offsets), which agrees with the 40-digit value to ~1e-14 relative.  The
+// device is therefore tested against the EXACT value (<= 1e-10, north_star's bar) and against the reference at
+// the reference's own accuracy (tests/test_am.py).
 #pragma once
 #include <cuda_runtime.h>
 #include <string>
@@ -92,41 +93,51 @@ struct AmWarp {
   double prm[2][5];
 };
 
-// obs_lin_prop_PA for ONE catalogue epoch (emp_model.py:1498-1573); tf = time_refed/(365.25*206265)
-__device__ inline void lin_prop_pa(const double* obs, double time_refed, double* out) {
-  const double ra = obs[0] * kDeg2Rad, de = obs[1] * kDeg2Rad;  // np.deg2rad = x * (pi/180)
-  const double plx = obs[2], pmra = obs[3], pmde = obs[4], rv = obs[5];
+// obs_lin_prop_PA for ONE catalogue epoch (emp_model.py:1498-1573), formulated on OFFSETS.
+// The reference propagates absolute angles (deg -> rad -> xyz -> atan2 -> deg) and then forms
+// (RA_bary - RA_catalogue) * 3.6e6: a difference of two ~70 degree numbers that agree to 1e-5, which leaves the
+// value of loglike_AM defined only to ~4e-9 relative (tests/test_am.py, tests/tools/am_truth_mpmath.py) — even in
+// its x87 80-bit arithmetic.  In the star's local frame (r, north, east) the propagated position is exactly
+//   p1 = (D + vr tf) r + (vde tf) n + (vra tf) e,         D = 1e3/plx,
+// so the CHANGE of the angles has a closed form without any cancellation:
+//   dRA = atan2(E, R cd - N sd),   sin(dDE) = (N - sd A kappa)/|p1|,  A = R cd - N sd, kappa = sqrt(1 + (E/A)^2) - 1.
+// Every difference against a catalogue position is then a sum of small, accurately known terms.  In plain FP64
+// this agrees with a 40-digit evaluation of the reference's formulas to 2e-15 relative (the reference: 4e-9).
+//   obs: ra, de [rad], plx, pmra, pmde, rv of the un-propagated barycentre; time_refed [d]
+//   out: dRA, dDE [deg] (position change), plx1, pmra1, pmde1, de1 [deg]
+__device__ inline void lin_prop_offsets(double ra, double de, double plx, double pmra, double pmde, double rv,
+                                        double time_refed, double* out) {
   double sinde, cosde, sinra, cosra;
   sincos(de, &sinde, &cosde);
   sincos(ra, &sinra, &cosra);
   const double d = 1.0 / plx;
-  const double x = cosde * cosra * d * kPcPerKpc, y = cosde * sinra * d * kPcPerKpc, z = sinde * d * kPcPerKpc;
+  const double D = d * kPcPerKpc;
   const double vra = pmra * d, vde = pmde * d, vr = rv / kAuyr2Kms;
+  const double tf = time_refed / (kDayPerYear * kPc2Au);
+  const double R = D + vr * tf, N = vde * tf, E = vra * tf;
+  const double A = R * cosde - N * sinde;
+  const double dra = atan2(E, A);
+  const double eps = (E / A) * (E / A);
+  const double kappa = eps / (1.0 + sqrt(1.0 + eps));
+  const double L = sqrt(R * R + N * N + E * E);
+  const double dde = asin((N - sinde * A * kappa) / L);
+  // proper motions / parallax at the new epoch: the velocity in the local frame of the NEW direction
   const double vx = vr * cosde * cosra - vde * sinde * cosra - vra * sinra;
   const double vy = vr * cosde * sinra - vde * sinde * sinra + vra * cosra;
   const double vz = vr * sinde + vde * cosde;
-  const double tf = time_refed / (kDayPerYear * kPc2Au);
-  const double x1 = x + vx * tf, y1 = y + vy * tf, z1 = z + vz * tf;
-  double b = atan2(z1, sqrt(x1 * x1 + y1 * y1));
-  if (b > kPi2) b -= kPi;
-  double l = fmod(atan2(y1, x1), kTwoPi);
-  if (l < 0.0) l += kTwoPi;
-  const double d1 = sqrt(x1 * x1 + y1 * y1 + z1 * z1) * 1e-3;
   double sinra1, cosra1, sinde1, cosde1;
-  sincos(l, &sinra1, &cosra1);
-  sincos(b, &sinde1, &cosde1);
-  // rot = roty @ rotz ; vequ = rot @ vv
+  sincos(ra + dra, &sinra1, &cosra1);
+  sincos(de + dde, &sinde1, &cosde1);
   const double r0 = cosra1 * vx + sinra1 * vy;
   const double r1 = -sinra1 * vx + cosra1 * vy;
-  const double r2 = vz;
-  const double v0 = cosde1 * r0 + sinde1 * r2;
-  const double v2 = -sinde1 * r0 + cosde1 * r2;
-  out[0] = l * kRad2Deg;
-  out[1] = b * kRad2Deg;
+  const double v2 = -sinde1 * r0 + cosde1 * vz;
+  const double d1 = L * 1e-3;
+  out[0] = dra * kRad2Deg;
+  out[1] = dde * kRad2Deg;
   out[2] = 1.0 / d1;
   out[3] = r1 / d1;
   out[4] = v2 / d1;
-  out[5] = v0 * kAuyr2Kms;
+  out[5] = (de + dde) * kRad2Deg;
 }
 
 // reflex-orbit offsets (mas) of one planet at relative time t: rows 0..2 of calc_astro_new
@@ -191,26 +202,29 @@ __global__ void __launch_bounds__(kAmWarps * 32) am_logl_kernel(const AmParams P
     p.plxfac = -p.beta * plx0 / 206265e3;
     w.pl[lane] = p;
   }
-  // barycentre (model_barycenter, emp_model.py:1483-1495): lane 0 -> Hipparcos epoch, lane 1 -> GDR3 epoch
+  // barycentre (model_barycenter, emp_model.py:1483-1495): lane 0 -> Hipparcos epoch, lane 1 -> GDR3 epoch.
+  // Positions are carried as offsets from the GDR3 catalogue position (lin_prop_offsets).
+  const double dec_ref = P.cat_ref[2];
+  const double dra_obs = -(off[0] / 3.6e6) / cos(dec_ref * kDeg2Rad);  // RA_obs - RA_ref [deg]
+  const double dde_obs = -off[1] / 3.6e6;                              // DE_obs - DE_ref [deg]
   if (lane < 2) {
-    double obs[6];
-    const double dec_ref = P.cat_ref[2];
-    obs[0] = P.cat_ref[1] - (off[0] / 3.6e6) / cos(dec_ref * kDeg2Rad);
-    obs[1] = P.cat_ref[2] - off[1] / 3.6e6;
-    obs[2] = P.cat_ref[3] - off[2];
-    obs[3] = P.cat_ref[4] - off[3];
-    obs[4] = P.cat_ref[5] - off[4];
-    obs[5] = P.cat_ref[6] - 0.0;
-    lin_prop_pa(obs, lane == 0 ? P.t_ref_h : 0.0, lane == 0 ? w.bary_h : w.bary_g);
+    const double ra = (P.cat_ref[1] + dra_obs) * kDeg2Rad, de = (P.cat_ref[2] + dde_obs) * kDeg2Rad;
+    double o[6];
+    lin_prop_offsets(ra, de, P.cat_ref[3] - off[2], P.cat_ref[4] - off[3], P.cat_ref[5] - off[4], P.cat_ref[6],
+                     lane == 0 ? P.t_ref_h : 0.0, o);
     if (lane == 0) {
-      // get_deltas_HIPP (emp_model.py:1403-1415)
-      const double* b = w.bary_h;
-      const double mean_dec = 0.5 * (P.cat_h[2] + b[1]);
-      w.deltas[0] = (b[0] - P.cat_h[1]) * cos(mean_dec * kDeg2Rad) * 3.6e6;
-      w.deltas[1] = (b[1] - P.cat_h[2]) * 3.6e6;
-      w.deltas[2] = b[2] - P.cat_h[3];
-      w.deltas[3] = b[3] - P.cat_h[4];
-      w.deltas[4] = b[4] - P.cat_h[5];
+      // get_deltas_HIPP (emp_model.py:1403-1415): (RA_ref - RA_hip) is an exact difference of nearby doubles
+      const double mean_dec = 0.5 * (P.cat_h[2] + o[5]);
+      w.deltas[0] = ((P.cat_ref[1] - P.cat_h[1]) + dra_obs + o[0]) * cos(mean_dec * kDeg2Rad) * 3.6e6;
+      w.deltas[1] = ((P.cat_ref[2] - P.cat_h[2]) + dde_obs + o[1]) * 3.6e6;
+      w.deltas[2] = o[2] - P.cat_h[3];
+      w.deltas[3] = o[3] - P.cat_h[4];
+      w.deltas[4] = o[4] - P.cat_h[5];
+    } else {
+      w.bary_g[0] = de;    // declination of the barycentre at the reference epoch [rad]
+      w.bary_g[2] = o[2];  // parallax, proper motions at the reference epoch
+      w.bary_g[3] = o[3];
+      w.bary_g[4] = o[4];
     }
   }
   __syncwarp();
@@ -235,21 +249,23 @@ __global__ void __launch_bounds__(kAmWarps * 32) am_logl_kernel(const AmParams P
 
   // ---- Gaia GOST epochs (_prepare_gost_inputs, obs_lin_prop_simple, get_deltas_GOST) --------
   {
-    const double* bg = w.bary_g;  // barycenter[-1]: RA, DEC [deg], PLX, PMRA, PMDEC, RV
-    const double ra = bg[0] * kDeg2Rad, de = bg[1] * kDeg2Rad;
-    const double ref_ra = P.cat_ref[1], ref_dec = P.cat_ref[2];
+    const double* bg = w.bary_g;  // barycentre at the reference epoch: [0] DEC [rad], [2] PLX, [3] PMRA, [4] PMDEC
+    const double de = bg[0];
+    const double ref_dec = P.cat_ref[2];
     for (int j = lane; j < P.n_gost; j += 32) {
       double ras = 0.0, dec = 0.0, plx = 0.0;
       const double t = P.t_rel[P.n_hipp + j];
       for (int k = 0; k < K; ++k) am_orbit(w.pl[k], t, P.H, ras, dec, plx);
       const double tg = P.tg_ref[j];
+      // obs_lin_prop_simple (emp_model.py:1576-1594) as offsets from the catalogue position [deg]
       const double decs = de + bg[4] * tg / kDayPerYear / 206265e3;
-      const double rass = ra + bg[3] * tg / kDayPerYear / cos(decs) / 206265e3;
-      const double b0 = rass * kRad2Deg, b1 = decs * kRad2Deg;
-      const double dec_deg = b1 + dec / 3.6e6;
+      const double dra_g = dra_obs + (bg[3] * tg / kDayPerYear / cos(decs) / 206265e3) * kRad2Deg;
+      const double dde_g = dde_obs + (bg[4] * tg / kDayPerYear / 206265e3) * kRad2Deg;
+      // get_deltas_GOST (emp_model.py:1418-1431)
+      const double dec_deg = ref_dec + dde_g + dec / 3.6e6;
       const double cos_dec = cos(dec_deg * kDeg2Rad);
-      const double dra = (b0 - ref_ra) * cos_dec * 3.6e6 + ras;
-      const double ddec = (b1 - ref_dec) * 3.6e6 + dec;  // == (dec_deg - ref_dec)*3.6e6 without the cancellation
+      const double dra = dra_g * cos_dec * 3.6e6 + ras;
+      const double ddec = dde_g * 3.6e6 + dec;
       const double dplx = bg[2] + plx;
       w.abs_g[j] = P.spsi_g[j] * dra + P.cpsi_g[j] * ddec + P.parf_g[j] * dplx;
     }

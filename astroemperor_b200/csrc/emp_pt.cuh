@@ -246,7 +246,7 @@ constexpr int kPlanMaxT = 2048;  // ladder length limit: the sweep's swap counts
 // kR = elements per thread = ceil(W / 1024).
 template <int kR, int kBuf>
 __global__ void __launch_bounds__(1024) pt_swap_plan_kernel(const PtPlan A) {
-  extern __shared__ __align__(16) unsigned char plan_smem[];
+  extern __shared__ __align__(128) unsigned char plan_smem[];
   const int32_t T = A.T, W = A.W;
   // roles rotate by pointer: hot = warmer row of the current pair, cold = its colder row, spare = staging
   double* lh = reinterpret_cast<double*>(plan_smem);
@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(1024) pt_swap_plan_kernel(const PtPlan A) {
 // here there are 4, the rest is conflict-free: 24 W bytes of shared memory, one barrier per pair.
 template <int kR>
 __global__ void __launch_bounds__(1024) pt_swap_plan_sorted_kernel(const PtPlan A) {
-  extern __shared__ __align__(16) unsigned char plan_smem[];
+  extern __shared__ __align__(128) unsigned char plan_smem[];
   const int32_t T = A.T, W = A.W;
   double* lc = reinterpret_cast<double*>(plan_smem);  // colder row of the current pair
   double* ls = lc + W;                                 // staging: colder row of the next pair
@@ -485,26 +485,31 @@ __global__ void __launch_bounds__(1024) pt_swap_plan_sorted_kernel(const PtPlan 
   plan_tail(A, s_x, s_nacc);
 }
 
-// The sorted plan fed by the TMA engine.  Measured (profiles/r02_plan_bench.log): the register-prefetch kernels take
-// 0.9 us per pair at W = 512 and +0.43 us per further 1024 walkers — one SM pulling 20 bytes per walker and pair
-// (partner index, uniform, logL) through its load/store unit, one pair of prefetch distance, is what bounds them, not
-// the shared-memory traffic.  Here every pair's three rows are contiguous in global memory, so ONE thread fetches
-// them with three 1-D bulk copies (cp.async.bulk -> mbarrier complete_tx) into a ring of n_stages stages, n_stages - 1
-// pairs ahead of their use; the 1024 threads only touch shared memory.  A stage is [logL row (becomes the colder
-// row, modified in place) | uniforms | partner indices | source indices] = 24 W bytes; W % 4 == 0 (16-byte rows).
+// The sorted plan fed by the TMA engine (W <= 2048).  Measured (profiles/r02_plan_bench.log): the register-prefetch
+// kernels take 0.9 us per pair at W = 512 and +0.9 us per further 1024 walkers.  They are bound by INSTRUCTION
+// ISSUE of the one SM they run on: ~108 SASS instructions per walker and pair (64-bit address arithmetic of the
+// global prefetches, range predicates, staging copies) x 32 warps / 4 issue slots.  Here every pair's three rows are
+// contiguous in global memory, so ONE thread fetches them with three 1-D bulk copies (cp.async.bulk -> mbarrier
+// complete_tx) into a ring of n_stages stages, n_stages - 1 pairs ahead of their use, and the 1024 threads only
+// touch shared memory with 32-bit indices: ~30 instructions per walker and pair.  Arrays are padded to kR * 1024
+// entries whose uniform is +inf (a padded slot never swaps), so the pair loop carries no range predicate.
+// A stage is [logL row (becomes the colder row, modified in place) | uniforms | partner indices | source indices]
+// = 24 * kR * 1024 bytes; W % 4 == 0 (16-byte rows for the bulk copies).
+template <int kR>
 __global__ void __launch_bounds__(1024) pt_swap_plan_tma_kernel(const PtPlan A, int n_stages) {
   extern __shared__ __align__(128) unsigned char plan_smem[];
   __shared__ __align__(8) uint64_t s_bar[8];
   __shared__ int32_t s_count[2];
   __shared__ int32_t s_nacc[kPlanMaxT];
   __shared__ double s_x[kPlanMaxT];
+  constexpr int kPad = kR * 1024;
+  constexpr uint32_t kStage = 24u * kPad;
   const int32_t T = A.T, W = A.W;
-  const size_t stage_bytes = size_t(W) * 24;
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
-  auto st_l = [&](int s) { return reinterpret_cast<double*>(plan_smem + s * stage_bytes); };
-  auto st_u = [&](int s) { return reinterpret_cast<double*>(plan_smem + s * stage_bytes + size_t(W) * 8); };
-  auto st_b = [&](int s) { return reinterpret_cast<int32_t*>(plan_smem + s * stage_bytes + size_t(W) * 16); };
-  auto st_s = [&](int s) { return reinterpret_cast<int32_t*>(plan_smem + s * stage_bytes + size_t(W) * 20); };
+  const int tid = threadIdx.x, lane = tid & 31;
+  auto st_l = [&](int s) { return reinterpret_cast<double*>(plan_smem + s * kStage); };
+  auto st_u = [&](int s) { return reinterpret_cast<double*>(plan_smem + s * kStage + 8u * kPad); };
+  auto st_b = [&](int s) { return reinterpret_cast<int32_t*>(plan_smem + s * kStage + 16u * kPad); };
+  auto st_s = [&](int s) { return reinterpret_cast<int32_t*>(plan_smem + s * kStage + 20u * kPad); };
   auto issue = [&](int jj) {  // thread 0: the three rows of pair jj -> stage jj % n_stages
     const int s = jj % n_stages;
     fence_proxy_async();
@@ -518,6 +523,18 @@ __global__ void __launch_bounds__(1024) pt_swap_plan_tma_kernel(const PtPlan A, 
     fence_barrier_init();
   }
   if (tid < 2) s_count[tid] = 0;
+  // padding of every stage (the bulk copies only ever write the first W entries)
+  for (int s = 0; s < n_stages; ++s) {
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      const int k = tid + r * 1024;
+      if (k >= W) {
+        st_l(s)[k] = 0.0;
+        st_u(s)[k] = INFINITY;
+        st_b(s)[k] = k;
+      }
+    }
+  }
   __syncthreads();
   // prologue: the first n_stages - 1 pairs are in flight before anything is decided.  Stage (T-1) % n_stages stays
   // empty: it is the one the first iteration refills (the stage "of pair T-1", which does not exist)
@@ -526,44 +543,46 @@ __global__ void __launch_bounds__(1024) pt_swap_plan_tma_kernel(const PtPlan A, 
     if (jj < 0) break;
     if (tid == 0) issue(jj);
     int32_t* sc = st_s(jj % n_stages);
-    for (int k = tid; k < W; k += nt) sc[k] = jj * W + k;
+#pragma unroll
+    for (int r = 0; r < kR; ++r) sc[tid + r * 1024] = jj * W + tid + r * 1024;
   }
-  // the warmest row lives in registers: up to 8 slots per thread (W <= 8192)
-  constexpr int kR = 8;
+  // the warmest row lives in registers
   double hl[kR];
   int32_t hs[kR];
+  bool valid[kR];
 #pragma unroll
   for (int r = 0; r < kR; ++r) {
-    const int k = tid + r * nt;
-    if (k < W) {
-      hl[r] = A.logl[int64_t(T - 1) * W + k];
-      hs[r] = (T - 1) * W + k;
-    }
+    const int k = tid + r * 1024;
+    valid[r] = k < W;
+    hl[r] = valid[r] ? A.logl[int64_t(T - 1) * W + k] : 0.0;
+    hs[r] = (T - 1) * W + k;
   }
+  int32_t* src_row = A.src + int64_t(T - 1) * W + tid;  // row j+1 of the plan, this thread's first slot
+  for (int i = tid; i < T; i += 1024) s_x[i] = A.betas[i];  // the ladder, read once (s_x is free until plan_tail)
   __syncthreads();
+  // ring bookkeeping without divisions: stage of pair j, stage of pair j+1, parity of the stage's current use
+  int s = (T - 2) % n_stages, s_prev = (T - 1) % n_stages, uses = 0;
+  uint32_t parity = 0;
   for (int j = T - 2; j >= 0; --j) {  // pair j: temperature j+1 (warmer, registers) with j (colder, its stage)
-    const int s = j % n_stages;
-    mbar_wait(&s_bar[s], uint32_t(((T - 2 - j) / n_stages) & 1));
+    mbar_wait(&s_bar[s], parity);
     double* lc = st_l(s);
     const double* us = st_u(s);
     const int32_t* bs = st_b(s);
     int32_t* sc = st_s(s);
-    const double dbeta = __dsub_rn(A.betas[j], A.betas[j + 1]);
+    const double dbeta = __dsub_rn(s_x[j], s_x[j + 1]);
     int local = 0;
 #pragma unroll
     for (int r = 0; r < kR; ++r) {
-      const int k = tid + r * nt;
-      if (k < W) {
-        const int b = bs[k];  // slot k of temp j+1 <-> slot b of temp j; b runs over a permutation
-        const double lb = lc[b];
-        if (__dmul_rn(dbeta, __dsub_rn(hl[r], lb)) > us[k]) {
-          const int32_t sb = sc[b];
-          sc[b] = hs[r];
-          lc[b] = hl[r];
-          hl[r] = lb;
-          hs[r] = sb;
-          ++local;
-        }
+      const int k = tid + r * 1024;
+      const int b = bs[k];  // slot k of temp j+1 <-> slot b of temp j; b runs over a permutation
+      const double lb = lc[b];
+      if (__dmul_rn(dbeta, __dsub_rn(hl[r], lb)) > us[k]) {
+        const int32_t sb = sc[b];
+        sc[b] = hs[r];
+        lc[b] = hl[r];
+        hl[r] = lb;
+        hs[r] = sb;
+        ++local;
       }
     }
     local = __reduce_add_sync(0xffffffffu, local);
@@ -572,13 +591,12 @@ __global__ void __launch_bounds__(1024) pt_swap_plan_tma_kernel(const PtPlan A, 
     // row j+1 of the plan is final (registers); row j, as the swaps left it, becomes the warmer row
 #pragma unroll
     for (int r = 0; r < kR; ++r) {
-      const int k = tid + r * nt;
-      if (k < W) {
-        A.src[int64_t(j + 1) * W + k] = hs[r];
-        hl[r] = lc[k];
-        hs[r] = sc[k];
-      }
+      const int k = tid + r * 1024;
+      if (valid[r]) src_row[r * 1024] = hs[r];
+      hl[r] = lc[k];
+      hs[r] = sc[k];
     }
+    src_row -= W;
     if (tid == 0) {
       const int32_t c = s_count[j & 1];
       A.n_acc[j] = c;
@@ -588,17 +606,25 @@ __global__ void __launch_bounds__(1024) pt_swap_plan_tma_kernel(const PtPlan A, 
     // the stage of pair j+1 was read back before this barrier by every thread: refill it, n_stages - 1 pairs ahead
     const int jj = j + 1 - n_stages;
     if (jj >= 0) {
-      if (tid == 0) issue(jj);
-      int32_t* sn = st_s(jj % n_stages);
-      for (int k = tid; k < W; k += nt) sn[k] = jj * W + k;
+      if (tid == 0) {
+        fence_proxy_async();
+        mbar_arrive_expect_tx(&s_bar[s_prev], uint32_t(W) * 20u);
+        tma_bulk_g2s(st_l(s_prev), A.logl + int64_t(jj) * W, uint32_t(W) * 8u, &s_bar[s_prev]);
+        tma_bulk_g2s(st_u(s_prev), A.lnu + int64_t(jj) * W, uint32_t(W) * 8u, &s_bar[s_prev]);
+        tma_bulk_g2s(st_b(s_prev), A.perm + (int64_t(jj) * 2 + 1) * W, uint32_t(W) * 4u, &s_bar[s_prev]);
+      }
+      int32_t* sn = st_s(s_prev);
+#pragma unroll
+      for (int r = 0; r < kR; ++r) sn[tid + r * 1024] = jj * W + tid + r * 1024;
     }
+    s_prev = s;
+    s = (s == 0) ? n_stages - 1 : s - 1;
+    if (++uses == n_stages) { uses = 0; parity ^= 1u; }
   }
   if (A.src) {
 #pragma unroll
-    for (int r = 0; r < kR; ++r) {
-      const int k = tid + r * nt;
-      if (k < W) A.src[k] = hs[r];
-    }
+    for (int r = 0; r < kR; ++r)
+      if (valid[r]) A.src[tid + r * 1024] = hs[r];
   }
   plan_tail(A, s_x, s_nacc);
 }

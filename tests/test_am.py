@@ -2,8 +2,10 @@
 
 CPU: the NumPy/longdouble oracle is bit-identical to the script the REAL reference generated
 (tests/golden/c3_*.npz); the file loader mirrors DataWrapper's AM preprocessing.
-GPU: the device block against the oracle.  Tolerance 1e-8 relative, not 1e-10: the reference
-itself is not reproducible below ~1e-9 on another libm (test_am_value_is_ill_conditioned)."""
+GPU: the device block against the EXACT value of the reference's formulas (40-digit evaluation,
+tests/tools/am_truth_mpmath.py -> tests/golden/c3_am_truth.npz) at north_star's 1e-10, and against the
+reference's float at 1e-8: that float is itself up to 3.9e-9 away from the exact value
+(test_am_value_is_ill_conditioned, test_reference_value_is_only_good_to_1e9_of_the_exact_value)."""
 import os
 
 import numpy as np
@@ -91,8 +93,10 @@ def test_am_device_matches_oracle(name):
     assert np.array_equal(np.isfinite(lp), fin) and np.all(ll[~fin] == -np.inf)
     ref = g["logl"][fin]
     rel = np.abs(ll[fin] - ref) / np.abs(ref)
-    print(f"{name}: max rel err {rel.max():.3e}")
-    assert rel.max() < 5e-8  # a 1-ulp nudge of the propagated barycentre alone moves the oracle by up to 8e-9
+    print(f"{name}: max rel err vs the reference's float {rel.max():.3e}")
+    # the REFERENCE's float is up to 3.9e-9 away from the exact value of its own formulas (40-digit evaluation,
+    # test_reference_value_is_only_good_to_1e9_of_the_exact_value); the device is held to the exact value below
+    assert rel.max() < 1e-8
     # the Isotropic prior on the inclination goes through device sin/log: 1e-14, not bit-exact
     assert np.max(np.abs(lp[fin] - g["logp"][fin])) < 1e-12
 
@@ -140,7 +144,9 @@ def test_am_device_is_at_least_as_close_to_the_exact_value_as_the_reference(name
     os.makedirs(out, exist_ok=True)
     with open(os.path.join(out, f"am_accuracy_{name}.json"), "w") as fh:
         json.dump(rec, fh)
-    assert np.all(e_dev <= np.maximum(e_ref, 1e-10)), (e_dev.max(), e_ref.max())
+    # north_star's 1e-10, against the exact value; and never worse than the reference itself
+    assert e_dev.max() < 1e-10, e_dev.max()
+    assert np.all(e_dev <= np.maximum(e_ref, 1e-12)), (e_dev.max(), e_ref.max())
 
 
 @pytest.mark.gpu
