@@ -342,7 +342,9 @@ class PTSampler:
         i = lay["i"] = 1 - lay["i"]
         # the H2D that last used this pinned buffer has finished (this also keeps the host at most two sweeps
         # ahead of the device: that copy is stream-ordered behind the sweep before it)
+        t_w = _time.perf_counter()
         lay["evt"][i].synchronize()
+        self.timings["wait_device"] = self.timings.get("wait_device", 0.0) + _time.perf_counter() - t_w
         t0 = _time.perf_counter()
         rows = None if sh.world == 1 else range(self.ntemps)[sh.local_slice]
         draw_sweep(self.streams, self.nwalkers, self.ndim, nsteps, self.a, temps=sh.local_slice,
@@ -577,7 +579,9 @@ class PTSampler:
         if nsweeps > 0:
             staged = pre[1] if (pre is not None and pre[0] == nsteps) else self.draw_staged(nsteps)
         for k in it:
+            t0 = _time.perf_counter()
             self.sweep_begin(staged)
+            self.timings["enqueue"] = self.timings.get("enqueue", 0.0) + _time.perf_counter() - t0
             # while the device runs this sweep the host draws the next one, packs it into the other pinned
             # buffer and enqueues its H2D copy (double-buffered on both sides)
             staged = self.draw_staged(nsteps)

@@ -344,6 +344,7 @@ def run_e2e(cx, samp, eng, steps, T, W):
     io["d2h"] = 0
     draws_bytes = samp.draw(1).nbytes()
     c0 = eng.counters()
+    samp.timings = {"draws": 0.0, "h2d": 0.0}
     cx.barrier()
     te0 = time.perf_counter()
     ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -356,7 +357,8 @@ def run_e2e(cx, samp, eng, steps, T, W):
     c1 = eng.counters()
     ms = cx.max_over_ranks(max(ee0.elapsed_time(ee1), (te1 - te0) * 1e3))  # host-bound loops are wall-clock bound
     chain_bytes = samp.shard.n_local * W * (samp.ndim + 2) * 8 if samp.store == "host" else 0
-    return dict(ms=ms, evaluated=cx.sum_over_ranks(c1["in_prior"] - c0["in_prior"]),
+    host = {k: v * 1e3 / steps for k, v in samp.timings.items() if v}
+    return dict(ms=ms, host_ms_per_step=host, evaluated=cx.sum_over_ranks(c1["in_prior"] - c0["in_prior"]),
                 proposals=cx.sum_over_ranks(c1["proposals"] - c0["proposals"]),
                 h2d=draws_bytes, d2h=io["d2h"] // steps + chain_bytes)
 
@@ -392,7 +394,8 @@ def run_leg(cx, name, steps, warmup, burn, cpu_budget):
            "value": evaluated * N / (ms * 1e-3), "value_nominal": proposals * N / (ms * 1e-3), "unit": UNIT,
            "ms_per_step": ms / steps, "evaluated_fraction": evaluated / max(proposals, 1),
            "e2e": {"value": e["evaluated"] * N / (e["ms"] * 1e-3), "unit": UNIT, "ms_per_step": e["ms"] / steps,
-                   "h2d_bytes_per_step": e["h2d"], "d2h_bytes_per_step": e["d2h"]},
+                   "h2d_bytes_per_step": e["h2d"], "d2h_bytes_per_step": e["d2h"],
+                   "host_ms_per_step_rank0": e["host_ms_per_step"]},
            "e2e_over_value": (e["evaluated"] / e["ms"]) / (evaluated / ms),
            "gpu_launches_per_step": launches / steps, "graph_captures": eng.graph_captures,
            "host_wall_ms_per_step": (tw1 - tw0) * 1e3 / steps}
@@ -624,6 +627,7 @@ def main():
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e["h2d"],
                    "d2h_bytes_per_step": e["d2h"], "ms_per_step": e["ms"] / args.steps,
                    "value_nominal": e["proposals"] * N / (e["ms"] * 1e-3),
+                   "host_ms_per_step_rank0": e["host_ms_per_step"],
                    "includes": "host RNG draws, pinned staging, H2D, the sweep (CUDA graph), the chain sample "
                                "[T,W,ndim+2] streamed to pinned host memory, D2H of logL[T,W]"},
            "callable_host": {"value": callable_value, "unit": UNIT, "ms_per_call": call_s * 1e3,
