@@ -54,56 +54,64 @@ def _f(x):
     return x.item() if isinstance(x, (np.floating, np.integer)) else x
 
 
+# Default (prior, limits) of every Keplerian parameter, by NAME.  Limits are symbolic: they are resolved against the
+# data set by `_resolve` (the values are the ones SmartSetter.set_Keplerian derives, block_repo.py:517-607; the
+# golden descriptors of tests/golden pin them for all eight parameterisations).
+_KEP_DEFAULTS = {
+    "Period": ("Uniform", (1.5, "span")),
+    "lPeriod": ("Jeffreys", ("ln 1.5", "ln span")),
+    "Amplitude": ("Uniform", (1e-6, "amp")),
+    "Amp_sin": ("Uniform", ("-root_half_amp", "root_half_amp")),
+    "Amp_cos": ("Uniform", ("-root_half_amp", "root_half_amp")),
+    "Phase": ("Uniform", (0.0, "2pi")),
+    "Longitude": ("Uniform", (0.0, "2pi")),
+    "T_0": ("Uniform", (-1000, 1000)),
+    "Eccentricity": ("Normal", "ecc"),          # limits / prargs come from the caller (sim.ecc_limits / ecc_prargs)
+    "Ecc_sin": ("Uniform", (-1, 1)),
+    "Ecc_cos": ("Uniform", (-1, 1)),
+    "Inclination": ("Isotropic", (0, "pi")),
+    "Omega": ("Uniform", (0.0, "2pi")),
+}
+# parameterisations whose eccentricity is derived (S^2 + C^2): prior of the derived quantity (emp.py:210-220)
+_KEP_DERIVED_ECC = {1: "Uniform", 2: "Uniform", 4: "Uniform", 7: "Normal"}
+# parameterisation 2 samples ln P with a plain Uniform prior (block_repo.py:553-563); 6 and 7 use 'Jeffreys'
+_KEP_PRIOR_OVERRIDE = {(2, "lPeriod"): "Uniform"}
+
+
+def _resolve(sym, data: RVData):
+    """A symbolic limit -> number, from the data-derived scales of SmartSetter (RV scatter, time span)."""
+    if not isinstance(sym, str):
+        return sym
+    span = data.t.max() - data.t.min()
+    amp = np.std(data.y) * np.sqrt(4)  # data['RV'].std(ddof=0) * sqrt(4)
+    table = {"span": span, "ln span": np.log(span), "ln 1.5": np.log(1.5), "amp": amp, "2pi": TWO_PI_LIMITS[1],
+             "pi": np.pi, "root_half_amp": np.sqrt(amp / 2), "-root_half_amp": -np.sqrt(amp / 2)}
+    return table[sym]
+
+
 def keplerian_block(data: RVData, number: int, parameterisation: int, ecc_limits, ecc_prargs,
                     astrometry: bool = False) -> BlockSpec:
-    """KeplerianBlock + SmartSetter.set_Keplerian (block_repo.py:22-78, 517-607)."""
-    sig_limiter = np.std(data.y)  # data['RV'].std(ddof=0)
-    per_limiter = data.t.max() - data.t.min()
-    amp_limiter = sig_limiter * np.sqrt(4)
-    uni, norm = "Uniform", "Normal"
+    """KeplerianBlock + SmartSetter.set_Keplerian (block_repo.py:22-78, 517-607) from the defaults table."""
     p = parameterisation
-    addi: List[AdditionalPrior] = []
-    if p == 0:
-        lims = [[1.5, per_limiter], [1e-6, amp_limiter], TWO_PI_LIMITS, ecc_limits, TWO_PI_LIMITS]
-        priors = [uni, uni, uni, norm, uni]
-        prargs = [None, None, None, list(ecc_prargs), None]
-    elif p == 1:
-        lims = [[1.5, per_limiter], [1e-6, amp_limiter], TWO_PI_LIMITS, [-1, 1], [-1, 1]]
-        priors, prargs = [uni] * 5, [None] * 5
-        addi.append(AdditionalPrior("Ecc", uni, [0, 1], None))
-    elif p == 2:
-        kamp = np.sqrt(amp_limiter / 2)
-        lims = [[np.log(1.5), np.log(per_limiter)], [-kamp, kamp], [-kamp, kamp], [-1, 1], [-1, 1]]
-        priors, prargs = [uni] * 5, [None] * 5
-        addi.append(AdditionalPrior("Ecc", uni, [0, 1], None))
-    elif p == 3:
-        lims = [[1.5, per_limiter], [1e-6, amp_limiter], [-1000, 1000], ecc_limits, TWO_PI_LIMITS]
-        priors = [uni, uni, uni, norm, uni]
-        prargs = [None, None, None, list(ecc_prargs), None]
-    elif p == 4:
-        lims = [[1.5, per_limiter], [1e-6, amp_limiter], [-1000, 1000], [-1, 1], [-1, 1]]
-        priors, prargs = [uni] * 5, [None] * 5
-        addi.append(AdditionalPrior("Ecc", uni, [0, 1], None))
-    elif p == 6:
-        lims = [[np.log(1.5), np.log(per_limiter)], [1e-6, amp_limiter], TWO_PI_LIMITS, ecc_limits,
-                TWO_PI_LIMITS]
-        priors = ["Jeffreys", uni, uni, norm, uni]
-        prargs = [None, None, None, list(ecc_prargs), None]
-    elif p == 7:
-        lims = [[np.log(1.5), np.log(per_limiter)], [1e-6, amp_limiter], TWO_PI_LIMITS, [-1, 1], [-1, 1]]
-        priors, prargs = ["Jeffreys", uni, uni, uni, uni], [None] * 5
-        addi.append(AdditionalPrior("Ecc", norm, [0, 1], list(ecc_prargs)))
-    else:
+    if p not in KEP_PARAM_NAMES:
         raise UnsupportedModelError(f"keplerian_parameterisation {p}")
     names = list(KEP_PARAM_NAMES[p])
     if astrometry:
         if p != 0:
             raise UnsupportedModelError("astrometric Keplerians use parameterisation 0 (block_repo.py:524-541)")
         names += ["Inclination", "Omega"]
-        lims += [[0, np.pi], TWO_PI_LIMITS]
-        priors += ["Isotropic", uni]
-        prargs += [None, None]
-    params = [_param(f"{n} {number}", pr, lim, pa) for n, pr, lim, pa in zip(names, priors, lims, prargs)]
+    params = []
+    for n in names:
+        prior, lim = _KEP_DEFAULTS[n]
+        prior = _KEP_PRIOR_OVERRIDE.get((p, n), prior)
+        prargs = None
+        if lim == "ecc":
+            lim, prargs = ecc_limits, list(ecc_prargs)
+        params.append(_param(f"{n} {number}", prior, [_resolve(lim[0], data), _resolve(lim[1], data)], prargs))
+    addi: List[AdditionalPrior] = []
+    if p in _KEP_DERIVED_ECC:
+        pr = _KEP_DERIVED_ECC[p]
+        addi.append(AdditionalPrior("Ecc", pr, [0, 1], list(ecc_prargs) if pr == "Normal" else None))
     return BlockSpec(type_="Keplerian", params=params, parameterisation=p, astrometry=astrometry,
                      number=number, additional=addi)
 

@@ -34,18 +34,31 @@ from .draws import DrawStreams, SweepDraws, default_betas, draw_sweep, initial_p
 
 class State:
     """What `run_mcmc` returns (emcee's State as EMPEROR uses it: support/endit_freeze1.scr passes it
-    back into the next `run_mcmc`).  `coords` is the whole ladder [T, W, ndim] on the host; handing the
-    same object back continues the run without re-evaluating anything."""
+    back into the next `run_mcmc`).  Handing the same object back continues the run without re-evaluating
+    anything.  `coords` / `log_like` / `log_prior` (the whole ladder, [T, W, ndim] / [T, W], on the host) are
+    pulled from the device on first access — a run that only chains `run_mcmc` calls never pays the copy — and
+    must be read before the sampler moves on."""
 
-    def __init__(self, sampler, coords, log_like, log_prior):
-        self._sampler_id, self._iteration = id(sampler), sampler.iteration
-        self.coords, self.log_like, self.log_prior = coords, log_like, log_prior
+    def __init__(self, sampler):
+        self._sampler, self._sampler_id, self._iteration = sampler, id(sampler), sampler.iteration
+        self._host = None
+
+    def _pull(self):
+        if self._host is None:
+            if self._sampler.iteration != self._iteration:
+                raise RuntimeError("this State was not read before the sampler continued; the ensemble has moved on")
+            self._host = self._sampler.state_numpy()
+        return self._host
+
+    coords = property(lambda self: self._pull()[0])
+    log_like = property(lambda self: self._pull()[1])
+    log_prior = property(lambda self: self._pull()[2])
 
     def __array__(self, dtype=None, copy=None):
         return np.asarray(self.coords, dtype=dtype)
 
     def __iter__(self):
-        return iter((self.coords, self.log_like, self.log_prior))
+        return iter(self._pull())
 
 
 class PTSampler:
@@ -597,8 +610,7 @@ class PTSampler:
             self._nan_seen = nan
         if self.backend_file:
             self.save_backend(self.backend_file)
-        p, ll, lp = self.state_numpy()
-        return State(self, p, ll, lp)
+        return State(self)
 
     def select_adjustment(self, mode):
         """reddemcee's ladder-adjustment selector as EMPEROR drives it: `support/endit_freeze1.scr:10` calls
