@@ -340,7 +340,9 @@ class PTSampler:
                 total += (int(np.prod(shp)) * np.dtype(dt).itemsize + 255) // 256 * 256
             torch.cuda.synchronize(self.dev)
             lay = {"nsteps": nsteps, "total": total, "host": [], "dev": [], "np": [], "out": [], "i": 0,
-                   "evt": [torch.cuda.Event(), torch.cuda.Event()]}
+                   "evt": [torch.cuda.Event(), torch.cuda.Event()],      # H2D of slot i landed
+                   "used": [None, None],                                 # the sweep that read slot i has finished
+                   "stream": torch.cuda.Stream(device=self.dev)}         # uploads overlap the running sweep
             for i in range(2):
                 host = torch.empty(total, dtype=torch.uint8).pin_memory()
                 dev = torch.empty(total, dtype=torch.uint8, device=self.dev)
@@ -363,15 +365,22 @@ class PTSampler:
         draw_sweep(self.streams, self.nwalkers, self.ndim, nsteps, self.a, temps=sh.local_slice,
                    swap=self.ntemps > 1, swap_rows=rows, out=lay["np"][i])
         self.timings["draws"] += _time.perf_counter() - t0
-        lay["dev"][i].copy_(lay["host"][i], non_blocking=True)
-        lay["evt"][i].record()
+        # upload on a side stream, behind the sweep that last read this slot: the copy overlaps the sweep in flight
+        st = lay["stream"]
+        if lay["used"][i] is not None:
+            st.wait_event(lay["used"][i])
+        with torch.cuda.stream(st):
+            lay["dev"][i].copy_(lay["host"][i], non_blocking=True)
+            lay["evt"][i].record(st)
         return lay["out"][i]
 
     def draw_resident(self, nsteps: int):
         """Draw one sweep and keep it packed in device memory (bench.py: the draws of the timed steps are
         resident in HBM before the clock starts); feed it back with `stage_resident`."""
         out = self.draw_staged(nsteps)
-        return self._lay["dev"][out["_stage_index"]].clone()
+        i = out["_stage_index"]
+        self.torch.cuda.current_stream(self.dev).wait_event(self._lay["evt"][i])
+        return self._lay["dev"][i].clone()
 
     def stage_resident(self, packed):
         """Device-to-device copy of a `draw_resident` buffer into the next staging slot (the slots are what the
@@ -379,6 +388,7 @@ class PTSampler:
         lay = self._lay
         i = lay["i"] = 1 - lay["i"]
         lay["dev"][i].copy_(packed, non_blocking=True)
+        lay["evt"][i].record()
         return lay["out"][i]
 
     def _sweep_args(self, draws, nsteps):
@@ -455,6 +465,10 @@ class PTSampler:
                     torch.cuda.current_stream(self.dev).wait_event(self._copy_done.pop(0)[1])
             if self._stored + len(stored_now) > self._chain.shape[0]:
                 self._alloc_store(max(len(stored_now), 1))
+        slot = draws.get("_stage_index") if getattr(self, "_lay", None) is not None and \
+            draws is self._lay["out"][draws.get("_stage_index") or 0] else None
+        if slot is not None:
+            torch.cuda.current_stream(self.dev).wait_event(self._lay["evt"][slot])
         self._mark("start")
         if self.ntemps > 1:
             perm, lnu_swap = draws["perm"], draws["lnu_swap"]
@@ -479,6 +493,10 @@ class PTSampler:
         if self.ntemps > 1:
             self._par = 1 - self._par
             self.p, self.logl, self.logp = self._state[self._par]
+        if slot is not None:
+            if self._lay["used"][slot] is None:
+                self._lay["used"][slot] = torch.cuda.Event()
+            self._lay["used"][slot].record()
         # host mirror of the device counters
         self._n_steps += nsteps
         first = self._stored
