@@ -82,6 +82,7 @@ SYMBOLS = [
     ("emp_draws_get_state", ctypes.c_int, [_P, _I32, _P, ctypes.POINTER(_I32)]),
     ("emp_draws_sweep", ctypes.c_int, [_P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _I32, _P, _P]),
     ("emp_pt_sweep", ctypes.c_int, [_P, ctypes.POINTER(EmpPtSweepC)]),
+    ("emp_pt_sweep_chunk", ctypes.c_int, [_P, ctypes.POINTER(EmpPtSweepC), ctypes.c_int32, _P, _P, ctypes.c_int64]),
     ("emp_pt_sweep_stretch", ctypes.c_int, [_P, ctypes.POINTER(EmpPtSweepC)]),
     ("emp_pt_sweep_swap", ctypes.c_int, [_P, ctypes.POINTER(EmpPtSweepC)]),
     ("emp_dev_alloc", ctypes.c_int, [ctypes.c_int, _I64, ctypes.POINTER(_P)]),

@@ -43,6 +43,13 @@ struct GraphEntry {
   cudaGraphExec_t exec = nullptr;
   int64_t launches = 0;
 };
+// a chunk of k sweeps (+ the upload of their draws) captured as ONE graph (emp_pt_sweep_chunk)
+constexpr int kChunkGraphCache = 4;
+struct ChunkGraphEntry {
+  std::vector<unsigned char> key;  // the k argument blocks + the copy parameters
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches = 0;
+};
 
 struct EmpHandle {
   int device = 0;
@@ -86,6 +93,8 @@ struct EmpHandle {
   GraphEntry graphs[kGraphCache];    // captured sweeps (emp_pt_sweep, use_graph)
   int graph_next = 0;
   int64_t graph_captures = 0;
+  ChunkGraphEntry chunk_graphs[kChunkGraphCache];
+  int chunk_next = 0;
   cudaStream_t cap_stream = nullptr;
   int64_t cap_index = 0;
   uint32_t* d_nan = nullptr;          // [0] NaN proposals
@@ -334,6 +343,8 @@ extern "C" int emp_destroy(EmpHandle* h) {
   cudaFree(h->d_q); cudaFree(h->d_llq); cudaFree(h->d_lpq); cudaFree(h->d_llwork); cudaFree(h->d_nan);
   cudaFree(h->d_nact2); cudaFree(h->d_smd_part); cudaFree(h->d_smd_ticket); cudaFree(h->d_model); cudaFree(h->d_err2);
   for (GraphEntry& g : h->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  for (ChunkGraphEntry& g : h->chunk_graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   am_free(&h->am);
@@ -902,6 +913,75 @@ extern "C" int emp_pt_sweep(EmpHandle* h, const EmpPtSweep* s) {
     h->graph_next = (h->graph_next + 1) % kGraphCache;
     if (slot.exec) cudaGraphExecDestroy(slot.exec);
     slot.key = *s;
+    slot.exec = exec;
+    slot.launches = n_launch;
+    hit = &slot;
+    h->graph_captures += 1;
+  }
+  CUDA_TRY(cudaGraphLaunch(hit->exec, h->stream));
+  h->launches += hit->launches;
+  return EMP_OK;
+}
+
+// k whole sweeps in ONE graph launch: small ensembles (BASELINE configs 1-3) finish a sweep in tens of
+// microseconds, so a host that enqueues sweep by sweep (draw, stage, upload, launch) is the bottleneck.  The
+// caller draws the k sweeps into one pinned block; the graph uploads it with a single copy node and then runs the
+// k sweeps back to back (each with its own argument block: the state parity alternates, the draw pointers advance).
+extern "C" int emp_pt_sweep_chunk(EmpHandle* h, const EmpPtSweep* s, int32_t k, void* draws_dev,
+                                  const void* draws_host, int64_t draws_bytes) {
+  if (!h || !s || k < 1) return fail(EMP_EINVAL, "bad chunk");
+  if ((draws_host != nullptr) != (draws_dev != nullptr) || (draws_host && draws_bytes < 1))
+    return fail(EMP_EINVAL, "draws_host / draws_dev / draws_bytes must come together");
+  for (int j = 0; j < k; ++j) {
+    int rc = prepare_sweep(h, s + j, true);
+    if (rc) return rc;
+    if (s[j].n_ranks != 1) return fail(EMP_EINVAL, "emp_pt_sweep_chunk is a single-GPU entry point");
+  }
+  if (h->timing) {  // per-launch event timing: plain stream launches
+    if (draws_host) CUDA_TRY(cudaMemcpyAsync(draws_dev, draws_host, size_t(draws_bytes), cudaMemcpyHostToDevice, h->stream));
+    for (int j = 0; j < k; ++j) {
+      int rc = enqueue_sweep(h, s + j, h->stream);
+      if (rc) return rc;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return EMP_OK;
+  }
+  std::vector<unsigned char> key(size_t(k) * sizeof(EmpPtSweep) + 3 * sizeof(int64_t));
+  memcpy(key.data(), s, size_t(k) * sizeof(EmpPtSweep));
+  const int64_t tail[3] = {int64_t(reinterpret_cast<uintptr_t>(draws_dev)),
+                           int64_t(reinterpret_cast<uintptr_t>(draws_host)), draws_bytes};
+  memcpy(key.data() + size_t(k) * sizeof(EmpPtSweep), tail, sizeof(tail));
+  ChunkGraphEntry* hit = nullptr;
+  for (ChunkGraphEntry& g : h->chunk_graphs)
+    if (g.exec && g.key == key) { hit = &g; break; }
+  if (!hit) {
+    if (!h->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    const int64_t l0 = h->launches;
+    CUDA_TRY(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = EMP_OK;
+    cudaError_t ec = cudaSuccess;
+    if (draws_host)
+      ec = cudaMemcpyAsync(draws_dev, draws_host, size_t(draws_bytes), cudaMemcpyHostToDevice, h->cap_stream);
+    for (int j = 0; j < k && rc == EMP_OK && ec == cudaSuccess; ++j) rc = enqueue_sweep(h, s + j, h->cap_stream);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
+    const int64_t n_launch = h->launches - l0;
+    h->launches = l0;
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ec != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      return fail(EMP_ECUDA, std::string("cudaMemcpyAsync (capture; the draws must be in pinned memory): ") +
+                                 cudaGetErrorString(ec));
+    }
+    if (e != cudaSuccess) return fail(EMP_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(EMP_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    ChunkGraphEntry& slot = h->chunk_graphs[h->chunk_next];
+    h->chunk_next = (h->chunk_next + 1) % kChunkGraphCache;
+    if (slot.exec) cudaGraphExecDestroy(slot.exec);
+    slot.key = std::move(key);
     slot.exec = exec;
     slot.launches = n_launch;
     hit = &slot;

@@ -105,8 +105,11 @@ class LikelihoodEngine:
         kepler.py 0.0.7 for every planet (include/emperor_b200.h emp_set_solver)."""
         _lib.check(self._L.emp_set_solver(self._h, self.SOLVERS[name]))
 
+    timing_enabled = False
+
     def set_timing(self, on: bool):
         _lib.check(self._L.emp_set_timing(self._h, 1 if on else 0))
+        self.timing_enabled = bool(on)
 
     def timing_collect(self):
         """(summed likelihood-kernel ms, launches) since the last collect; synchronises."""

@@ -66,7 +66,8 @@ class PTSampler:
                  backend=None, betas=None, tsw_history: bool = True, smd_history: bool = True,
                  adapt_tau: float = 1000, adapt_nu: float = 1, adapt_mode: int = 0, a: float = 2.0,
                  seed: Optional[int] = None, store: str = "device", thin_by: int = 1, adapt: bool = True, group=None,
-                 layout: str = "strided", exchange: str = "peer", graph: bool = True, native_draws: bool = True):
+                 layout: str = "strided", exchange: str = "peer", graph: bool = True, native_draws: bool = True,
+                 chunk: Optional[int] = None):
         """`log_like` is the LikelihoodEngine (it carries the prior as well; `log_prior` and `pool` are
         accepted for signature compatibility and ignored — the walkers are evaluated on the GPU, not
         through a multiprocessing pool).  `backend`: None, or a file name: the run is written there in
@@ -107,6 +108,9 @@ class PTSampler:
             raise ValueError("exchange must be 'peer' (CUDA IPC over NVLink) or 'allgather' (NCCL)")
         self.exchange = exchange
         self.graph = bool(graph)
+        # sweeps per graph launch in run_mcmc: None = as many as fit ~1 MB of draws (at most 64; 1 for the large
+        # ensembles, whose sweep takes milliseconds), 1 = sweep by sweep
+        self.chunk = None if chunk is None else max(int(chunk), 1)
         self.iteration = 0   # sweeps done
         self.time = 0        # reddemcee's ladder clock (= sweeps done)
         self._n_steps = 0    # stretch steps done
@@ -267,14 +271,14 @@ class PTSampler:
                 dst[: self._stored].copy_(srcb[: self._stored])
         self._chain, self._ll, self._lp = new
 
-    def _alloc_ring(self, nsteps):
+    def _alloc_ring(self, nsteps, k=1):
         """store='host': the device writes its samples into a small ring that a copy stream drains into the
-        pinned host chain one sweep behind the compute stream (C5 produces 147 MB per step: nothing of the
-        chain accumulates in HBM)."""
+        pinned host chain one sweep (one chunk of k sweeps) behind the compute stream (C5 produces 147 MB per
+        step: nothing of the chain accumulates in HBM)."""
         torch = self.torch
         m = (nsteps + self.thin_by - 1) // self.thin_by + 1
-        slots = 2 * m
-        if self._ring is not None and self._ring[0].shape[0] == slots:
+        slots = 2 * m * k
+        if self._ring is not None and self._ring[0].shape[0] >= slots:
             return
         torch.cuda.synchronize(self.dev)
         Tl, W, nd = self.shard.n_local, self.nwalkers, self.ndim
@@ -391,10 +395,12 @@ class PTSampler:
         lay["evt"][i].record()
         return lay["out"][i]
 
-    def _sweep_args(self, draws, nsteps):
+    def _sweep_args(self, draws, nsteps, par=None):
         """The EmpPtSweep argument block of one sweep (include/emperor_b200.h).  The blocks of the steady state
-        (double-buffered state x double-buffered staging) are built once and reused."""
-        key = (self._par, draws["zz"].data_ptr() if draws.get("_stage_index") is not None else None, nsteps,
+        (double-buffered state x double-buffered staging) are built once and reused.  `par`: which of the two
+        state blocks the sweep starts from (default: the current one)."""
+        par = self._par if par is None else par
+        key = (par, draws["zz"].data_ptr() if draws.get("_stage_index") is not None else None, nsteps,
                self.adapt, self._hist_cap,
                None if self._chain is None else self._chain.data_ptr(),
                None if self._ring is None else self._ring[0].data_ptr(), self.D_ is not None)
@@ -409,7 +415,7 @@ class PTSampler:
         A.n_ranks, A.rank, A.strided = sh.world, sh.rank, 1 if sh.layout == "strided" else 0
         # graphs are keyed on the argument block: only the double-buffered pinned staging repeats its pointers
         A.use_graph = 1 if (self.graph and sh.world == 1 and draws.get("_stage_index") is not None) else 0
-        cur, alt = self._state[self._par], self._state[1 - self._par]
+        cur, alt = self._state[par], self._state[1 - par]
         A.p, A.logl, A.logp = cur[0].data_ptr(), cur[1].data_ptr(), cur[2].data_ptr()
         A.p_alt, A.logl_alt, A.logp_alt = alt[0].data_ptr(), alt[1].data_ptr(), alt[2].data_ptr()
         A.betas = self._betas_dev.data_ptr()
@@ -463,6 +469,8 @@ class PTSampler:
                 # the ring slots this sweep overwrites were drained two sweeps ago at the latest
                 while self._copy_done and self._copy_done[0][0] <= self.iteration - 2:
                     torch.cuda.current_stream(self.dev).wait_event(self._copy_done.pop(0)[1])
+                while getattr(self, "_chunk_drains", None):   # drains of a chunked run still in flight
+                    torch.cuda.current_stream(self.dev).wait_event(self._chunk_drains.pop(0))
             if self._stored + len(stored_now) > self._chain.shape[0]:
                 self._alloc_store(max(len(stored_now), 1))
         slot = draws.get("_stage_index") if getattr(self, "_lay", None) is not None and \
@@ -518,6 +526,206 @@ class PTSampler:
         self.time += 1
         self.iteration += 1
         self._betas_stale = self._betas_stale or bool(A.adapt)
+
+    # ---- chunked runs: k sweeps per graph launch (ensembles whose sweep takes tens of microseconds) -----------
+    def _chunk_len(self, nsteps):
+        """Sweeps per graph launch of `run_mcmc`.  A sweep of a small ensemble (BASELINE configs 1-3) is 0.1-0.2 ms
+        of device time: enqueueing sweep by sweep from Python (draw, stage, upload, launch: ~0.1 ms) would make
+        the host the bottleneck.  Large ensembles (config 4: 3 MB of draws and 11 ms per sweep) stay at 1."""
+        if not self.graph or self.shard.world > 1 or self.engine.timing_enabled:
+            return 1
+        if self.chunk is not None:
+            return self.chunk
+        n_rows = max(self.ntemps - 1, 1)
+        per = sum(int(np.prod(shp)) * np.dtype(dt).itemsize
+                  for _, shp, dt in sweep_shapes(self.shard.n_local, self.nwalkers, nsteps, n_rows))
+        k = int(min(64, (1 << 20) // max(per, 1)))
+        return max(k - (k & 1), 1)  # even: the state parity at the start of a chunk does not alternate
+
+    def _chunk_layout(self, k, nsteps):
+        """Pinned and device blocks for the draws of k sweeps (double-buffered), the NumPy views the generator
+        and the vectorised log pass write through, the argument tuples of the native generator per sweep."""
+        torch, sh = self.torch, self.shard
+        lay = getattr(self, "_clay", None)
+        if lay is not None and lay["k"] == k and lay["nsteps"] == nsteps:
+            return lay
+        T, W = self.ntemps, self.nwalkers
+        n_rows = max(T - 1, 1)
+        shapes = sweep_shapes(sh.n_local, W, nsteps, n_rows)
+        offs, total = [], 0
+        for f, shp, dt in shapes:
+            offs.append(total)
+            total += (int(np.prod(shp)) * np.dtype(dt).itemsize + 255) // 256 * 256
+        torch.cuda.synchronize(self.dev)
+        lay = {"k": k, "nsteps": nsteps, "total": total, "host": [], "dev": [], "np": [], "out": [], "gen": [],
+               "used": [None, None], "i": 0, "blocks": {}}
+        L, dh = _lib.lib(), (self.streams.handle() if self.streams.native else None)
+        ts = np.arange(T, dtype=np.int32)
+        rs = np.array([T + j for j in range(T - 1)], dtype=np.int32)
+        lay["keep"] = (ts, rs)
+        for i in range(2):
+            host = torch.empty(k * total, dtype=torch.uint8).pin_memory()
+            dev = torch.empty(k * total, dtype=torch.uint8, device=self.dev)
+            hv = host.numpy()
+            views, outs, gens = {}, [], []
+            for (f, shp, dt), o in zip(shapes, offs):  # [k, ...] views, one row per sweep of the chunk
+                st = np.empty(shp, dtype=dt).strides
+                views[f] = np.ndarray((k,) + tuple(shp), dtype=dt, buffer=hv, offset=o, strides=(total,) + st)
+            for j in range(k):
+                out, ptr = {"sharded_swap": False, "_stage_index": None}, {}
+                for (f, shp, dt), o in zip(shapes, offs):
+                    nb = int(np.prod(shp)) * np.dtype(dt).itemsize
+                    a, b = j * total + o, j * total + o + nb
+                    out[f] = dev[a:b].view(torch.int32 if dt == np.int32 else torch.float64).view(shp)
+                    ptr[f] = hv[a:b].ctypes.data
+                outs.append(out)
+                gens.append((dh, ts.ctypes.data, T, W, nsteps, ptr["half_idx"], ptr["zz"], ptr["rint"], ptr["lnu"],
+                             rs.ctypes.data, len(rs), ptr["perm"], ptr["lnu_swap"]))
+            lay["host"].append(host), lay["dev"].append(dev), lay["np"].append(views)
+            lay["out"].append(outs), lay["gen"].append(gens)
+            if T < 2:
+                views["perm"][...] = 0
+                views["lnu_swap"][...] = 1.0
+        self._clay = lay
+        return lay
+
+    def _chunk_draw(self, lay, i, n):
+        """Draw the next n sweeps into pinned block i: the generator sweep by sweep (the streams advance exactly
+        as in the sweep-by-sweep path), then ONE vectorised pass for the stretch factors and the logs (NumPy's
+        on every path: thresholds are the same bits for the device and the oracle)."""
+        t0 = _time.perf_counter()
+        v = lay["np"][i]
+        if self.streams.native:
+            fn = _lib.lib().emp_draws_sweep
+            for j in range(n):
+                _lib.check(fn(*lay["gen"][i][j]))
+        else:
+            for j in range(n):
+                draw_sweep(self.streams, self.nwalkers, self.ndim, lay["nsteps"], self.a, swap=self.ntemps > 1,
+                           out={f: v[f][j] for f in SweepDraws.FIELDS})
+            self.timings["draws"] += _time.perf_counter() - t0
+            return
+        zz, fac, lnu, lsw = v["zz"][:n], v["factors"][:n], v["lnu"][:n], v["lnu_swap"][:n]
+        zz[...] = ((self.a - 1.0) * zz + 1) ** 2.0 / self.a  # draws._zz_from_u
+        np.multiply(np.log(zz), self.ndim - 1.0, out=fac)
+        with np.errstate(divide="ignore"):
+            np.log(lnu, out=lnu)
+            if self.ntemps > 1:
+                np.log(lsw, out=lsw)
+        self.timings["draws"] += _time.perf_counter() - t0
+
+    def _chunk_blocks(self, lay, i, n):
+        """The n argument blocks of a chunk read from device block i, starting at the current state parity."""
+        key = (i, n, self._par, self.adapt, self._hist_cap, None if self._chain is None else self._chain.data_ptr(),
+               None if self._ring is None else self._ring[0].data_ptr(), self.D_ is not None)
+        arr = lay["blocks"].get(key)
+        if arr is None:
+            if len(lay["blocks"]) > 8:
+                lay["blocks"].clear()
+            arr = (_lib.EmpPtSweepC * n)()
+            flip = 1 if self.ntemps > 1 else 0
+            for j in range(n):
+                arr[j] = self._sweep_args(lay["out"][i][j], lay["nsteps"], par=(self._par + j * flip) & 1)
+            lay["blocks"][key] = arr
+        return arr
+
+    def _chunk_launch(self, lay, i, n, upload=True):
+        """Enqueue the n sweeps whose draws are in block i (ONE graph launch; with `upload` the graph first copies
+        the pinned block to the device), mirror the device counters on the host and, with store='host', queue the
+        drain of the samples the chunk stores."""
+        torch, eng = self.torch, self.engine
+        nsteps = lay["nsteps"]
+        main = torch.cuda.current_stream(self.dev)
+        host_store = self._chain is not None and self.store == "host"
+        if host_store:
+            self._alloc_ring(nsteps, lay["k"])
+            self._chunk_drains = getattr(self, "_chunk_drains", [])
+            while len(self._chunk_drains) > 1:   # the ring holds two chunks: chunk c-2 must have been drained
+                main.wait_event(self._chunk_drains.pop(0))
+            while self._copy_done:               # drains of the sweep-by-sweep path still in flight
+                main.wait_event(self._copy_done.pop(0)[1])
+        arr = self._chunk_blocks(lay, i, n)
+        if upload:
+            _lib.check(eng._L.emp_pt_sweep_chunk(eng._h, arr, n, lay["dev"][i].data_ptr(), lay["host"][i].data_ptr(),
+                                                 n * lay["total"]))
+        else:
+            _lib.check(eng._L.emp_pt_sweep_chunk(eng._h, arr, n, None, None, 0))
+        if lay["used"][i] is None:
+            lay["used"][i] = torch.cuda.Event()
+        lay["used"][i].record()
+        n0, first = self._n_steps, self._stored
+        if self._chain is not None:
+            stored = [n_ for n_ in range(n0, n0 + n * nsteps) if n_ % self.thin_by == 0]
+            self._sample_sweep += [self.iteration + (n_ - n0) // nsteps for n_ in stored]
+            self._stored += len(stored)
+            if host_store and stored:
+                slots = self._ring[0].shape[0]
+                ev = torch.cuda.Event()
+                ev.record()
+                with torch.cuda.stream(self._copy_stream):
+                    self._copy_stream.wait_event(ev)
+                    s0, cnt, dst0 = (stored[0] // self.thin_by) % slots, len(stored), first
+                    while cnt > 0:   # at most two contiguous runs (the ring wraps once)
+                        run = min(cnt, slots - s0)
+                        for dst, ring in zip((self._chain, self._ll, self._lp), self._ring):
+                            dst[dst0:dst0 + run].copy_(ring[s0:s0 + run], non_blocking=True)
+                        s0, cnt, dst0 = (s0 + run) % slots, cnt - run, dst0 + run
+                    drained = torch.cuda.Event()
+                    drained.record()
+                self._chunk_drains.append(drained)
+        self._n_steps += n * nsteps
+        self.time += n
+        self.iteration += n
+        if self.ntemps > 1 and (n & 1):
+            self._par = 1 - self._par
+        self.p, self.logl, self.logp = self._state[self._par]
+        self._betas_stale = self._betas_stale or bool(self.adapt and self.ntemps > 2)
+
+    def _run_chunks(self, nsweeps, nsteps, k, bar=None):
+        """`nsweeps` sweeps, k per graph launch.  While the device runs a chunk the host draws the next one into the
+        other pinned block; the graph itself uploads its block (one copy node) before its first sweep."""
+        lay = self._chunk_layout(k, nsteps)
+        done = 0
+        i = lay["i"]
+        n_next = min(k, nsweeps)
+        if lay["used"][i] is not None:
+            lay["used"][i].synchronize()
+        self._chunk_draw(lay, i, n_next)
+        while done < nsweeps:
+            n = n_next
+            t0 = _time.perf_counter()
+            self._chunk_launch(lay, i, n)
+            done += n
+            self.timings["enqueue"] = self.timings.get("enqueue", 0.0) + _time.perf_counter() - t0
+            if bar is not None:
+                bar.update(n)
+            # the next chunk's draws, while the device works
+            i = lay["i"] = 1 - i
+            n_next = min(k, nsweeps - done)
+            if n_next > 0:
+                if lay["used"][i] is not None:
+                    t_w = _time.perf_counter()
+                    lay["used"][i].synchronize()
+                    self.timings["wait_device"] = self.timings.get("wait_device", 0.0) + _time.perf_counter() - t_w
+                self._chunk_draw(lay, i, n_next)
+
+    def draw_chunk_resident(self, k, nsteps=1):
+        """Draw k sweeps and keep them packed in device memory (bench.py: the draws of the timed steps are resident
+        in HBM before the clock starts); feed the block back with `run_chunk_resident`."""
+        lay = self._chunk_layout(k, nsteps)
+        i = lay["i"]
+        if lay["used"][i] is not None:
+            lay["used"][i].synchronize()
+        self._chunk_draw(lay, i, k)
+        return lay["host"][i].to(self.dev, non_blocking=False)
+
+    def run_chunk_resident(self, packed, nsteps=1):
+        """Device-to-device copy of a `draw_chunk_resident` block into the next device block, then its k sweeps
+        from one graph launch (no host-to-device traffic)."""
+        lay = self._clay
+        i = lay["i"] = 1 - lay["i"]
+        lay["dev"][i].copy_(packed, non_blocking=True)
+        self._chunk_launch(lay, i, lay["k"], upload=False)
 
     def _peer_pointers(self, A):
         """Where the swap finds the CURRENT (p | logl | logp) block of every rank: peer HBM mapped with CUDA IPC
@@ -607,6 +815,17 @@ class PTSampler:
         # warm-up then measurement — do not pay the pipeline fill again
         staged, pre = None, getattr(self, "_prefetched", None)
         self._prefetched = None
+        k = self._chunk_len(nsteps) if on_sweep is None else 1
+        if k > 1 and nsweeps > 1:
+            # small ensembles: k sweeps per graph launch (a sweep staged by an earlier call goes first)
+            if pre is not None and pre[0] == nsteps:
+                self.sweep_begin(pre[1])
+                nsweeps -= 1
+            bar = it if hasattr(it, "update") else None
+            self._run_chunks(nsweeps, nsteps, k, bar)
+            if bar is not None:
+                bar.close()
+            nsweeps, it = 0, range(0)
         if nsweeps > 0:
             staged = pre[1] if (pre is not None and pre[0] == nsteps) else self.draw_staged(nsteps)
         for k in it:

@@ -340,17 +340,25 @@ def run_e2e(cx, samp, eng, steps, T, W):
             io["sum"] += float(ll_host[1 - i][0, 0])
         io["d2h"] += ll_host[i].numel() * 8
 
-    samp.run_mcmc(None, nsweeps=2, nsteps=1, on_sweep=read_back)  # warm the staging buffers and the graphs
+    # small ensembles: run_mcmc replays k sweeps per graph launch; every step's sample (positions, logL, logP) still
+    # lands in pinned host memory through the chain store, and logL of every step is read there after the run
+    k = samp._chunk_len(1)
+    chunked = k > 1 and samp.store == "host"
+    cb = None if chunked else read_back
+    samp.run_mcmc(None, nsweeps=2 * k, nsteps=1, on_sweep=cb)  # warm the staging buffers and the graphs
     io["d2h"] = 0
     draws_bytes = samp.draw(1).nbytes()
     c0 = eng.counters()
     samp.timings = {"draws": 0.0, "h2d": 0.0}
+    first = samp._stored
     cx.barrier()
     te0 = time.perf_counter()
     ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ee0.record()
-    samp.run_mcmc(None, nsweeps=steps, nsteps=1, on_sweep=read_back)
+    samp.run_mcmc(None, nsweeps=steps, nsteps=1, on_sweep=cb)
     samp._sync_store()
+    if chunked:
+        io["sum"] += float(samp._ll[first:first + steps].sum())  # the host copy of every step's logL[T, W]
     ee1.record()
     cx.barrier()
     te1 = time.perf_counter()
@@ -358,7 +366,8 @@ def run_e2e(cx, samp, eng, steps, T, W):
     ms = cx.max_over_ranks(max(ee0.elapsed_time(ee1), (te1 - te0) * 1e3))  # host-bound loops are wall-clock bound
     chain_bytes = samp.shard.n_local * W * (samp.ndim + 2) * 8 if samp.store == "host" else 0
     host = {k: v * 1e3 / steps for k, v in samp.timings.items() if v}
-    return dict(ms=ms, host_ms_per_step=host, evaluated=cx.sum_over_ranks(c1["in_prior"] - c0["in_prior"]),
+    return dict(ms=ms, host_ms_per_step=host, chunk=k if chunked else 1,
+                evaluated=cx.sum_over_ranks(c1["in_prior"] - c0["in_prior"]),
                 proposals=cx.sum_over_ranks(c1["proposals"] - c0["proposals"]),
                 h2d=draws_bytes, d2h=io["d2h"] // steps + chain_bytes)
 
@@ -366,20 +375,36 @@ def run_e2e(cx, samp, eng, steps, T, W):
 def run_leg(cx, name, steps, warmup, burn, cpu_budget):
     """A short leg of another BASELINE config: device-side rate with pre-generated draws and the e2e rate."""
     wl = Workload(name)
-    eng, samp, T = make_sampler(cx, wl, total_sweeps=burn + warmup + 2 * steps + 8)
+    eng, samp, T = make_sampler(cx, wl)
     W, N = wl.w["W"], wl.n_units
+    k = samp._chunk_len(1)   # sweeps per graph launch (1 for the large ensembles and for sharded ladders)
+    if k > 1:
+        steps = (max(steps, 4 * k) + k - 1) // k * k
+    total = burn + warmup + 2 * steps + 6 * k + 8
+    samp._alloc_store(total)   # chain / history storage up front: nothing is (re)allocated inside a timed region
+    samp._alloc_hist(total)
     samp.run_mcmc(None, nsweeps=burn + warmup, nsteps=1)
-    # value: the draws of the timed steps are resident in HBM before the clock starts; per step a device-to-device
-    # copy into the staging slot the captured graph reads, then the graph replay
-    pre = [samp.draw_resident(1) for _ in range(steps)]
+    # value: the draws of the timed steps are resident in HBM before the clock starts; per step (per chunk of k
+    # steps) a device-to-device copy into the block the captured graph reads, then the graph replay
+    if k > 1:
+        samp._prefetched = None
+        for _ in range(2):   # both device blocks' graphs are captured before the clock starts
+            samp.run_chunk_resident(samp.draw_chunk_resident(k))
+        pre = [samp.draw_chunk_resident(k) for _ in range(steps // k)]
+    else:
+        pre = [samp.draw_resident(1) for _ in range(steps)]
     cx.barrier()
     c0 = eng.counters()
     l0 = eng.launch_count
     ev0, ev1 = cx.torch.cuda.Event(enable_timing=True), cx.torch.cuda.Event(enable_timing=True)
     tw0 = time.perf_counter()
     ev0.record()
-    for d in pre:
-        samp.sweep_begin(samp.stage_resident(d))
+    if k > 1:
+        for d in pre:
+            samp.run_chunk_resident(d)
+    else:
+        for d in pre:
+            samp.sweep_begin(samp.stage_resident(d))
     ev1.record()
     cx.barrier()
     tw1 = time.perf_counter()
@@ -389,6 +414,7 @@ def run_leg(cx, name, steps, warmup, burn, cpu_budget):
     evaluated = cx.sum_over_ranks(c1["in_prior"] - c0["in_prior"])
     proposals = cx.sum_over_ranks(c1["proposals"] - c0["proposals"])
     samp._prefetched = None
+    del pre
     e = run_e2e(cx, samp, eng, steps, T, W)
     out = {"workload": wl.w["desc"], "ntemps": T, "nwalkers": W, "n_points": N, "ndim": wl.spec.ndim, "steps": steps,
            "value": evaluated * N / (ms * 1e-3), "value_nominal": proposals * N / (ms * 1e-3), "unit": UNIT,
@@ -398,6 +424,7 @@ def run_leg(cx, name, steps, warmup, burn, cpu_budget):
                    "host_ms_per_step_rank0": e["host_ms_per_step"]},
            "e2e_over_value": (e["evaluated"] / e["ms"]) / (evaluated / ms),
            "gpu_launches_per_step": launches / steps, "graph_captures": eng.graph_captures,
+           "sweeps_per_graph_launch": k,
            "host_wall_ms_per_step": (tw1 - tw0) * 1e3 / steps}
     del samp
     eng.close()

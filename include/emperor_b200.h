@@ -316,6 +316,14 @@ typedef struct EmpPtSweep {
 } EmpPtSweep;
 /* Single GPU: the whole sweep (6 launches at nsteps = 1). */
 int emp_pt_sweep(EmpHandle *h, const EmpPtSweep *s);
+/* k consecutive single-GPU sweeps replayed from ONE graph launch (argument blocks s[0..k-1]; the state parity
+ * alternates and the draw pointers advance from block to block).  When draws_host is not NULL the graph begins
+ * with one copy node that uploads draws_bytes from the PINNED host block draws_host to draws_dev — the k sweeps'
+ * draws, which the blocks point into.  For ensembles whose sweep takes tens of microseconds (BASELINE configs
+ * 1-3) this removes the per-sweep host work of `sampler.run_mcmc(p1, nsweeps=, nsteps=)`
+ * (support/endit_reddemcee.scr:3): draw, stage, upload and launch happen once per chunk. */
+int emp_pt_sweep_chunk(EmpHandle *h, const EmpPtSweep *s, int32_t k, void *draws_dev, const void *draws_host,
+                       int64_t draws_bytes);
 /* Sharded ladder: the stretch phase, then — after the caller all-gathered logL (and the swap draws)
  * over NCCL — the replicated swap plan + adaptation and the row gather straight from the owners' HBM. */
 int emp_pt_sweep_stretch(EmpHandle *h, const EmpPtSweep *s);

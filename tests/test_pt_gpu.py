@@ -83,7 +83,7 @@ def test_sweeps_bit_identical_to_oracle(name, T, W, nsweeps, nsteps, graph):
 
 def test_launches_per_sweep():
     """VERDICT r1 #4: a sweep with nsteps = 1 is at most 6 kernel launches (was 13 + torch glue)."""
-    g, spec, eng, samp, orc, p0 = _setup("c2_synth3p_2ins_n400", 10, 512, seed=5, with_D=True)
+    g, spec, eng, samp, orc, p0 = _setup("c2_synth3p_2ins_n400", 10, 512, seed=5, with_D=True, chunk=1)
     samp._init_state(p0)
     samp._alloc_store(13)   # storage of the whole test up front: a re-allocation moves the chain, i.e. new graphs
     samp._alloc_hist(13)
@@ -92,6 +92,38 @@ def test_launches_per_sweep():
     samp.run_mcmc(None, nsweeps=10, nsteps=1)
     assert (eng.launch_count - l0) == 60, eng.launch_count - l0
     assert eng.graph_captures <= 2  # state and staging are double-buffered in step: two argument blocks alternate
+
+
+@pytest.mark.parametrize("name,T,W,nsweeps,nsteps,kw", [
+    ("c1_51peg_k1_p0", 2, 100, 37, 1, dict()),                              # BASELINE config 1 shape, automatic chunk
+    ("c2_synth3p_2ins_n400", 4, 64, 11, 2, dict(store="host", thin_by=3, chunk=4)),  # ring drained per chunk
+    ("c2_synth3p_2ins_n400", 3, 32, 10, 1, dict(chunk=3)),                  # odd chunk: the parity alternates
+    ("synth_k1_p0_ma1_global", 1, 32, 9, 1, dict(chunk=4)),                 # a single temperature: no swap sweep
+])
+def test_chunked_run_equals_sweep_by_sweep(name, T, W, nsweeps, nsteps, kw):
+    """run_mcmc replays k sweeps per graph launch for small ensembles (emp_pt_sweep_chunk: one upload node + k
+    sweeps): chains, histories and counters must be the bits of the sweep-by-sweep run, across calls too."""
+    g, spec, eng_a, a, _, p0 = _setup(name, T, W, seed=21, with_D=True, **{**kw, "chunk": 1})
+    g, spec, eng_b, b, _, p0b = _setup(name, T, W, seed=21, with_D=True, **kw)
+    assert b._chunk_len(nsteps) > 1 and a._chunk_len(nsteps) == 1
+    for s, q in ((a, p0), (b, p0b)):
+        st = s.run_mcmc(q, nsweeps=nsweeps, nsteps=nsteps)
+        s.run_mcmc(st, nsweeps=3, nsteps=nsteps)          # continue: a staged sweep may be pending
+        s.run_mcmc(None, nsweeps=1, nsteps=nsteps)        # a single sweep takes the sweep-by-sweep path
+    l0 = eng_b.launch_count
+    b.run_mcmc(None, nsweeps=2 * b._chunk_len(nsteps), nsteps=nsteps)
+    a.run_mcmc(None, nsweeps=2 * b._chunk_len(nsteps), nsteps=nsteps)
+    per_sweep = (eng_b.launch_count - l0) / (2 * b._chunk_len(nsteps))
+    assert per_sweep <= 6 * nsteps + (2 if T > 1 else 1), per_sweep
+    assert np.array_equal(a.get_chain(), b.get_chain())
+    assert np.array_equal(a.get_log_like(), b.get_log_like())
+    assert np.array_equal(a.get_log_prob(), b.get_log_prob())
+    assert np.array_equal(a.get_betas(), b.get_betas()) and np.array_equal(a.betas, b.betas)
+    assert np.array_equal(a.get_tsw(), b.get_tsw()) and np.array_equal(a.get_smd(), b.get_smd())
+    assert np.array_equal(a.acceptance_fraction, b.acceptance_fraction)
+    pa, pb = a.state_numpy(), b.state_numpy()
+    assert all(np.array_equal(x, y) for x, y in zip(pa, pb))
+    assert a.iteration == b.iteration and a._n_steps == b._n_steps and a._stored == b._stored
 
 
 def test_run_mcmc_api_and_storage():
