@@ -88,6 +88,8 @@ struct EmpHandle {
   bool plan_no_tma = false;          // EMP_PLAN_NO_TMA=1: keep the register-prefetch plan kernels (A/B measurements)
   double* d_smd_part = nullptr;      // swap-mean-distance partial sums of the plan application
   uint32_t* d_smd_ticket = nullptr;
+  int32_t* d_plan_cnt = nullptr;     // chain plan kernel: swap counts of all CTAs ([kPlanMaxT] + the ticket behind them)
+  bool plan_no_chain = false;        // EMP_PLAN_NO_CHAIN=1: the single-CTA shared-memory plan kernels (A/B measurements)
   int64_t cap_smd = 0;
   double *d_model = nullptr, *d_err2 = nullptr;  // emp_model_host scratch
   GraphEntry graphs[kGraphCache];    // captured sweeps (emp_pt_sweep, use_graph)
@@ -342,6 +344,7 @@ extern "C" int emp_destroy(EmpHandle* h) {
   cudaFree(h->d_desc); cudaFree(h->d_theta); cudaFree(h->d_ll); cudaFree(h->d_lp);
   cudaFree(h->d_q); cudaFree(h->d_llq); cudaFree(h->d_lpq); cudaFree(h->d_llwork); cudaFree(h->d_nan);
   cudaFree(h->d_nact2); cudaFree(h->d_smd_part); cudaFree(h->d_smd_ticket); cudaFree(h->d_model); cudaFree(h->d_err2);
+  cudaFree(h->d_plan_cnt);
   for (GraphEntry& g : h->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   for (ChunkGraphEntry& g : h->chunk_graphs)
@@ -651,6 +654,13 @@ static int enqueue_plan(EmpHandle* h, const PtPlan& A, cudaStream_t st) {
   PlanKernel k = nullptr;
   size_t smem = 0;
   // TMA-fed kernel: arrays padded to kR * 1024 entries, at least 3 ring stages -> W <= 2048
+  if (A.hot_sorted && A.T >= 2 && !h->plan_no_chain) {
+    const unsigned grid = unsigned((W + kChainThreads - 1) / kChainThreads);
+    pt_swap_plan_chain_kernel<<<grid, kChainThreads, 0, st>>>(A, h->d_plan_cnt,
+                                                              reinterpret_cast<uint32_t*>(h->d_plan_cnt + kPlanMaxT));
+    h->launches += 1;
+    return EMP_OK;
+  }
   const int tma_r = (W + 1023) / 1024;
   const int tma_stages = tma_r <= 2 ? int(std::min<size_t>(kPlanSmemMax / (size_t(tma_r) * 1024 * 24), 8)) : 0;
   if (A.hot_sorted && (W % 4) == 0 && tma_stages >= 3 && A.T >= 2 && !h->plan_no_tma) {
@@ -685,6 +695,10 @@ static int ensure_plan_scratch(EmpHandle* h, int32_t W) {
   if (!h->plan_attr_set) {  // once per handle, not per call
     const char* env = getenv("EMP_PLAN_NO_TMA");
     h->plan_no_tma = env && env[0] == '1';
+    const char* env2 = getenv("EMP_PLAN_NO_CHAIN");
+    h->plan_no_chain = env2 && env2[0] == '1';
+    CUDA_TRY(cudaMalloc(&h->d_plan_cnt, (kPlanMaxT + 1) * sizeof(int32_t)));
+    CUDA_TRY(cudaMemset(h->d_plan_cnt, 0, (kPlanMaxT + 1) * sizeof(int32_t)));
     const void* ks[] = {(const void*)pt_swap_plan_kernel<1, 3>, (const void*)pt_swap_plan_kernel<2, 3>,
                         (const void*)pt_swap_plan_kernel<4, 3>, (const void*)pt_swap_plan_kernel<6, 3>,
                         (const void*)pt_swap_plan_kernel<8, 2>, (const void*)pt_swap_plan_sorted_kernel<1>,

@@ -629,6 +629,93 @@ __global__ void __launch_bounds__(1024) pt_swap_plan_tma_kernel(const PtPlan A, 
   plan_tail(A, s_x, s_nacc);
 }
 
+// ---- swap plan by chains (default when the pairs are listed by their slot in the warmer row) ------------------
+// The hot -> cold sweep looks sequential over the T-1 pairs AND coupled over the walkers, but it is W INDEPENDENT
+// CHAINS.  Pair j couples slot s of the warmer row j+1 with slot b = perm_j[s] of the colder row j, and row j is
+// untouched until pair j is decided; so the element that pair j-1 finds in slot b of row j is either the walker the
+// chain carried down to (j+1, s) or the original walker of (j, b) — it depends on ONE decision, which depends on the
+// one before it along the path s_{T-1} = k, s_j = perm_j[s_{j+1}].  The path does not depend on the decisions at
+// all.  One thread per chain follows its path from the hottest row down with the carried walker (source index,
+// logL) in registers: no shared-memory exchange and no barrier between pairs, chains spread over many SMs.  Per
+// pair a thread issues three independent L2 gathers at the new slot (the colder row's logL, the next partner, the
+// next uniform) and decides the PREVIOUS pair while they are in flight: the critical path is one L2 latency per
+// pair (~0.13 us; the single-CTA shared-memory kernels above need 1.24 us per pair at W = 2048, all of it
+// bank-conflict replays and one block barrier).  Decisions are the same expressions on the same operands as in
+// those kernels: the plan is bit-identical.  Swap counts: warp ballot -> shared-memory counters per CTA -> global
+// integer atomics (order-independent); the last CTA to finish (ticket) publishes n_acc, resets the scratch for the
+// next launch and runs the ladder adaptation + histories (plan_tail).
+constexpr int kChainThreads = 64;
+__global__ void __launch_bounds__(kChainThreads) pt_swap_plan_chain_kernel(const PtPlan A, int32_t* __restrict__ g_cnt,
+                                                                            uint32_t* __restrict__ g_ticket) {
+  __shared__ int32_t s_nacc[kPlanMaxT];
+  __shared__ double s_x[kPlanMaxT];
+  __shared__ int s_last;
+  const int32_t T = A.T, W = A.W;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int k = blockIdx.x * kChainThreads + tid;
+  const bool valid = k < W;
+  for (int i = tid; i < T; i += kChainThreads) { s_x[i] = A.betas[i]; s_nacc[i] = 0; }
+  __syncthreads();
+  if (T >= 2) {
+    // carried walker of the chain that starts in slot k of the hottest row
+    int s = valid ? k : 0;                                     // slot in row j+1
+    double hl = A.logl[int64_t(T - 1) * W + s];
+    int32_t hs = (T - 1) * W + s;
+    // pair T-2: partner slot and uniform
+    int b = __ldg(A.perm + (int64_t(T - 2) * 2 + 1) * W + s);
+    double u = __ldg(A.lnu + int64_t(T - 2) * W + s);
+    // The decision of pair j is taken one iteration late, under the gathers of pair j-1: its operands arrived
+    // together with the partner slot those gathers needed.
+    auto decide = [&](int j, int s_w, int s_c, double lb, double uu) {
+      // pair j: temperature j+1 (carried walker in slot s_w) with temperature j (slot s_c, logL lb)
+      const double dbeta = __dsub_rn(s_x[j], s_x[j + 1]);
+      const bool acc = valid && (__dmul_rn(dbeta, __dsub_rn(hl, lb)) > uu);
+      const int32_t cold = j * W + s_c;
+      if (valid) A.src[int64_t(j + 1) * W + s_w] = acc ? cold : hs;  // row j+1 of the plan is final in slot s_w
+      if (!acc) { hl = lb; hs = cold; }                               // the chain goes on with whoever sits in (j, s_c)
+      const unsigned m = __ballot_sync(0xffffffffu, acc);
+      if (lane == 0 && m) atomicAdd(&s_nacc[j], __popc(m));
+    };
+    int p_s = 0, p_b = 0;
+    double p_lb = 0.0, p_u = 0.0;
+    for (int j = T - 2; j >= 0; --j) {
+      // gathers at slot b of row j: its logL (pair j), the partner and the uniform of pair j-1
+      const double lb_new = __ldg(A.logl + int64_t(j) * W + b);
+      int b_next = 0;
+      double u_next = 0.0;
+      if (j > 0) {
+        b_next = __ldg(A.perm + (int64_t(j - 1) * 2 + 1) * W + b);
+        u_next = __ldg(A.lnu + int64_t(j - 1) * W + b);
+      }
+      if (j < T - 2) decide(j + 1, p_s, p_b, p_lb, p_u);
+      p_s = s; p_b = b; p_lb = lb_new; p_u = u;
+      s = b; b = b_next; u = u_next;
+    }
+    decide(0, p_s, p_b, p_lb, p_u);
+    if (valid) A.src[s] = hs;  // row 0
+  } else if (valid && A.src) {
+    A.src[k] = k;
+  }
+  __syncthreads();
+  // per-CTA counts -> global; the last CTA owns the totals
+  for (int i = tid; i < T - 1; i += kChainThreads)
+    if (s_nacc[i]) atomicAdd(&g_cnt[i], s_nacc[i]);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(g_ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int i = tid; i < T - 1; i += kChainThreads) {
+    const int32_t c = atomicExch(&g_cnt[i], 0);   // read the total and leave the scratch zeroed for the next launch
+    s_nacc[i] = c;
+    if (A.n_acc) A.n_acc[i] = c;
+  }
+  if (tid == 0) *g_ticket = 0;
+  for (int i = tid; i < T; i += kChainThreads) s_x[i] = 0.0;
+  plan_tail(A, s_x, s_nacc);
+}
+
 // Fallback for ensembles whose rows do not fit in shared memory (W > 8192): rows in global scratch.
 __global__ void __launch_bounds__(1024) pt_swap_plan_global_kernel(const PtPlan A, double* __restrict__ ll_work) {
   __shared__ int32_t s_count;

@@ -488,7 +488,9 @@ class PTSampler:
             eng.pt_sweep_stretch(A)
             self._mark("stretch")
             if draws.get("sharded_swap"):
-                # every rank replays the whole plan: gather the pair rows (NCCL, behind the stretch kernels)
+                # every rank replays the whole plan: gather the pair rows (NCCL, behind the stretch kernels: on a
+                # side stream under them the NCCL kernels spin on SMs the likelihood kernel needs — measured
+                # +0.35 ms of stretch phase for 0.09 ms of hidden gathers at 4 GPUs)
                 perm = sh.all_gather_rows(perm)[: self.ntemps - 1].contiguous()
                 lnu_swap = sh.all_gather_rows(lnu_swap)[: self.ntemps - 1].contiguous()
             logl_all = sh.all_gather_rows(self.logl).contiguous()  # [T, W] in ladder order

@@ -59,7 +59,7 @@ WORKLOADS = {
                     "10k points, 32 temps x 2048 walkers per GPU"),
     "c4noop": dict(seed=4, n=10000, nins=4, kplan=5, ma="perins", param=0, T=32, W=2048,
                    desc="configs[3] with the reference's default per-instrument MA template (no-op on logL)"),
-    "c5": dict(seed=5, n=50000, nins=4, kplan=5, ma=None, param=0, T=8, W=8192,
+    "c5": dict(seed=5, n=50000, nins=4, kplan=5, ma=None, param=0, T=8, W=8192, ladder_T=64,
                desc="BASELINE configs[4]: 5 Keplerians, 50k points, 8 temps x 8192 walkers per GPU"),
     "tiny": dict(seed=1, n=400, nins=2, kplan=2, ma="global", param=0, T=2, W=64, desc="smoke-sized"),
 }
@@ -303,11 +303,26 @@ class Ctx:
         return allr.cpu().tolist()
 
 
+def ladder(wl, world):
+    """The ladder of a run on `world` GPUs: T = T_per_gpu x world rungs, geometric, between beta = 1 and the hottest
+    rung of the config's own ladder (`ladder_T` rungs, default T_per_gpu, with the default spacing).  More GPUs
+    buy a DENSER ladder over the same temperature range, so every GPU holds the same mix of cold and hot rungs
+    (strided layout) and does the same work at every N: that is what weak scaling compares.  (Extending the
+    default spacing to 8 x 32 rungs would only add rungs at beta < 1e-5 that sample the prior, propose 35 % of
+    their moves outside its box and are never evaluated.)"""
+    from astroemperor_b200.draws import default_betas
+    T = wl.w["T"] * world
+    b1 = default_betas(wl.spec.ndim, wl.w.get("ladder_T", wl.w["T"]))
+    if len(b1) == T or T < 2:
+        return b1[:T]
+    return b1[-1] ** (np.arange(T, dtype=np.float64) / (T - 1))
+
+
 def make_sampler(cx, wl, total_sweeps=0, seed=2026, store="host", **kw):
     from astroemperor_b200.sampler import PTSampler
     eng = wl.engine(cx.local_rank)
     T = wl.w["T"] * cx.world
-    samp = PTSampler(wl.w["W"], wl.spec.ndim, eng, ntemps=T, seed=seed, store=store, **kw)
+    samp = PTSampler(wl.w["W"], wl.spec.ndim, eng, ntemps=T, seed=seed, store=store, betas=ladder(wl, cx.world), **kw)
     samp.D_ = wl.spec.prior_widths()
     p0 = samp.initial_positions(wl.spec) if cx.rank == 0 else None
     if cx.world > 1:
@@ -515,6 +530,7 @@ def main():
     eng, samp, T = make_sampler(cx, wl, total_sweeps=args.burn + args.warmup + 2 * args.steps + 8,
                                 exchange=args.exchange)
     W, ndim = w["W"], wl.spec.ndim
+    samp_betas0 = ladder(wl, world)
     eng.set_solver(args.solver)
     samp.run_mcmc(None, nsweeps=args.burn, nsteps=1)
     peak_tf = fp64_peak_tflops(local_rank)
@@ -643,6 +659,9 @@ def main():
            "config": {"workload": w["desc"], "name": args.workload, "n_points": wl.n, "n_keplerians": w["kplan"],
                       "n_instruments": w["nins"], "ndim": ndim, "ntemps": T, "nwalkers": W,
                       "parallelism": f"temperature ladder sharded over {world} GPU(s)", "solver": args.solver,
+                      "ladder": f"{T} rungs, geometric between beta = 1 and {float(samp_betas0[-1]):.3g} (the range of "
+                                f"the config's {w.get('ladder_T', w['T'])}-rung ladder at every N: more GPUs = a denser "
+                                "ladder, the same work per GPU), adapted on the device every sweep",
                       "exchange": args.exchange if world > 1 else None,
                       "l2": "each step's inputs (draws 2.4 MB/step + state 18 MB) differ per step; the 280 KB "
                             "data set is L2-resident by design (re-read by every CTA)"},
