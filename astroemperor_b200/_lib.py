@@ -54,7 +54,7 @@ class EmpPtSweepC(ctypes.Structure):
                 ("hist_cap", _I64), ("D", _P), ("chain", _P), ("chain_ll", _P), ("chain_lp", _P),
                 ("store_cap", _I64), ("store_ring", _I32), ("perm_hot_sorted", _I32),
                 ("peer_p", _P * EMP_MAX_PEERS), ("peer_logl", _P * EMP_MAX_PEERS), ("peer_logp", _P * EMP_MAX_PEERS),
-                ("logl_all", _P)]
+                ("logl_all", _P), ("peer_gath", (_P * EMP_MAX_PEERS) * 2)]
 
 
 # every symbol include/emperor_b200.h declares: (name, restype, argtypes)
@@ -82,6 +82,7 @@ SYMBOLS = [
     ("emp_draws_get_state", ctypes.c_int, [_P, _I32, _P, ctypes.POINTER(_I32)]),
     ("emp_draws_sweep", ctypes.c_int, [_P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _I32, _P, _P]),
     ("emp_pt_sweep", ctypes.c_int, [_P, ctypes.POINTER(EmpPtSweepC)]),
+    ("emp_gather_block_bytes", ctypes.c_int, [_I32, _I32, ctypes.POINTER(_I64)]),
     ("emp_pt_sweep_chunk", ctypes.c_int, [_P, ctypes.POINTER(EmpPtSweepC), ctypes.c_int32, _P, _P, ctypes.c_int64]),
     ("emp_pt_sweep_stretch", ctypes.c_int, [_P, ctypes.POINTER(EmpPtSweepC)]),
     ("emp_pt_sweep_swap", ctypes.c_int, [_P, ctypes.POINTER(EmpPtSweepC)]),

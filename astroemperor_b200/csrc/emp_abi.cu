@@ -697,8 +697,8 @@ static int ensure_plan_scratch(EmpHandle* h, int32_t W) {
     h->plan_no_tma = env && env[0] == '1';
     const char* env2 = getenv("EMP_PLAN_NO_CHAIN");
     h->plan_no_chain = env2 && env2[0] == '1';
-    CUDA_TRY(cudaMalloc(&h->d_plan_cnt, (kPlanMaxT + 1) * sizeof(int32_t)));
-    CUDA_TRY(cudaMemset(h->d_plan_cnt, 0, (kPlanMaxT + 1) * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&h->d_plan_cnt, (kPlanMaxT + 2) * sizeof(int32_t)));  // counts | plan ticket | publish ticket
+    CUDA_TRY(cudaMemset(h->d_plan_cnt, 0, (kPlanMaxT + 2) * sizeof(int32_t)));
     const void* ks[] = {(const void*)pt_swap_plan_kernel<1, 3>, (const void*)pt_swap_plan_kernel<2, 3>,
                         (const void*)pt_swap_plan_kernel<4, 3>, (const void*)pt_swap_plan_kernel<6, 3>,
                         (const void*)pt_swap_plan_kernel<8, 2>, (const void*)pt_swap_plan_sorted_kernel<1>,
@@ -771,7 +771,13 @@ static int validate_sweep(EmpHandle* h, const EmpPtSweep* s, bool need_swap) {
     if (!s->perm || !s->lnu_swap || !s->src || !s->n_acc || !s->p_alt || !s->logl_alt || !s->logp_alt)
       return fail(EMP_EINVAL, "NULL swap draws / plan / alternate buffers");
     if (s->n_ranks > 1) {
-      if (!s->logl_all) return fail(EMP_EINVAL, "sharded ladder: logl_all is NULL");
+      const bool push = s->peer_gath[0][s->rank] != nullptr;
+      if (push) {
+        for (int q = 0; q < 2; ++q)
+          for (int r = 0; r < s->n_ranks; ++r)
+            if (!s->peer_gath[q][r]) return fail(EMP_EINVAL, "NULL gathered block of a peer");
+        if (!s->perm_hot_sorted) return fail(EMP_EINVAL, "the peer-push exchange needs perm_hot_sorted");
+      } else if (!s->logl_all) return fail(EMP_EINVAL, "sharded ladder: logl_all is NULL");
       for (int r = 0; r < s->n_ranks; ++r)
         if (!s->peer_p[r] || !s->peer_logl[r] || !s->peer_logp[r]) return fail(EMP_EINVAL, "NULL peer buffer");
     }
@@ -856,6 +862,23 @@ static int enqueue_stretch_phase(EmpHandle* h, const EmpPtSweep* s, bool swap_fo
 static int enqueue_swap_phase(EmpHandle* h, const EmpPtSweep* s, cudaStream_t st) {
   PtPlan P = {};
   P.T = s->T_all; P.W = s->W;
+  const bool push = s->n_ranks > 1 && s->peer_gath[0][s->rank] != nullptr;
+  if (push) {
+    // this rank's rows of logL and of the swap draws go straight into every peer's gathered block over NVLink
+    PtPublish U = {};
+    U.T_loc = s->T_loc; U.W = s->W; U.T_all = s->T_all; U.G = s->n_ranks; U.rank = s->rank; U.strided = s->strided;
+    U.logl = s->logl; U.perm = s->perm; U.lnu = s->lnu_swap;
+    for (int q = 0; q < 2; ++q)
+      for (int r = 0; r < s->n_ranks; ++r) U.peer[q][r] = static_cast<unsigned char*>(s->peer_gath[q][r]);
+    U.sweep_counter = (const long long*)s->sweep_counter;
+    U.ticket = reinterpret_cast<uint32_t*>(h->d_plan_cnt + kPlanMaxT + 1);
+    const dim3 grid((s->W + kPublishThreads - 1) / kPublishThreads, s->T_loc);
+    pt_publish_kernel<<<grid, kPublishThreads, 0, st>>>(U);
+    h->launches += 1;
+    P.gath[0] = static_cast<const unsigned char*>(s->peer_gath[0][s->rank]);
+    P.gath[1] = static_cast<const unsigned char*>(s->peer_gath[1][s->rank]);
+    P.n_ranks = s->n_ranks;
+  }
   P.logl = (s->n_ranks > 1) ? s->logl_all : s->logl;
   P.betas = s->betas; P.perm = s->perm; P.lnu = s->lnu_swap; P.src = s->src; P.n_acc = s->n_acc;
   P.adapt = s->adapt; P.adapt_tau = s->adapt_tau; P.adapt_nu = s->adapt_nu;
@@ -896,7 +919,10 @@ static int prepare_sweep(EmpHandle* h, const EmpPtSweep* s, bool need_swap) {
 extern "C" int emp_pt_sweep(EmpHandle* h, const EmpPtSweep* s) {
   int rc = prepare_sweep(h, s, true);
   if (rc) return rc;
-  if (s->n_ranks != 1) return fail(EMP_EINVAL, "emp_pt_sweep is the single-GPU sweep; use emp_pt_sweep_stretch/_swap");
+  if (s->n_ranks != 1 && !s->peer_gath[0][s->rank])
+    return fail(EMP_EINVAL, "emp_pt_sweep runs a sharded sweep only with the peer-push exchange (peer_gath); "
+                            "use emp_pt_sweep_stretch/_swap around the NCCL all-gather otherwise");
+  if (s->n_ranks != 1 && !s->sweep_counter) return fail(EMP_EINVAL, "the peer-push exchange needs sweep_counter");
   if (!s->use_graph || h->timing) {
     rc = enqueue_sweep(h, s, h->stream);
     if (rc) return rc;
@@ -1022,6 +1048,12 @@ extern "C" int emp_pt_sweep_swap(EmpHandle* h, const EmpPtSweep* s) {
   rc = enqueue_swap_phase(h, s, h->stream);
   if (rc) return rc;
   CUDA_TRY(cudaGetLastError());
+  return EMP_OK;
+}
+
+extern "C" int emp_gather_block_bytes(int32_t T_all, int32_t W, int64_t* bytes) {
+  if (!bytes || T_all < 1 || W < 1) return fail(EMP_EINVAL, "bad argument");
+  *bytes = int64_t(gath_bytes(T_all, W));
   return EMP_OK;
 }
 

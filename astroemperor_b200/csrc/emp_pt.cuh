@@ -189,7 +189,76 @@ struct PtPlan {
   double* beta_hist;        // [hist_cap, T] ladder after each sweep (may be NULL)
   int32_t* nacc_hist;       // [hist_cap, T-1] swap counts of each sweep (may be NULL)
   long long hist_cap;
+  // sharded ladder with the peer-push exchange (pt_publish_kernel): logl / lnu / the partner rows are read from
+  // the gathered block of the sweep's parity once every rank's flag says its rows have landed (chain kernel only)
+  const unsigned char* gath[2];
+  int32_t n_ranks;
 };
+
+// ---- gathered block of a sharded ladder (peer-push exchange) ---------------------------------------------------
+// Every rank owns two such blocks (sweep parity), mapped into every peer with CUDA IPC.  After the stretch phase a
+// rank WRITES its rows of logL and of the swap draws straight into every peer's block over NVLink
+// (pt_publish_kernel) and then raises its flag there; the plan kernel of a rank waits for all flags of the
+// sweep.  No NCCL call, no staging copy, rows land in ladder order.
+//   [logl  T_all x W f64 | lnu  T_all x W f64 | partner  T_all x W i32 | flags  kMaxPeers i64]
+__host__ __device__ inline size_t gath_lnu_off(int T, int W) { return size_t(T) * W * 8; }
+__host__ __device__ inline size_t gath_partner_off(int T, int W) { return size_t(T) * W * 16; }
+__host__ __device__ inline size_t gath_flags_off(int T, int W) { return (size_t(T) * W * 20 + 127) / 128 * 128; }
+__host__ __device__ inline size_t gath_bytes(int T, int W) { return gath_flags_off(T, W) + 16 * 8; }
+
+__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
+  long long v;
+  asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
+  asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+struct PtPublish {
+  int32_t T_loc, W, T_all, G, rank, strided;
+  const double* logl;        // [T_loc, W] this rank's log-likelihoods after the stretch phase
+  const int32_t* perm;       // [T_loc, 2, W] the swap pairs this rank drew (row t: pair index = its temperature)
+  const double* lnu;         // [T_loc, W]
+  unsigned char* peer[2][kMaxPeers];  // gathered blocks (parity 0 / 1) of every rank, own block included
+  const long long* sweep_counter;     // sweeps finished: parity and flag value of this sweep
+  uint32_t* ticket;
+};
+
+constexpr int kPublishThreads = 256;
+__global__ void __launch_bounds__(kPublishThreads) pt_publish_kernel(const PtPublish A) {
+  __shared__ int s_last;
+  const long long k = *A.sweep_counter;
+  const int q = int(k & 1);
+  const int t = blockIdx.y;
+  const int w = blockIdx.x * kPublishThreads + threadIdx.x;
+  const int j = A.strided ? t * A.G + A.rank : A.rank * A.T_loc + t;  // temperature (= pair index) of local row t
+  if (w < A.W) {
+    const double ll = A.logl[int64_t(t) * A.W + w];
+    const double lu = A.lnu[int64_t(t) * A.W + w];
+    const int32_t pb = A.perm[(int64_t(t) * 2 + 1) * A.W + w];
+    const size_t o = size_t(j) * A.W + w;
+    const size_t o_lnu = gath_lnu_off(A.T_all, A.W), o_par = gath_partner_off(A.T_all, A.W);
+    for (int r = 0; r < A.G; ++r) {
+      unsigned char* g = A.peer[q][(A.rank + r) % A.G];  // start at home, then round the peers
+      reinterpret_cast<double*>(g)[o] = ll;
+      reinterpret_cast<double*>(g + o_lnu)[o] = lu;
+      reinterpret_cast<int32_t*>(g + o_par)[o] = pb;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0)
+    s_last = (atomicAdd(A.ticket, 1u) == gridDim.x * gridDim.y - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  if (threadIdx.x < A.G) {
+    long long* f = reinterpret_cast<long long*>(A.peer[q][threadIdx.x] + gath_flags_off(A.T_all, A.W)) + A.rank;
+    st_release_sys(f, k + 1);
+  }
+  if (threadIdx.x == 0) *A.ticket = 0;
+}
 
 // The adaptation of oracle/pt_oracle.py::adapt_ladder (same operations, same order):
 //   decay = tau/(time+tau); kappa = decay/nu; dS_i = kappa (A_i - A_{i+1}); dT_i = (1/b_{i+1} - 1/b_i) exp(dS_i);
@@ -655,15 +724,34 @@ __global__ void __launch_bounds__(kChainThreads) pt_swap_plan_chain_kernel(const
   const int k = blockIdx.x * kChainThreads + tid;
   const bool valid = k < W;
   for (int i = tid; i < T; i += kChainThreads) { s_x[i] = A.betas[i]; s_nacc[i] = 0; }
+  // operands: the caller's arrays, or (sharded ladder, peer-push exchange) the gathered block of this sweep's parity
+  const double* __restrict__ g_logl = A.logl;
+  const double* __restrict__ g_lnu = A.lnu;
+  const int32_t* __restrict__ g_par = A.perm + W;  // partner row of pair j at g_par + j * par_stride
+  int64_t par_stride = 2 * int64_t(W);
+  if (A.gath[0]) {
+    const long long sweep = *A.sweep_counter;      // read by every CTA before the last one increments it
+    const unsigned char* g = A.gath[sweep & 1];
+    g_logl = reinterpret_cast<const double*>(g);
+    g_lnu = reinterpret_cast<const double*>(g + gath_lnu_off(T, W));
+    g_par = reinterpret_cast<const int32_t*>(g + gath_partner_off(T, W));
+    par_stride = W;
+    if (tid < A.n_ranks) {  // every rank's rows of this sweep have landed (bounded spin: a dead peer must not hang us)
+      const long long* f = reinterpret_cast<const long long*>(g + gath_flags_off(T, W)) + tid;
+      const long long t0 = clock64();
+      while (ld_acquire_sys(f) < sweep + 1)
+        if (clock64() - t0 > 60000000000ll) __trap();
+    }
+  }
   __syncthreads();
   if (T >= 2) {
     // carried walker of the chain that starts in slot k of the hottest row
     int s = valid ? k : 0;                                     // slot in row j+1
-    double hl = A.logl[int64_t(T - 1) * W + s];
+    double hl = __ldcg(g_logl + int64_t(T - 1) * W + s);
     int32_t hs = (T - 1) * W + s;
     // pair T-2: partner slot and uniform
-    int b = __ldg(A.perm + (int64_t(T - 2) * 2 + 1) * W + s);
-    double u = __ldg(A.lnu + int64_t(T - 2) * W + s);
+    int b = __ldcg(g_par + int64_t(T - 2) * par_stride + s);
+    double u = __ldcg(g_lnu + int64_t(T - 2) * W + s);
     // The decision of pair j is taken one iteration late, under the gathers of pair j-1: its operands arrived
     // together with the partner slot those gathers needed.
     auto decide = [&](int j, int s_w, int s_c, double lb, double uu) {
@@ -680,12 +768,12 @@ __global__ void __launch_bounds__(kChainThreads) pt_swap_plan_chain_kernel(const
     double p_lb = 0.0, p_u = 0.0;
     for (int j = T - 2; j >= 0; --j) {
       // gathers at slot b of row j: its logL (pair j), the partner and the uniform of pair j-1
-      const double lb_new = __ldg(A.logl + int64_t(j) * W + b);
+      const double lb_new = __ldcg(g_logl + int64_t(j) * W + b);
       int b_next = 0;
       double u_next = 0.0;
       if (j > 0) {
-        b_next = __ldg(A.perm + (int64_t(j - 1) * 2 + 1) * W + b);
-        u_next = __ldg(A.lnu + int64_t(j - 1) * W + b);
+        b_next = __ldcg(g_par + int64_t(j - 1) * par_stride + b);
+        u_next = __ldcg(g_lnu + int64_t(j - 1) * W + b);
       }
       if (j < T - 2) decide(j + 1, p_s, p_b, p_lb, p_u);
       p_s = s; p_b = b; p_lb = lb_new; p_u = u;

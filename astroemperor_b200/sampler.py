@@ -186,8 +186,19 @@ class PTSampler:
             self._state.append((mk((Tl, W, nd), 0), mk((Tl, W), n_row * nd * 8), mk((Tl, W), n_row * (nd + 1) * 8)))
         self._par = 0
         self.p, self.logl, self.logp = self._state[0]
+        self._gath, self._peer_gath = [], [[], []]
         if peer:
-            self._exchange_ipc_handles(nbytes)
+            # gathered blocks of the peer-push exchange (one per sweep parity): every rank writes its rows of logL
+            # and of the swap draws straight into them over NVLink (pt_publish_kernel) — no NCCL call in a sweep
+            nb = ctypes.c_int64()
+            _lib.check(_lib.lib().emp_gather_block_bytes(self.ntemps, W, ctypes.byref(nb)))
+            from .engine import SharedDeviceBuffer
+            for q in range(2):
+                g = SharedDeviceBuffer(self.engine.device, nb.value)
+                g.tensor((nb.value,), 0, typestr="|u1").zero_()
+                self._gath.append(g)
+            torch.cuda.synchronize(self.dev)
+            self._exchange_ipc_handles(nbytes, nb.value)
         self.accepted = torch.zeros((Tl, W), dtype=torch.uint8, device=self.dev)
         self._n_accepted = torch.zeros((Tl, W), dtype=torch.int32, device=self.dev)
         self._src = torch.empty((self.ntemps, W), dtype=torch.int32, device=self.dev)
@@ -198,19 +209,23 @@ class PTSampler:
         self._counters[1] = self._n_steps
         self.shard.warm_up(self.dev)
 
-    def _exchange_ipc_handles(self, nbytes):
-        """All ranks publish the CUDA IPC handles of their two state blocks once; every rank maps its peers'."""
+    def _exchange_ipc_handles(self, nbytes, gbytes):
+        """All ranks publish the CUDA IPC handles of their two state blocks and their two gathered blocks once;
+        every rank maps its peers'."""
         from .engine import SharedDeviceBuffer
         td, sh = self.shard.td, self.shard
-        mine = [b.export() for b in self._blocks]
+        mine = [b.export() for b in self._blocks] + [g.export() for g in self._gath]
         allh = [None] * sh.world
         td.all_gather_object(allh, mine, group=sh.group)
         for par in range(2):
-            row = []
+            row, grow = [], []
             for r in range(sh.world):
                 row.append(self._blocks[par] if r == sh.rank
                            else SharedDeviceBuffer.open(self.engine.device, allh[r][par], nbytes))
+                grow.append(self._gath[par] if r == sh.rank
+                            else SharedDeviceBuffer.open(self.engine.device, allh[r][2 + par], gbytes))
             self._peer_blocks[par] = row
+            self._peer_gath[par] = grow
 
     def _init_state(self, p0):
         torch = self.torch
@@ -414,7 +429,8 @@ class PTSampler:
         A.T_loc, A.W, A.nsteps, A.T_all = sh.n_local, self.nwalkers, nsteps, self.ntemps
         A.n_ranks, A.rank, A.strided = sh.world, sh.rank, 1 if sh.layout == "strided" else 0
         # graphs are keyed on the argument block: only the double-buffered pinned staging repeats its pointers
-        A.use_graph = 1 if (self.graph and sh.world == 1 and draws.get("_stage_index") is not None) else 0
+        push = sh.world > 1 and self.exchange == "peer"
+        A.use_graph = 1 if (self.graph and (sh.world == 1 or push) and draws.get("_stage_index") is not None) else 0
         cur, alt = self._state[par], self._state[1 - par]
         A.p, A.logl, A.logp = cur[0].data_ptr(), cur[1].data_ptr(), cur[2].data_ptr()
         A.p_alt, A.logl_alt, A.logp_alt = alt[0].data_ptr(), alt[1].data_ptr(), alt[2].data_ptr()
@@ -441,8 +457,16 @@ class PTSampler:
             A.store_cap = tgt[0].shape[0]
             A.store_ring = 1 if self.store == "host" else 0
         A.perm_hot_sorted = 1  # draws.py lists every pair by its slot in the warmer row
-        if sh.world == 1 and self.ntemps > 1:
+        if (sh.world == 1 or push) and self.ntemps > 1:
+            # the whole ladder's pairs, or (sharded, peer-push exchange) the pairs this rank drew
             A.perm, A.lnu_swap = draws["perm"].data_ptr(), draws["lnu_swap"].data_ptr()
+        if push:
+            if not draws.get("sharded_swap"):
+                raise ValueError("the peer-push exchange takes the swap draws sharded (this rank's pair rows)")
+            self._peer_pointers(A, par)
+            for q in range(2):
+                for r in range(sh.world):
+                    A.peer_gath[q][r] = self._peer_gath[q][r].ptr
         if key[1] is not None:
             if len(cache) > 16:
                 cache.clear()
@@ -483,6 +507,9 @@ class PTSampler:
         A = self._sweep_args(draws, nsteps)
         if sh.world == 1:
             eng.pt_sweep(A)
+            self._mark("sweep")
+        elif self.exchange == "peer":
+            eng.pt_sweep(A)   # stretch, publish to the peers' gathered blocks, plan, peer-read application
             self._mark("sweep")
         else:
             eng.pt_sweep_stretch(A)
@@ -729,17 +756,18 @@ class PTSampler:
         lay["dev"][i].copy_(packed, non_blocking=True)
         self._chunk_launch(lay, i, lay["k"], upload=False)
 
-    def _peer_pointers(self, A):
+    def _peer_pointers(self, A, par=None):
         """Where the swap finds the CURRENT (p | logl | logp) block of every rank: peer HBM mapped with CUDA IPC
         (exchange='peer': only the rows a rank receives cross NVLink), or, with exchange='allgather' (the fallback
         for platforms without CUDA IPC), one NCCL all-gather of the blocks into a scratch buffer, read by the same
         kernel through the same pointer table."""
         sh = self.shard
+        par = self._par if par is None else par
         nd, n_row = self.ndim, sh.n_local * self.nwalkers
         if self.exchange == "peer":
-            bases = [self._peer_blocks[self._par][r].ptr for r in range(sh.world)]
+            bases = [self._peer_blocks[par][r].ptr for r in range(sh.world)]
         else:
-            blk = self._blocks[self._par]
+            blk = self._blocks[par]
             self._gathered = sh.all_gather_flat(blk)[0]
             bases = [self._gathered.data_ptr() + r * blk.numel() * 8 for r in range(sh.world)]
         for r, base in enumerate(bases):

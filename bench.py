@@ -337,23 +337,23 @@ def make_sampler(cx, wl, total_sweeps=0, seed=2026, store="host", **kw):
 
 
 def run_e2e(cx, samp, eng, steps, T, W):
-    """The user's call: run_mcmc with host draws every sweep + D2H of logL[T_loc, W] every sweep (the chain
-    itself streams to pinned host memory behind the compute stream, store='host')."""
+    """The user's call: run_mcmc with host draws every sweep.  Every step's sample (positions, logL, logP of the
+    whole local ladder) is streamed to pinned host memory by the chain store (store='host', a copy stream one sweep
+    behind the compute stream) — that is the step's device -> host read; the host consumes logL[T_loc, W] of the
+    PREVIOUS sweep there while the current one runs.  (A separate copy of logL on the compute stream queued behind
+    the 20 MB chain drain in the copy engine and stalled the next sweep by 0.2 ms on one GPU, 0.9 ms on eight.)"""
     torch = cx.torch
-    ll_host = [torch.empty((samp.shard.n_local, W), dtype=torch.float64).pin_memory() for _ in range(2)]
-    landed = [torch.cuda.Event(), torch.cuda.Event()]
-    io = {"d2h": 0, "sum": 0.0}
+    io = {"d2h": 0, "sum": 0.0, "prev": None}
 
     def read_back(s, k):
-        # every sweep's logL[T_loc, W] is copied to pinned host memory; the host consumes the copy of the
-        # PREVIOUS sweep while this one runs (one sweep of pipelining instead of a stall per sweep)
-        i = k & 1
-        ll_host[i].copy_(s.logl, non_blocking=True)
-        landed[i].record()
-        if k >= 1:
-            landed[1 - i].synchronize()
-            io["sum"] += float(ll_host[1 - i][0, 0])
-        io["d2h"] += ll_host[i].numel() * 8
+        if s.store != "host" or not s._copy_done:
+            return
+        cur = (s._stored - 1, s._copy_done[-1][1])   # this sweep's sample index and the event of its drain
+        if io["prev"] is not None:
+            idx, ev = io["prev"]
+            ev.synchronize()
+            io["sum"] += float(s._ll[idx][0, 0])
+        io["prev"] = cur
 
     # small ensembles: run_mcmc replays k sweeps per graph launch; every step's sample (positions, logL, logP) still
     # lands in pinned host memory through the chain store, and logL of every step is read there after the run
@@ -674,8 +674,9 @@ def main():
                    "d2h_bytes_per_step": e["d2h"], "ms_per_step": e["ms"] / args.steps,
                    "value_nominal": e["proposals"] * N / (e["ms"] * 1e-3),
                    "host_ms_per_step_rank0": e["host_ms_per_step"],
-                   "includes": "host RNG draws, pinned staging, H2D, the sweep (CUDA graph), the chain sample "
-                               "[T,W,ndim+2] streamed to pinned host memory, D2H of logL[T,W]"},
+                   "includes": "host RNG draws, pinned staging, H2D, the sweep (CUDA graph), every step's sample "
+                               "[T,W,ndim+2] (positions, logL, logP) streamed to pinned host memory, where the host "
+                               "reads that step's logL one sweep later"},
            "callable_host": {"value": callable_value, "unit": UNIT, "ms_per_call": call_s * 1e3,
                              "n_eval_per_call": int(len(th_host)),
                              "what": "emp_logl_batch_host on the current ensemble (all inside the prior): pageable "

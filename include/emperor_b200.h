@@ -312,9 +312,20 @@ typedef struct EmpPtSweep {
   /* sharded ladder only: CURRENT buffers (p, logl, logp) of every rank, peer HBM mapped with
    * emp_ipc_open; entry `rank` must equal p / logl / logp */
   const double *peer_p[EMP_MAX_PEERS], *peer_logl[EMP_MAX_PEERS], *peer_logp[EMP_MAX_PEERS];
-  const double *logl_all;   /* [T_all, W] all-gathered logL (sharded) or NULL (= logl)             */
+  const double *logl_all;   /* [T_all, W] all-gathered logL (sharded, NCCL exchange) or NULL          */
+  /* sharded ladder, peer-push exchange (no NCCL, emp_pt_sweep runs the whole sweep): the gathered blocks
+   * (emp_gather_block_bytes, zero-initialised, one per sweep parity) of every rank, peers mapped with
+   * emp_ipc_open.  After the stretch phase a rank writes its rows of logL and of the swap draws (perm /
+   * lnu_swap then hold THIS rank's T_loc pair rows: row t = the pair whose index is the rank's t-th temperature)
+   * into every block over NVLink and raises its flag there; the plan kernel waits for the flags of the sweep.
+   * All NULL: not used. */
+  void *peer_gath[2][EMP_MAX_PEERS];
 } EmpPtSweep;
-/* Single GPU: the whole sweep (6 launches at nsteps = 1). */
+/* Size of a gathered block of the peer-push exchange: [logL | swap uniforms | partner slots] of the whole ladder
+ * in ladder order + one arrival flag per rank. */
+int emp_gather_block_bytes(int32_t T_all, int32_t W, int64_t *bytes);
+/* The whole sweep: single GPU (6 launches at nsteps = 1), or a sharded ladder with the peer-push exchange
+ * (7 launches: + pt_publish_kernel; nothing but this library's kernels, so the sweep is graph-capturable). */
 int emp_pt_sweep(EmpHandle *h, const EmpPtSweep *s);
 /* k consecutive single-GPU sweeps replayed from ONE graph launch (argument blocks s[0..k-1]; the state parity
  * alternates and the draw pointers advance from block to block).  When draws_host is not NULL the graph begins

@@ -126,6 +126,26 @@ def test_chunked_run_equals_sweep_by_sweep(name, T, W, nsweeps, nsteps, kw):
     assert a.iteration == b.iteration and a._n_steps == b._n_steps and a._stored == b._stored
 
 
+def test_chain_plan_kernel_equals_shared_memory_plan_kernels(monkeypatch):
+    """The swap plan as W independent chains (pt_swap_plan_chain_kernel, the default) against the single-CTA
+    shared-memory kernels it replaced (EMP_PLAN_NO_CHAIN=1), on ladders larger than the oracle tests can afford:
+    plans, swap counts, adapted ladders and chains must be the same bits."""
+    for T, W in ((48, 2048), (9, 4100), (130, 256)):
+        runs = []
+        for no_chain in ("0", "1"):
+            monkeypatch.setenv("EMP_PLAN_NO_CHAIN", no_chain)   # read when the handle first prepares a plan
+            g, spec, eng, samp, _, p0 = _setup("c1_51peg_k1_p0", T, W, seed=31, with_D=True, chunk=1, store=None)
+            samp.run_mcmc(p0, nsweeps=4, nsteps=1)
+            runs.append((samp.state_numpy(), samp._src.cpu().numpy(), samp.betas.copy(), samp.get_tsw(), samp.get_smd()))
+            del samp
+            eng.close()
+        a, b = runs
+        assert all(np.array_equal(x, y) for x, y in zip(a[0], b[0])), (T, W)
+        assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3]), (T, W)
+        assert np.array_equal(a[4], b[4]), (T, W)
+        assert a[3].mean() > 0.05  # swaps did happen
+
+
 def test_run_mcmc_api_and_storage():
     g, spec, eng, samp, orc, p0 = _setup("c1_51peg_k1_p0", 3, 32, seed=3)
     state = samp.run_mcmc(p0, nsweeps=12, nsteps=2, progress=False)
