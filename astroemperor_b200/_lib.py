@@ -81,6 +81,7 @@ SYMBOLS = [
     ("emp_draws_destroy", ctypes.c_int, [_P]),
     ("emp_draws_get_state", ctypes.c_int, [_P, _I32, _P, ctypes.POINTER(_I32)]),
     ("emp_draws_sweep", ctypes.c_int, [_P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _I32, _P, _P]),
+    ("emp_draws_sweeps", ctypes.c_int, [_P, _I32, _I64, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _I32, _P, _P]),
     ("emp_pt_sweep", ctypes.c_int, [_P, ctypes.POINTER(EmpPtSweepC)]),
     ("emp_gather_block_bytes", ctypes.c_int, [_I32, _I32, ctypes.POINTER(_I64)]),
     ("emp_pt_sweep_chunk", ctypes.c_int, [_P, ctypes.POINTER(EmpPtSweepC), ctypes.c_int32, _P, _P, ctypes.c_int64]),

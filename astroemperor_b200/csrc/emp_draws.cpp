@@ -267,3 +267,40 @@ extern "C" int emp_draws_sweep(EmpDrawStreams* d, const int32_t* temp_streams, i
   d->pool->run(n_temps + n_rows, item);
   return EMP_OK;
 }
+
+// k consecutive sweeps in ONE parallel region: sweep q's arrays start q * stride_bytes behind the given pointers
+// (the chunk layout of `emp_pt_sweep_chunk`).  A stream's k sweeps are drawn by one worker in order, so the draws are
+// exactly those of k successive emp_draws_sweep calls — but small ladders (2 temperatures at BASELINE config 1) pay
+// one pool dispatch per chunk instead of one per sweep.
+extern "C" int emp_draws_sweeps(EmpDrawStreams* d, int32_t k, int64_t stride_bytes, const int32_t* temp_streams,
+                                int32_t n_temps, int32_t W, int32_t nsteps, int32_t* half_idx, double* u_zz,
+                                int32_t* rint, double* u_acc, const int32_t* pair_streams, int32_t n_rows,
+                                int32_t* perm, double* u_swap) {
+  if (!d || k < 1 || stride_bytes < 0 || n_temps < 0 || n_rows < 0 || W < 2 || (W & 1) || nsteps < 0)
+    return dfail(EMP_EINVAL);
+  if (n_temps > 0 && (!temp_streams || !half_idx || !u_zz || !rint || !u_acc)) return dfail(EMP_EINVAL);
+  if (n_rows > 0 && (!pair_streams || !perm || !u_swap)) return dfail(EMP_EINVAL);
+  const int ns = int(d->s.size());
+  for (int j = 0; j < n_temps; ++j)
+    if (temp_streams[j] < 0 || temp_streams[j] >= ns) return dfail(EMP_EINVAL);
+  for (int r = 0; r < n_rows; ++r)
+    if (pair_streams[r] >= ns) return dfail(EMP_EINVAL);
+  auto at = [stride_bytes](auto* p, int q) {
+    using T = decltype(p);
+    return reinterpret_cast<T>(reinterpret_cast<char*>(p) + size_t(q) * size_t(stride_bytes));
+  };
+  const std::function<void(int)> item = [=](int i) {
+    for (int q = 0; q < k; ++q) {
+      if (i < n_temps) {
+        stretch_stream(d->s[temp_streams[i]], i, n_temps, W, nsteps, at(half_idx, q), at(u_zz, q), at(rint, q),
+                       at(u_acc, q));
+      } else {
+        const int r = i - n_temps;
+        swap_stream(pair_streams[r] < 0 ? nullptr : &d->s[pair_streams[r]], W, at(perm, q) + size_t(r) * 2 * W,
+                    at(u_swap, q) + size_t(r) * W);
+      }
+    }
+  };
+  d->pool->run(n_temps + n_rows, item);
+  return EMP_OK;
+}

@@ -13,11 +13,16 @@
 // the NumPy oracle.
 //
 // A sweep with nsteps = 1 is SIX launches (round 1: 13 + torch glue + a host synchronisation):
-//   per half-ensemble  pt_propose_prior_kernel   proposal + prior program + compaction
-//                      logl_rv_kernel            likelihood + Metropolis accept in its epilogue
-//   per sweep          pt_swap_plan_kernel       hot->cold swap plan + ladder adaptation + histories
-//                      pt_apply_plan_kernel      row gather (local or peer HBM over NVLink) + swap mean
-//                                                distance + chain store
+//   per half-ensemble  pt_propose_prior_kernel    proposal + prior program + compaction
+//                      logl_rv_kernel             likelihood + Metropolis accept in its epilogue
+//   per sweep          pt_swap_plan_chain_kernel  hot->cold swap plan as W independent chains + ladder adaptation
+//                                                 + histories (the single-CTA shared-memory kernels pt_swap_plan_*
+//                                                 remain for pairs that are not listed by their warmer slot)
+//                      pt_apply_plan_kernel       row gather (local or peer HBM over NVLink) + swap mean
+//                                                 distance + chain store
+// A ladder sharded over several GPUs adds ONE launch and no NCCL call: pt_publish_kernel writes the rank's rows of
+// logL and of the swap draws into every peer's gathered block over NVLink and raises a flag; the plan kernel waits
+// for the flags of the sweep.
 #pragma once
 #include <stdint.h>
 #include "emp_device.cuh"

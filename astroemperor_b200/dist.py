@@ -4,12 +4,16 @@ One process per GPU (`torch.distributed`, NCCL over NVLink/NVSwitch).  Every ran
 temperatures (positions, logL, logP) and a full replica of the data set.  The
 within-temperature stretch steps need no communication.  Once per sweep:
 
-  1. all-gather of logL[T, W] (FP64; config 5: 4 MiB in total);
-  2. every rank replays the SAME sequential hot -> cold swap sweep on the gathered logL with
-     the same host draws (kernel pt_swap_plan) and so knows the whole permutation `src[T, W]`;
-  3. rows (position, logL, logP) whose source lives on another rank are exchanged
-     point-to-point: because the plan is replicated, sender and receiver derive the same row
-     lists without any handshake (`exchange_rows`).
+  1. logL[T, W] (FP64; config 5: 4 MiB in total) and the swap draws reach every rank: by peer writes
+     over NVLink into CUDA-IPC-mapped gathered blocks (sampler.py, exchange='peer': no NCCL call in a
+     sweep), or by NCCL all-gathers (`all_gather_rows`, exchange='allgather');
+  2. every rank replays the SAME hot -> cold swap sweep on the gathered logL with the same host draws
+     (kernel pt_swap_plan_chain) and so knows the whole permutation `src[T, W]`;
+  3. rows (position, logL, logP) whose source lives on another rank are read from the owner's HBM by
+     the plan-application kernel (exchange='peer'), gathered from an all-gathered copy of the blocks
+     (exchange='allgather'), or — `exchange_rows`, the NCCL point-to-point formulation kept for
+     platforms without peer access, not used by the sampler — sent pairwise: because the plan is
+     replicated, sender and receiver derive the same row lists without any handshake.
 
 Layouts:
   * "strided" (default): rank r holds temperatures r, r+G, r+2G, ...  Cold chains converge and

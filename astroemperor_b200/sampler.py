@@ -10,13 +10,17 @@ plan, the ladder adaptation (reddemcee adapt_tau / adapt_nu, adapt_mode 0), the 
 beta histories and the chain store.  The host only supplies the random draws (draws.py), one
 sweep ahead, through a double-buffered pinned staging area; there is NO host synchronisation
 inside a run: with nsteps = 1 a sweep is six kernel launches, replayed from a CUDA graph.
+Small ensembles (a sweep of tens of microseconds) are replayed k sweeps per graph launch
+(`emp_pt_sweep_chunk`: the graph uploads the k sweeps' draws with one copy node).
 
 With `torch.distributed` initialised (one process per GPU) the temperature ladder is sharded
 over the ranks, T/G temperatures each, interleaved by default (dist.py): the stretch steps need
-no communication; per sweep logL[T, W] (and the swap draws each rank generated for its own
-pairs) are all-gathered over NCCL, every rank replays the same plan + adaptation, and the swap is
-applied by reading the source rows straight from the owners' HBM over NVLink (CUDA IPC): only
-the rows a rank receives cross the links.
+no communication; per sweep every rank WRITES its rows of logL[T, W] and of the swap draws it
+generated for its own pairs into every peer's gathered block over NVLink (CUDA IPC, one small
+kernel + release/acquire flags), every rank replays the same plan + adaptation, and the swap is
+applied by reading the source rows straight from the owners' HBM: only the rows a rank receives
+cross the links, and a sweep contains no NCCL call (7 launches, graph-replayed).
+`exchange='allgather'` keeps the NCCL formulation (all-gathers of logL, the draws and the blocks).
 """
 from __future__ import annotations
 
@@ -625,9 +629,8 @@ class PTSampler:
         t0 = _time.perf_counter()
         v = lay["np"][i]
         if self.streams.native:
-            fn = _lib.lib().emp_draws_sweep
-            for j in range(n):
-                _lib.check(fn(*lay["gen"][i][j]))
+            g0 = lay["gen"][i][0]   # sweep q of the chunk sits q * total bytes behind sweep 0: one call draws them all
+            _lib.check(_lib.lib().emp_draws_sweeps(g0[0], n, lay["total"], *g0[1:]))
         else:
             for j in range(n):
                 draw_sweep(self.streams, self.nwalkers, self.ndim, lay["nsteps"], self.a, swap=self.ntemps > 1,

@@ -670,6 +670,7 @@ def main():
            "value_nominal": value_nominal,
            "evaluated_fraction": evaluated / max(proposals, 1),
            "logl_evals_per_s": evaluated / (ms * 1e-3),
+           "pt_sweeps_per_s": args.steps / (ms * 1e-3),   # full PT steps (stretch + swap + adaptation) per second
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e["h2d"],
                    "d2h_bytes_per_step": e["d2h"], "ms_per_step": e["ms"] / args.steps,
                    "value_nominal": e["proposals"] * N / (e["ms"] * 1e-3),

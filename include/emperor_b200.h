@@ -370,6 +370,12 @@ int emp_draws_sweep(EmpDrawStreams *d, const int32_t *temp_streams, int32_t n_te
                     int32_t *half_idx, double *u_zz, int32_t *rint, double *u_acc, const int32_t *pair_streams,
                     int32_t n_rows, int32_t *perm, double *u_swap);
 
+/* The same for k consecutive sweeps in one call: sweep q's arrays start q * stride_bytes behind the given
+ * pointers (the chunk layout of emp_pt_sweep_chunk); identical to k successive emp_draws_sweep calls. */
+int emp_draws_sweeps(EmpDrawStreams *d, int32_t k, int64_t stride_bytes, const int32_t *temp_streams,
+                     int32_t n_temps, int32_t W, int32_t nsteps, int32_t *half_idx, double *u_zz, int32_t *rint,
+                     double *u_acc, const int32_t *pair_streams, int32_t n_rows, int32_t *perm, double *u_swap);
+
 /* ---- introspection -------------------------------------------------------- */
 /* Number of kernels this handle has launched since creation (bench.py gpu_launches). */
 int emp_launch_count(EmpHandle *h, int64_t *count);

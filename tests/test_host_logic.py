@@ -33,6 +33,40 @@ def test_native_draws_are_bit_identical_to_numpy_randomstate(built_lib, T, W, ns
     assert db.zz is out["zz"] and all(np.array_equal(getattr(da, f), out[f]) for f in da.FIELDS)
 
 
+@pytest.mark.parametrize("T,W,nsteps,k,threads", [(3, 20, 2, 5, 3), (2, 100, 1, 64, 8), (1, 16, 1, 4, 2)])
+def test_native_draws_of_a_chunk_equal_sweep_by_sweep(built_lib, T, W, nsteps, k, threads):
+    """emp_draws_sweeps (the k sweeps of a chunk in one parallel region, sweep q at q * stride bytes) gives exactly
+    the bytes of k successive emp_draws_sweep calls: a chunked run_mcmc consumes the same random streams."""
+    from astroemperor_b200 import _lib
+    from astroemperor_b200.draws import DrawStreams, sweep_shapes
+    L = _lib.lib()
+    shapes = sweep_shapes(T, W, nsteps, max(T - 1, 1))
+    offs, tot = [], 0
+    for f, shp, dt in shapes:
+        offs.append(tot)
+        tot += (int(np.prod(shp)) * np.dtype(dt).itemsize + 255) // 256 * 256
+
+    def run(chunked):
+        streams = DrawStreams(5, T, native=True, n_threads=threads)   # owns the C generator: keep it alive
+        h = streams.handle()
+        buf = np.zeros(k * tot, dtype=np.uint8)
+        ts = np.arange(T, dtype=np.int32)
+        rs = np.array([T + j for j in range(T - 1)], dtype=np.int32)
+        p = {f: buf.ctypes.data + o for (f, _, _), o in zip(shapes, offs)}
+        if chunked:
+            _lib.check(L.emp_draws_sweeps(h, k, tot, ts.ctypes.data, T, W, nsteps, p["half_idx"], p["zz"], p["rint"],
+                                          p["lnu"], rs.ctypes.data, len(rs), p["perm"], p["lnu_swap"]))
+        else:
+            for q in range(k):
+                o = q * tot
+                _lib.check(L.emp_draws_sweep(h, ts.ctypes.data, T, W, nsteps, p["half_idx"] + o, p["zz"] + o,
+                                             p["rint"] + o, p["lnu"] + o, rs.ctypes.data, len(rs), p["perm"] + o,
+                                             p["lnu_swap"] + o))
+        return buf
+    a, b = run(True), run(False)
+    assert a.any() and np.array_equal(a, b)
+
+
 def test_deterministic_exp_of_the_ladder_adaptation():
     """oracle exp_det (replayed operation by operation on the device, emp_pt.cuh) is within 1 ulp of exp; NumPy's own
     exp is not correctly rounded either, so "the reference's np.exp" is only defined to that level; over 2000
