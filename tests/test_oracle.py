@@ -45,6 +45,46 @@ def test_kat_51peg_k1_notebook_fit():
     assert -869.6 < best[0] < -869.4, best
 
 
+def test_kat_51peg_acceleration_notebook_value():
+    """tests/00_mini_test.ipynb cell 14 (Acceleration + Offset + Jitter, no Keplerian) prints the best sample
+    (-0.006, 2.256, 35.868), "The maximum likelihood is -1307.004" and "The chi2 is 301.791": the acceleration
+    template (acc.model:2) at the printed, rounded parameters gives -1307.015 and 301.81."""
+    from astroemperor_b200.data import RVData
+    from astroemperor_b200.frontend import default_spec
+    g, _ = load_golden("c1_51peg_k0")
+    data = RVData(t=g["t"], y=g["y"], yerr=g["yerr"], flag=g["flag"], common_t=0.0, labels=["51peg"])
+    cm = default_spec(data, 0, acceleration=1).compile()
+    orc = RVOracle(cm, g["t"], g["y"], g["yerr"], g["flag"])
+    th = np.array([-0.006, 2.256, 35.868])
+    assert abs(orc.my_likelihood(th) - (-1307.004)) < 0.03
+    m0, e0 = orc.my_model(th)
+    assert abs(float(np.sum((g["y"] - m0) ** 2 / e0)) - 301.791) < 0.05
+
+
+def test_kat_hip21850_astrometry_notebook_fit():
+    """tests/03_hip21850_test.ipynb cell 7 (joint RV + Hipparcos-Gaia astrometry, 1 Keplerian, 23 dims) prints the
+    best sample's parameters to 3 decimals, "The maximum likelihood is -642.157" and "The chi2 is 134.916".  The
+    oracle (RV likelihood + loglike_AM, a00.like:5-8) evaluated at that rounded table gives -641.83 and chi2 134.25:
+    the published numbers pin the astrometric block at the level the rounding of 23 printed parameters allows."""
+    from oracle.am_oracle import AMOracle
+    g, spec = load_golden("c3_hip21850_am_k1")
+    cm = spec.compile()
+    am = {k[3:]: g[k] for k in g.files if k.startswith("am_")}
+    ao, ro = AMOracle(cm, am), RVOracle(cm, g["t"], g["y"], g["yerr"], g["flag"])
+    # Period, Amplitude, Phase, Ecc, Longitude, Inclination, Omega | Acceleration | Offset 1-4 | Jitter 1-4 |
+    # Offset RA, DE, PLX, pm RA, pm DE | Jitter Hipparcos, Jitter Gaia   ("Value (max)" column of the notebook)
+    th = np.array([2567.37, 120.188, 5.553, 0.201, 0.659, 1.084, 4.289, 0.006, -24.341, -4.909, -105.186, -97.556,
+                   29.644, 0.825, 8.933, 1.743, -0.437, -0.257, 0.003, -0.183, 0.154, 0.257, 1.086])
+    assert len(th) == cm.ndim_free
+    with np.errstate(all="ignore"):
+        ll = float(ro.my_likelihood(th) + ao.loglike_AM(th))
+    assert abs(ll - (-642.157)) < 0.5, ll
+    m0, e0 = ro.my_model(th)
+    chi2 = float(np.sum((g["y"] - m0) ** 2 / e0))   # emp.py:1189
+    assert abs(chi2 - 134.916) < 1.0, chi2
+    assert len(g["y"]) - len(th) == 74 and abs(chi2 / 74 - 1.823) < 0.015   # "The reduced chi2 is 1.823"
+
+
 def test_kepler_residual_grid():
     """|E - e sin E - M| small over a grid incl. the corners SURVEY.md §8c lists."""
     eccs = [0.0, 1e-7, 0.3, 0.9, 0.99]
