@@ -98,58 +98,72 @@ class WorkerPool {
     cv_.notify_all();
     for (auto& t : th_) t.join();
   }
-  // runs fn(0..n-1) on the workers and the calling thread; returns when all are done
+  // runs fn(0..n-1) on the workers and the calling thread; returns when all are done.
+  // Every run owns its counters (a Job on the caller's stack) and workers pick the job pointer up UNDER the mutex,
+  // together with their "active" mark: a worker that wakes late — after the run it was woken for has finished, maybe
+  // while the next one is being set up — either finds no job, or a job whose owner cannot return before the worker
+  // has left it.  (Shared counters + an unsynchronised function pointer let such a worker claim item 0 of the NEXT
+  // run with the stale null pointer of the previous one and drop it: the caller then waited for ever.)
   void run(int n, const std::function<void(int)>& fn) {
     if (th_.empty() || n <= 1) {
       for (int i = 0; i < n; ++i) fn(i);
       return;
     }
+    Job job;
+    job.fn = &fn;
+    job.n = n;
     {
       std::lock_guard<std::mutex> lk(m_);
-      fn_.store(&fn);
-      n_.store(n);
-      next_.store(0);
-      done_.store(0);
+      job_ = &job;
       ++gen_;
     }
     cv_.notify_all();
-    work();
-    while (done_.load(std::memory_order_acquire) < n) std::this_thread::yield();
-    // every item is done: a worker that wakes up late finds nothing to do; wait for those still inside work()
-    // (they may hold the pointer to `fn`, which dies with the caller's frame)
-    fn_.store(nullptr);
+    work(job);
+    while (job.done.load(std::memory_order_acquire) < n) std::this_thread::yield();
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      job_ = nullptr;
+    }
     while (active_.load(std::memory_order_acquire) > 0) std::this_thread::yield();
   }
 
  private:
-  void work() {
+  struct Job {
+    const std::function<void(int)>* fn = nullptr;
+    int n = 0;
+    std::atomic<int> next{0}, done{0};
+  };
+  static void work(Job& j) {
     for (;;) {
-      const std::function<void(int)>* f = fn_.load();
-      const int i = next_.fetch_add(1);
-      if (!f || i >= n_.load()) break;
-      (*f)(i);
-      done_.fetch_add(1, std::memory_order_release);
+      const int i = j.next.fetch_add(1);
+      if (i >= j.n) break;
+      (*j.fn)(i);
+      j.done.fetch_add(1, std::memory_order_release);
     }
   }
   void loop() {
     uint64_t seen = 0;
     for (;;) {
+      Job* j = nullptr;
       {
         std::unique_lock<std::mutex> lk(m_);
         cv_.wait(lk, [&]() { return gen_ != seen; });
         seen = gen_;
         if (stop_) return;
-        active_.fetch_add(1);
+        j = job_;
+        if (j) active_.fetch_add(1);
       }
-      work();
-      active_.fetch_sub(1, std::memory_order_release);
+      if (j) {
+        work(*j);
+        active_.fetch_sub(1, std::memory_order_release);
+      }
     }
   }
   std::vector<std::thread> th_;
   std::mutex m_;
   std::condition_variable cv_;
-  std::atomic<const std::function<void(int)>*> fn_{nullptr};
-  std::atomic<int> n_{0}, next_{0}, done_{0}, active_{0};
+  Job* job_ = nullptr;            // guarded by m_
+  std::atomic<int> active_{0};
   uint64_t gen_ = 0;
   bool stop_ = false;
 };

@@ -253,6 +253,12 @@ class SharedDeviceBuffer:
             (L.emp_dev_free if self.owner else L.emp_ipc_close)(self.device, ctypes.c_void_p(self.ptr))
             self.ptr = 0
 
+    def __del__(self):   # a sampler that goes away returns its blocks (views keep the buffer alive: _keepalive)
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def __del__(self):
         try:
             self.close()

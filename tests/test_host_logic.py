@@ -67,6 +67,24 @@ def test_native_draws_of_a_chunk_equal_sweep_by_sweep(built_lib, T, W, nsteps, k
     assert a.any() and np.array_equal(a, b)
 
 
+@pytest.mark.timeout(120)
+def test_native_draw_pool_survives_oversubscription(built_lib):
+    """Tens of thousands of back-to-back tiny sweeps on a pool with four times more workers than this host has
+    cores: workers wake up late, after the run they were woken for is over.  (The first pool shared its item counter
+    between runs: a late worker could claim item 0 of the NEXT run with the previous run's cleared function pointer
+    and drop it, and the caller waited for ever — seen once as a hung GPU test session.)"""
+    from astroemperor_b200.draws import DrawStreams, draw_sweep
+    st = DrawStreams(3, 2, native=True, n_threads=4 * (os.cpu_count() or 8))
+    ref = DrawStreams(3, 2, native=False)
+    for it in range(40000):
+        d = draw_sweep(st, 4, 3, 1)
+        if it % 8000 == 0:
+            r = draw_sweep(ref, 4, 3, 1)
+            for _ in range(7999 if it + 8000 <= 40000 else 0):
+                r2 = draw_sweep(ref, 4, 3, 1)   # keep the NumPy streams in step
+            assert np.array_equal(d.zz, r.zz) and np.array_equal(d.perm, r.perm)
+
+
 def test_deterministic_exp_of_the_ladder_adaptation():
     """oracle exp_det (replayed operation by operation on the device, emp_pt.cuh) is within 1 ulp of exp; NumPy's own
     exp is not correctly rounded either, so "the reference's np.exp" is only defined to that level; over 2000
