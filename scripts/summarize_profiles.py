@@ -143,7 +143,7 @@ def kernel_metrics():
 def benches():
     for name in ("c4", "c5", "c2", "reference"):
         p = os.path.join(G, f"{src_tag}_bench_{name}.json")
-        if os.path.exists(p):
+        if os.path.exists(p) and os.path.getsize(p) > 2:
             line = open(p).read().strip().splitlines()[-1]
             json.loads(line)
             open(os.path.join(P, f"{dst_tag}_bench_{name}.json"), "w").write(line + "\n")
