@@ -226,6 +226,7 @@ class SharedDeviceBuffer:
         self.ptr = int(ptr)
 
     def export(self) -> bytes:
+        self.exported = True
         buf = ctypes.create_string_buffer(64)
         _lib.check(_lib.lib().emp_ipc_export(self.device, ctypes.c_void_p(self.ptr), buf))
         return buf.raw
@@ -253,9 +254,16 @@ class SharedDeviceBuffer:
             (L.emp_dev_free if self.owner else L.emp_ipc_close)(self.device, ctypes.c_void_p(self.ptr))
             self.ptr = 0
 
-    def __del__(self):   # a sampler that goes away returns its blocks (views keep the buffer alive: _keepalive)
+    exported = False
+
+    def __del__(self):
+        # A sampler that goes away unmaps its peers' blocks and frees its own — except own blocks that were exported:
+        # freeing memory a peer may still have mapped is undefined behaviour, and a destructor cannot run the
+        # barrier that would order the two.  Those stay allocated until `close()` is called after a barrier, or
+        # the process exits (two state blocks + two gathered blocks per sharded sampler).
         try:
-            self.close()
+            if not (self.owner and self.exported):
+                self.close()
         except Exception:
             pass
 
