@@ -164,6 +164,49 @@ def test_draw_sweep_protocol():
         draw_sweep(DrawStreams(1, 2), 7, 3, 1)
 
 
+def chain_swap_plan(logl, betas, perm, lnu_swap):
+    """NumPy restatement of csrc/emp_pt.cuh::pt_swap_plan_chain_kernel: the hot -> cold swap sweep as W independent
+    chains.  Chain k starts in slot k of the hottest row carrying that walker (source index, logL); at pair j it moves
+    from slot s of row j+1 to slot b = partner_j[s] of row j, decides the swap with the ORIGINAL occupant of (j, b)
+    and carries whoever sits in (j, b) afterwards.  No chain reads anything another chain wrote."""
+    T, W = logl.shape
+    src = np.empty((T, W), dtype=np.int32)
+    n_acc = np.zeros(max(T - 1, 0), dtype=np.int32)
+    for k in range(W):                      # one device thread per chain
+        s, hl, hs = k, logl[T - 1, k], (T - 1) * W + k
+        for j in range(T - 2, -1, -1):
+            assert perm[j, 0, s] == s       # pairs are listed by their slot in the warmer row
+            b = perm[j, 1, s]
+            lb, cold = logl[j, b], j * W + b
+            acc = (betas[j] - betas[j + 1]) * (hl - lb) > lnu_swap[j, s]
+            src[j + 1, s] = cold if acc else hs
+            if not acc:
+                hl, hs = lb, cold
+            n_acc[j] += int(acc)
+            s = b
+        src[0, s] = hs
+    return n_acc, src
+
+
+@pytest.mark.parametrize("T,W,scale", [(2, 6, 1.0), (7, 40, 3.0), (16, 64, 0.3), (33, 10, 30.0)])
+def test_swap_sweep_is_W_independent_chains(T, W, scale):
+    """The claim behind the chain plan kernel: following each walker's path down the ladder gives
+    the plan and the swap counts of the reference-order sweep (oracle/pt_oracle.py::swap_sweep, sequential over the
+    pairs with whole rows exchanged) bit for bit, for any acceptance rate."""
+    from astroemperor_b200.draws import DrawStreams, draw_sweep
+    from oracle.pt_oracle import swap_sweep
+    rng = np.random.RandomState(T * 1000 + W)
+    d = draw_sweep(DrawStreams(9, T), W, 3, 1)
+    logl = rng.normal(size=(T, W)) * scale - 50.0
+    logl[rng.randint(T), rng.randint(W)] = -np.inf   # a walker outside the support never blocks a chain
+    betas = np.geomspace(1.0, 1e-3, T)
+    p = rng.normal(size=(T, W, 2))
+    n_ref, src_ref, _ = swap_sweep(p.copy(), logl.copy(), np.zeros((T, W)), betas, d.perm, d.lnu_swap)
+    n_chain, src_chain = chain_swap_plan(logl, betas, d.perm, d.lnu_swap)
+    assert np.array_equal(n_ref, n_chain) and np.array_equal(src_ref, src_chain)
+    assert 0 < n_ref.sum() < (T - 1) * W or T == 2   # both outcomes occur
+
+
 def test_initial_positions_follow_set_init():
     from astroemperor_b200.draws import initial_positions
     g, spec = load_golden("mini_51peg_k1_p1")

@@ -56,7 +56,24 @@ def test_likelihood_kernels_are_tma_fp64_and_register_resident(sass):
 
 def test_every_kernel_of_the_path_is_present(sass):
     names = " ".join(sass)
-    for k in ("prior_compact_kernel", "pt_propose_prior_kernel", "pt_swap_plan_kernel", "pt_apply_plan_kernel",
-              "pt_gather_rows_kernel", "am_logl_kernel", "model_rv_kernel", "kepler_solve_kernel",
-              "kepler_grid_kernel", "fp64_peak_kernel"):
+    for k in ("prior_compact_kernel", "pt_propose_prior_kernel", "pt_swap_plan_kernel", "pt_swap_plan_chain_kernel",
+              "pt_publish_kernel", "pt_apply_plan_kernel", "pt_gather_rows_kernel", "am_logl_kernel", "model_rv_kernel",
+              "kepler_solve_kernel", "kepler_grid_kernel", "fp64_peak_kernel"):
         assert k in names, k
+
+
+def test_peer_exchange_kernels_use_system_scope_release_acquire(sass):
+    """Sharded ladder without NCCL: pt_publish_kernel stores into peer memory, fences at system scope
+    and raises its flag with a system-scope release store; the chain plan kernel polls the flags with system-scope
+    acquire loads (bounded by the clock: a dead peer traps instead of hanging), gathers through L2 only, keeps no
+    chain state in shared memory (no barrier inside the pair loop) and nothing in local memory."""
+    pub = _ops(next(v for k, v in sass.items() if "pt_publish_kernel" in k))
+    assert "MEMBAR.SC.SYS" in pub and any(o.startswith("STG.E.64.STRONG.SYS") for o in pub)
+    chain_lines = next(v for k, v in sass.items() if "pt_swap_plan_chain_kernel" in k)
+    chain = _ops(chain_lines)
+    assert any(o.startswith("LDG.E.64.STRONG.SYS") for o in chain), "no system-scope acquire load of the flags"
+    assert any(o.startswith("BPT") for o in chain) and any("SR_CLOCK" in l for l in chain_lines)
+    assert sum(o.startswith("LDG.E") and "STRONG.GPU" in o for o in chain) >= 3   # __ldcg gathers: L2, not L1
+    first_exit = next(i for i, o in enumerate(chain) if o == "EXIT")
+    assert not any(o.startswith(("LDL", "STL")) for o in chain[:first_exit])
+    assert not any(o.startswith(("UBLKCP", "HMMA", "UTC")) for o in chain)
