@@ -654,7 +654,7 @@ static int enqueue_plan(EmpHandle* h, const PtPlan& A, cudaStream_t st) {
   PlanKernel k = nullptr;
   size_t smem = 0;
   // TMA-fed kernel: arrays padded to kR * 1024 entries, at least 3 ring stages -> W <= 2048
-  if (A.hot_sorted && A.T >= 2 && !h->plan_no_chain) {
+  if (A.hot_sorted && A.T >= 2 && (!h->plan_no_chain || A.gath[0])) {  // gathered operands: chain kernel only
     const unsigned grid = unsigned((W + kChainThreads - 1) / kChainThreads);
     pt_swap_plan_chain_kernel<<<grid, kChainThreads, 0, st>>>(A, h->d_plan_cnt,
                                                               reinterpret_cast<uint32_t*>(h->d_plan_cnt + kPlanMaxT));

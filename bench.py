@@ -303,6 +303,9 @@ class Ctx:
         return allr.cpu().tolist()
 
 
+LADDER_MODE = "range"   # --ladder: "range" (default) or "extend" (the default spacing carried on to T x world rungs)
+
+
 def ladder(wl, world):
     """The ladder of a run on `world` GPUs: T = T_per_gpu x world rungs, geometric, between beta = 1 and the hottest
     rung of the config's own ladder (`ladder_T` rungs, default T_per_gpu, with the default spacing).  More GPUs
@@ -312,6 +315,8 @@ def ladder(wl, world):
     their moves outside its box and are never evaluated.)"""
     from astroemperor_b200.draws import default_betas
     T = wl.w["T"] * world
+    if LADDER_MODE == "extend":
+        return default_betas(wl.spec.ndim, T)
     b1 = default_betas(wl.spec.ndim, wl.w.get("ladder_T", wl.w["T"]))
     if len(b1) == T or T < 2:
         return b1[:T]
@@ -502,7 +507,13 @@ def main():
                     help="untimed sweeps before the warm-up so that the ensemble has left its uniform "
                          "initial state (a young chain proposes ~40%% of its moves outside the prior box, "
                          "which are never evaluated)")
+    ap.add_argument("--ladder", default="range", choices=["range", "extend"],
+                    help="N-GPU ladder: 'range' = T x N rungs over the temperature range of the config's own ladder "
+                         "(denser ladder, the same work per GPU at every N); 'extend' = the default spacing carried on "
+                         "to T x N rungs (round 1: the added rungs sample the prior and are mostly never evaluated)")
     args = ap.parse_args()
+    global LADDER_MODE
+    LADDER_MODE = args.ladder
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -678,9 +689,12 @@ def main():
            "config": {"workload": w["desc"], "name": args.workload, "n_points": wl.n, "n_keplerians": w["kplan"],
                       "n_instruments": w["nins"], "ndim": ndim, "ntemps": T, "nwalkers": W,
                       "parallelism": f"temperature ladder sharded over {world} GPU(s)", "solver": args.solver,
-                      "ladder": f"{T} rungs, geometric between beta = 1 and {float(samp_betas0[-1]):.3g} (the range of "
-                                f"the config's {w.get('ladder_T', w['T'])}-rung ladder at every N: more GPUs = a denser "
-                                "ladder, the same work per GPU), adapted on the device every sweep",
+                      "ladder": (f"{T} rungs, geometric between beta = 1 and {float(samp_betas0[-1]):.3g} (the range of "
+                                 f"the config's {w.get('ladder_T', w['T'])}-rung ladder at every N: more GPUs = a denser "
+                                 "ladder, the same work per GPU), adapted on the device every sweep"
+                                 if args.ladder == "range" else
+                                 f"{T} rungs with the default spacing (coldest 1, hottest {float(samp_betas0[-1]):.3g}), "
+                                 "adapted on the device every sweep"),
                       "exchange": args.exchange if world > 1 else None,
                       "l2": "each step's inputs (draws 2.4 MB/step + state 18 MB) differ per step; the 280 KB "
                             "data set is L2-resident by design (re-read by every CTA)"},
