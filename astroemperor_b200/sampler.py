@@ -592,7 +592,7 @@ class PTSampler:
         torch.cuda.synchronize(self.dev)
         lay = {"k": k, "nsteps": nsteps, "total": total, "host": [], "dev": [], "np": [], "out": [], "gen": [],
                "used": [None, None], "i": 0, "blocks": {}}
-        L, dh = _lib.lib(), (self.streams.handle() if self.streams.native else None)
+        dh = self.streams.handle() if self.streams.native else None
         ts = np.arange(T, dtype=np.int32)
         rs = np.array([T + j for j in range(T - 1)], dtype=np.int32)
         lay["keep"] = (ts, rs)
@@ -623,9 +623,10 @@ class PTSampler:
         return lay
 
     def _chunk_draw(self, lay, i, n):
-        """Draw the next n sweeps into pinned block i: the generator sweep by sweep (the streams advance exactly
-        as in the sweep-by-sweep path), then ONE vectorised pass for the stretch factors and the logs (NumPy's
-        on every path: thresholds are the same bits for the device and the oracle)."""
+        """Draw the next n sweeps into pinned block i: ONE call of the native generator (every stream draws its n
+        sweeps in order, so the streams advance exactly as in the sweep-by-sweep path), then ONE vectorised pass for
+        the stretch factors and the logs (NumPy's on every path: thresholds are the same bits for the device and
+        the oracle)."""
         t0 = _time.perf_counter()
         v = lay["np"][i]
         if self.streams.native:
@@ -751,7 +752,7 @@ class PTSampler:
         self._chunk_draw(lay, i, k)
         return lay["host"][i].to(self.dev, non_blocking=False)
 
-    def run_chunk_resident(self, packed, nsteps=1):
+    def run_chunk_resident(self, packed):
         """Device-to-device copy of a `draw_chunk_resident` block into the next device block, then its k sweeps
         from one graph launch (no host-to-device traffic)."""
         lay = self._clay
