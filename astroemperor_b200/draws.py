@@ -207,10 +207,30 @@ def initial_positions(rng: np.random.RandomState, spec, ntemps: int, nwalkers: i
     return pos
 
 
+# Geometric spacing of the default ladder per dimension (index ndim - 1): the table of emcee v2's PTSampler /
+# ptemcee `default_beta_ladder` (Vousden, Farr & Mandel 2016: the spacing that gives ~25 % swap acceptance for a
+# unimodal Gaussian of that dimension).  reddemcee 0.9 uses it unchanged — the reference's own notebooks show it:
+# tests/00_mini_test.ipynb / 01_51peg_basic.ipynb print hottest rungs 5.057e-10 = 7**-11 and 2.478e-08 = 7**-9 for the
+# 2-parameter model with 12 and 10 temperatures (table[1] = 7), tests/quickstart.ipynb prints [1.0, 0.4002] for the
+# 7-parameter model with 2 temperatures (1 / table[6] = 0.40019): tests/test_host_logic.py pins both.
+_TSTEP = np.array([
+    25.2741, 7., 4.47502, 3.5236, 3.0232, 2.71225, 2.49879, 2.34226, 2.22198, 2.12628,
+    2.04807, 1.98276, 1.92728, 1.87946, 1.83774, 1.80096, 1.76826, 1.73895, 1.7125, 1.68849,
+    1.66657, 1.64647, 1.62795, 1.61083, 1.59494, 1.58014, 1.56632, 1.55338, 1.54123, 1.5298,
+    1.51901, 1.50881, 1.49916, 1.49, 1.4813, 1.47302, 1.46512, 1.45759, 1.45039, 1.4435,
+    1.4369, 1.43056, 1.42448, 1.41864, 1.41302, 1.40761, 1.40239, 1.39736, 1.3925, 1.38781,
+    1.38327, 1.37888, 1.37463, 1.37051, 1.36652, 1.36265, 1.35889, 1.35524, 1.3517, 1.34825,
+    1.3449, 1.34164, 1.33847, 1.33538, 1.33236, 1.32943, 1.32656, 1.32377, 1.32104, 1.31838,
+    1.31578, 1.31325, 1.31076, 1.30834, 1.30596, 1.30364, 1.30137, 1.29915, 1.29697, 1.29484,
+    1.29275, 1.29071, 1.2887, 1.28673, 1.2848, 1.28291, 1.28106, 1.27923, 1.27745, 1.27569,
+    1.27397, 1.27227, 1.27061, 1.26898, 1.26737, 1.26579, 1.26424, 1.26271, 1.26121, 1.25973])
+
+
 def default_betas(ndim: int, ntemps: int) -> np.ndarray:
-    """Geometric ladder with the emcee-v2 / ptemcee `default_beta_ladder` spacing (the table for
-    ndim <= 100 is fitted by the large-ndim law below to < 3 % for ndim >= 3; Tmax = inf is not
-    used: the hottest chain keeps a finite temperature).  reddemcee's own default is not
-    recoverable offline; pass `betas=` for an exact ladder."""
-    tstep = 1.0 + 2.0 * np.sqrt(np.log(4.0)) / np.sqrt(ndim)
+    """The default ladder `betas = tstep**-arange(ntemps)` of ptemcee's `default_beta_ladder(ndim, ntemps)` (Tmax not
+    given: the hottest chain keeps a finite temperature), which reddemcee 0.9 uses when EMPEROR passes `betas=None`
+    (`emp.py:2372`): tstep from the table above for ndim <= 100, `1 + 2 sqrt(ln 4 / ndim)` beyond it."""
+    if ndim < 1:
+        raise ValueError("ndim must be >= 1")
+    tstep = _TSTEP[ndim - 1] if ndim <= len(_TSTEP) else 1.0 + 2.0 * np.sqrt(np.log(4.0)) / np.sqrt(ndim)
     return tstep ** (-np.arange(ntemps, dtype=np.float64))

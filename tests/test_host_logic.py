@@ -207,6 +207,22 @@ def test_swap_sweep_is_W_independent_chains(T, W, scale):
     assert 0 < n_ref.sum() < (T - 1) * W or T == 2   # both outcomes occur
 
 
+def test_default_ladder_matches_the_ladders_the_reference_notebooks_print():
+    """reddemcee's default ladder (EMPEROR passes betas=None, emp.py:2372) is ptemcee's default_beta_ladder.  The
+    reference's notebooks print ladders whose FIXED ends pin the table: 'Beta Detail' ends in 5.057e-10 for the
+    2-parameter model with 12 temperatures (tests/00_mini_test.ipynb) and in 2.478e-08 with 10
+    (tests/01_51peg_basic.ipynb) — the hottest rung is not adapted —, and tests/quickstart.ipynb prints
+    [1.0, 0.4002] for the 7-parameter model with 2 temperatures (no adaptation with fewer than 3)."""
+    from astroemperor_b200.draws import _TSTEP, default_betas
+    assert float("%.4g" % default_betas(2, 12)[-1]) == 5.057e-10
+    assert float("%.4g" % default_betas(2, 10)[-1]) == 2.478e-08
+    assert [float("%.4g" % b) for b in default_betas(7, 2)] == [1.0, 0.4002]
+    assert len(_TSTEP) == 100 and np.all(np.diff(_TSTEP) < 0) and _TSTEP[-1] > 1.0
+    big = default_betas(400, 5)   # beyond the table: 1 + 2 sqrt(ln 4 / ndim)
+    assert np.isclose(big[1], 1.0 / (1.0 + 2.0 * np.sqrt(np.log(4.0)) / 20.0))
+    assert default_betas(35, 32)[0] == 1.0 and np.all(np.diff(default_betas(35, 32)) < 0)
+
+
 def test_initial_positions_follow_set_init():
     from astroemperor_b200.draws import initial_positions
     g, spec = load_golden("mini_51peg_k1_p1")
